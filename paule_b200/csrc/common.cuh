@@ -1,0 +1,57 @@
+// Shared helpers for the paule_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/paule_b200.h"
+
+namespace paule {
+
+extern thread_local char g_last_cuda_error[256];
+
+inline int record_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return PAULE_OK;
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+  return PAULE_ERR_CUDA;
+}
+
+#define PAULE_CUDA(call)                                       \
+  do {                                                         \
+    int _rc = ::paule::record_cuda((call), #call);             \
+    if (_rc != PAULE_OK) return _rc;                           \
+  } while (0)
+
+#define PAULE_LAUNCH_CHECK(name)                               \
+  do {                                                         \
+    int _rc = ::paule::record_cuda(cudaGetLastError(), name);  \
+    if (_rc != PAULE_OK) return _rc;                           \
+  } while (0)
+
+#define PAULE_TRY(expr)                                        \
+  do {                                                         \
+    int _rc = (expr);                                          \
+    if (_rc != PAULE_OK) return _rc;                           \
+  } while (0)
+
+#define PAULE_REQUIRE(cond)                                    \
+  do {                                                         \
+    if (!(cond)) return PAULE_ERR_ARG;                         \
+  } while (0)
+
+inline cudaStream_t as_stream(paule_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// paule/paule.py:592-597
+constexpr float kMelWeight = 5.0f;
+constexpr float kVelWeight = 80.0f;
+constexpr float kJerkWeight = 400.0f;
+constexpr float kSemWeight = 10.0f;
+constexpr float kLocalLinearWeight = 100000.0f;
+
+int sm_count();
+
+}  // namespace paule

@@ -1,0 +1,399 @@
+// Fused loss / analytic-gradient / Adam kernels of the planning loop (HBM-bound, fp32).
+//
+// Reference arithmetic being replaced (all /root/reference):
+//   criterion          paule/paule.py:647-662 (+ :705-717 acoustic, :760-773 semvec), weights :592-597
+//   RMSE (eps = 0)     paule/util.py:570-572, instance paule/paule.py:68
+//   5-point stencil    paule/util.py:600, nested 1x/2x/3x in get_vel_acc_jerk :634-636
+//   local_linear       paule/util.py:613-614
+//   Adam + clamp       paule/paule.py:797,1199-1211; torch/optim/adam.py::_single_tensor_adam
+//
+// Layout: time-major [T,B,C]; a word's frames are B*C floats apart, so every stencil tap of a warp
+// is a coalesced row segment.
+#include "common.cuh"
+#include "plan_internal.cuh"
+
+namespace paule {
+
+constexpr int kTileT = 64;   // output frames per CTA of the smoothness kernel
+constexpr int kHalo = 12;    // three nested 5-point stencils reach 6 frames, their adjoints another 6
+constexpr int kMaxC = 32;    // channels (30 in PAULE)
+
+// d5(v)[i] = (-v[i+4] + 8 v[i+3] - 8 v[i+1] + v[i]) / 12   -- same operation order as util.py:600, no FMA
+// contraction so that the value matches the reference's separately rounded tensor ops.
+__device__ __forceinline__ float d5(float v0, float v1, float v3, float v4) {
+  float s = __fadd_rn(-v4, __fmul_rn(8.0f, v3));
+  s = __fsub_rn(s, __fmul_rn(8.0f, v1));
+  s = __fadd_rn(s, v0);
+  return __fdiv_rn(s, 12.0f);
+}
+
+// Smoothness terms of one (word, time tile): vel/jerk/local-linear partial sums and their gradient.
+// Buffers in shared memory hold frames [t0-12, t0+kTileT+12) of the word, all C channels.
+//   x -> vel (valid: T-4) -> acc (T-8) -> jerk (T-12);  r3 = s_j*jerk; r2 = D^T r3; r1 = D^T r2 + s_v*vel; g = D^T r1 + ll part
+__global__ void __launch_bounds__(256)
+smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth, float* __restrict__ partial,
+                    int64_t T, int64_t B, int64_t C, int n_tiles) {
+  constexpr int W = kTileT + 2 * kHalo;  // 88 frames
+  __shared__ float sx[W * kMaxC];
+  __shared__ float sa[W * kMaxC];
+  __shared__ float sb[W * kMaxC];
+  __shared__ float sred[3][8];
+  const int64_t b = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * kTileT;
+  const int tid = threadIdx.x;
+  const int n = W * (int)C;
+  const float sv = 2.0f * kVelWeight / (float)((T - 4) * C);
+  const float sj = 2.0f * kJerkWeight / (float)((T - 12) * C);
+  const float sl = 2.0f * kLocalLinearWeight / (float)((T - 2) * C);
+
+  // frame index f in [0,W) <-> global t = t0 - kHalo + f
+  for (int e = tid; e < n; e += 256) {
+    const int f = e / (int)C, c = e % (int)C;
+    const int64_t t = t0 - kHalo + f;
+    sx[e] = (t >= 0 && t < T) ? __ldg(cp + (t * B + b) * C + c) : 0.f;
+  }
+  __syncthreads();
+  // vel[i] uses x[i..i+4], i in [0, T-4): stored at frame of global index i  -> sa
+  for (int e = tid; e < n; e += 256) {
+    const int f = e / (int)C, c = e % (int)C;
+    const int64_t i = t0 - kHalo + f;
+    float v = 0.f;
+    if (i >= 0 && i < T - 4 && f + 4 < W)
+      v = d5(sx[e], sx[e + (int)C], sx[e + 3 * (int)C], sx[e + 4 * (int)C]);
+    sa[e] = v;
+  }
+  __syncthreads();
+  // local partial sums of vel^2 and ll^2 over the frames this CTA owns
+  float pv = 0.f, pj = 0.f, pl = 0.f;
+  for (int e = tid; e < kTileT * (int)C; e += 256) {
+    const int f = kHalo + e / (int)C, c = e % (int)C;
+    const int64_t i = t0 + e / (int)C;
+    const int idx = f * (int)C + c;
+    if (i < T - 4) pv += sa[idx] * sa[idx];
+    if (i >= 1 && i < T - 1) {
+      // ll[i-1] = (2 x[i] - x[i-1] - x[i+1]) / 2   (util.py:614)
+      const float l = __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[idx]), sx[idx - (int)C]), sx[idx + (int)C]), 2.0f);
+      pl += l * l;
+    }
+  }
+  // acc[i] = d5(vel)[i], i in [0, T-8) -> sb
+  for (int e = tid; e < n; e += 256) {
+    const int f = e / (int)C;
+    const int64_t i = t0 - kHalo + f;
+    float v = 0.f;
+    if (i >= 0 && i < T - 8 && f + 4 < W)
+      v = d5(sa[e], sa[e + (int)C], sa[e + 3 * (int)C], sa[e + 4 * (int)C]);
+    sb[e] = v;
+  }
+  __syncthreads();
+  // jerk[i] = d5(acc)[i], i in [0, T-12); r3 = sj * jerk -> kept in registers then written over sb (after sync)
+  float r3loc[(W * kMaxC + 255) / 256];
+  {
+    int q = 0;
+    for (int e = tid; e < n; e += 256, ++q) {
+      const int f = e / (int)C;
+      const int64_t i = t0 - kHalo + f;
+      float v = 0.f;
+      if (i >= 0 && i < T - 12 && f + 4 < W) {
+        v = d5(sb[e], sb[e + (int)C], sb[e + 3 * (int)C], sb[e + 4 * (int)C]);
+        if (f >= kHalo && f < kHalo + kTileT) pj += v * v;
+      }
+      r3loc[q] = sj * v;
+    }
+  }
+  __syncthreads();
+  {
+    int q = 0;
+    for (int e = tid; e < n; e += 256, ++q) sb[e] = r3loc[q];
+  }
+  __syncthreads();
+  // adjoint of d5: (D^T r)[k] = (r[k] - 8 r[k-1] + 8 r[k-3] - r[k-4]) / 12  with r = 0 outside its range.
+  // r2 = D^T r3 (index range T-8), accumulate into registers, then r1 = D^T r2 + sv*vel (range T-4), g = D^T r1.
+  auto adj = [&](const float* r, int e, int f) -> float {
+    const int c1 = (int)C;
+    const float r0 = r[e];
+    const float r1 = (f >= 1) ? r[e - c1] : 0.f;
+    const float r3 = (f >= 3) ? r[e - 3 * c1] : 0.f;
+    const float r4 = (f >= 4) ? r[e - 4 * c1] : 0.f;
+    return (r0 - 8.0f * r1 + 8.0f * r3 - r4) * (1.0f / 12.0f);
+  };
+  {
+    int q = 0;
+    for (int e = tid; e < n; e += 256, ++q) {
+      const int f = e / (int)C;
+      const int64_t k = t0 - kHalo + f;
+      r3loc[q] = (k >= 0 && k < T - 8) ? adj(sb, e, f) : 0.f;  // r2
+    }
+  }
+  __syncthreads();
+  {
+    int q = 0;
+    for (int e = tid; e < n; e += 256, ++q) sb[e] = r3loc[q];  // sb = r2
+  }
+  __syncthreads();
+  {
+    int q = 0;
+    for (int e = tid; e < n; e += 256, ++q) {
+      const int f = e / (int)C;
+      const int64_t k = t0 - kHalo + f;
+      r3loc[q] = (k >= 0 && k < T - 4) ? adj(sb, e, f) + sv * sa[e] : 0.f;  // r1 = D^T r2 + sv * vel
+    }
+  }
+  __syncthreads();
+  {
+    int q = 0;
+    for (int e = tid; e < n; e += 256, ++q) sa[e] = r3loc[q];  // sa = r1
+  }
+  __syncthreads();
+  for (int e = tid; e < kTileT * (int)C; e += 256) {
+    const int f = kHalo + e / (int)C, c = e % (int)C;
+    const int64_t t = t0 + e / (int)C;
+    if (t >= T) continue;
+    const int idx = f * (int)C + c;
+    float g = adj(sa, idx, f);
+    // local-linear adjoint: ll[i] = x[i+1] - (x[i] + x[i+2])/2, i in [0,T-2); g_ll[t] = sl*(ll[t-1] - ll[t]/2 - ll[t-2]/2)
+    auto ll_at = [&](int64_t i, int fi) -> float {  // ll with centre frame fi (global centre i+1)
+      if (i < 0 || i >= T - 2) return 0.f;
+      const int id = fi * (int)C + c;
+      return __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[id]), sx[id - (int)C]), sx[id + (int)C]), 2.0f);
+    };
+    const float lc = ll_at(t - 1, f), lm = ll_at(t - 2, f - 1), lp = ll_at(t, f + 1);
+    g += sl * (lc - 0.5f * lm - 0.5f * lp);
+    dcp_smooth[(t * B + b) * C + c] = g;
+  }
+  // block reduce the three partial sums (fixed order -> deterministic)
+  for (int o = 16; o > 0; o >>= 1) {
+    pv += __shfl_down_sync(0xffffffffu, pv, o);
+    pj += __shfl_down_sync(0xffffffffu, pj, o);
+    pl += __shfl_down_sync(0xffffffffu, pl, o);
+  }
+  if ((tid & 31) == 0) { sred[0][tid >> 5] = pv; sred[1][tid >> 5] = pj; sred[2][tid >> 5] = pl; }
+  __syncthreads();
+  if (tid < 3) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += sred[tid][w];
+    partial[(b * n_tiles + blockIdx.x) * 3 + tid] = s;
+  }
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < 8; ++w) s += sh[w];
+  return s;
+}
+
+// One CTA per word: RMSE terms, the six logged loss terms, dmel and dsv.
+__global__ void __launch_bounds__(256)
+word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, const float* __restrict__ sv,
+                 const float* __restrict__ tsv, const float* __restrict__ partial, int n_tiles,
+                 float* __restrict__ terms, const int32_t* __restrict__ step_count, int slots,
+                 float* __restrict__ dmel, float* __restrict__ dsv, int64_t T, int64_t Tm,
+                 int64_t B, int64_t C, int64_t Cm, int64_t S, int objective) {
+  __shared__ float sh[8];
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool use_mel = objective != PAULE_OBJ_SEMVEC, use_sem = objective != PAULE_OBJ_ACOUSTIC;
+  float sm = 0.f;
+  const int64_t nm = Tm * Cm;
+  for (int64_t e = tid; e < nm; e += 256) {
+    const int64_t t = e / Cm, c = e % Cm;
+    const int64_t off = (t * B + b) * Cm + c;
+    const float d = mel[off] - tmel[off];
+    sm += d * d;
+  }
+  sm = block_sum_256(sm, sh);
+  float ss = 0.f;
+  if (sv != nullptr)
+    for (int64_t e = tid; e < S; e += 256) {
+      const float d = sv[b * S + e] - tsv[b * S + e];
+      ss += d * d;
+    }
+  ss = block_sum_256(ss, sh);
+  float pv = 0.f, pj = 0.f, pl = 0.f;
+  for (int i = 0; i < n_tiles; ++i) {  // fixed order
+    pv += partial[(b * n_tiles + i) * 3 + 0];
+    pj += partial[(b * n_tiles + i) * 3 + 1];
+    pl += partial[(b * n_tiles + i) * 3 + 2];
+  }
+  const float rmse_m = sqrtf(sm / (float)nm);
+  const float rmse_s = sqrtf(ss / (float)S);
+  const float l_mel = kMelWeight * rmse_m;
+  const float l_sem = (sv != nullptr) ? kSemWeight * rmse_s : 0.f;
+  const float l_vel = kVelWeight * (pv / (float)((T - 4) * C));
+  const float l_jerk = kJerkWeight * (pj / (float)((T - 12) * C));
+  const float l_ll = kLocalLinearWeight * (pl / (float)((T - 2) * C));
+  if (tid == 0) {
+    float total;
+    if (objective == PAULE_OBJ_ACOUSTIC_SEMVEC) total = l_mel + l_vel + l_jerk + l_sem + l_ll;  // paule.py:660
+    else if (objective == PAULE_OBJ_ACOUSTIC) total = l_mel + l_vel + l_jerk + l_ll;            // :715
+    else total = l_vel + l_jerk + l_sem + l_ll;                                                  // :771
+    const int64_t slot = step_count ? (int64_t)((*step_count - 1) % slots + slots) % slots : 0;
+    float* o = terms + (slot * B + b) * 6;
+    o[0] = total; o[1] = l_mel; o[2] = l_sem; o[3] = l_vel; o[4] = l_jerk; o[5] = l_ll;
+  }
+  // d(w*sqrt(mean(e^2)))/de = w*e/(N*rmse); eps = 0 -> NaN at zero error, as in the reference (paule.py:68)
+  const float gm = use_mel ? kMelWeight / ((float)nm * rmse_m) : 0.f;
+  for (int64_t e = tid; e < nm; e += 256) {
+    const int64_t t = e / Cm, c = e % Cm;
+    const int64_t off = (t * B + b) * Cm + c;
+    dmel[off] = use_mel ? gm * (mel[off] - tmel[off]) : 0.f;
+  }
+  if (dsv != nullptr) {
+    const float gs = (use_sem && sv != nullptr) ? kSemWeight / ((float)S * rmse_s) : 0.f;
+    for (int64_t e = tid; e < S; e += 256)
+      dsv[b * S + e] = (use_sem && sv != nullptr) ? gs * (sv[b * S + e] - tsv[b * S + e]) : 0.f;
+  }
+}
+
+__global__ void step_tick_kernel(int32_t* step_count) { *step_count += 1; }
+
+// torch/optim/adam.py::_single_tensor_adam (foreach/fused variants are arithmetic-equivalent):
+//   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); x.addcdiv_(m, sqrt(v)/sqrt(bc2) + eps, -lr/bc1)
+__global__ void __launch_bounds__(256)
+adam_clamp_kernel(float* __restrict__ cp, const float* __restrict__ g_a, const float* __restrict__ g_b,
+                  float* __restrict__ m, float* __restrict__ v, const int32_t* __restrict__ step_count, float lr,
+                  float beta1, float beta2, float eps, float clampv, int smiling, const float* __restrict__ past_cp,
+                  int64_t past_n, float* __restrict__ grad_out, int64_t n, int C) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const int step = *step_count;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    s_step_size = (float)((double)lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e0 < n; e0 += stride) {
+    float x[4], g[4], mm[4], vv[4];
+    const bool full = (e0 + 4 <= n);
+    if (full) {
+      const float4 X = *reinterpret_cast<const float4*>(cp + e0);
+      const float4 G = *reinterpret_cast<const float4*>(g_a + e0);
+      const float4 M = *reinterpret_cast<const float4*>(m + e0);
+      const float4 V = *reinterpret_cast<const float4*>(v + e0);
+      x[0] = X.x; x[1] = X.y; x[2] = X.z; x[3] = X.w;
+      g[0] = G.x; g[1] = G.y; g[2] = G.z; g[3] = G.w;
+      mm[0] = M.x; mm[1] = M.y; mm[2] = M.z; mm[3] = M.w;
+      vv[0] = V.x; vv[1] = V.y; vv[2] = V.z; vv[3] = V.w;
+      if (g_b) {
+        const float4 G2 = *reinterpret_cast<const float4*>(g_b + e0);
+        g[0] += G2.x; g[1] += G2.y; g[2] += G2.z; g[3] += G2.w;
+      }
+    } else {
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = e0 + i < n;
+        x[i] = ok ? cp[e0 + i] : 0.f;
+        g[i] = ok ? g_a[e0 + i] + (g_b ? g_b[e0 + i] : 0.f) : 0.f;
+        mm[i] = ok ? m[e0 + i] : 0.f;
+        vv[i] = ok ? v[e0 + i] : 0.f;
+      }
+    }
+    if (grad_out != nullptr)
+      for (int i = 0; i < 4 && e0 + i < n; ++i) grad_out[e0 + i] = g[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mm[i] = mm[i] + w1 * (g[i] - mm[i]);
+      vv[i] = vv[i] * beta2 + (w2 * g[i]) * g[i];
+      const float denom = sqrtf(vv[i]) / bc2_sqrt + eps;
+      float xn = x[i] - step_size * (mm[i] / denom);
+      xn = fminf(fmaxf(xn, -clampv), clampv);
+      const int64_t e = e0 + i;
+      if (smiling) {
+        const int c = (int)(e % C);
+        if (c == 4) xn = -1.0f;   // "LP"  paule.py:1207
+        if (c == 1) xn = 1.0f;    // "HY"  paule.py:1208
+      }
+      if (past_cp != nullptr && e < past_n) xn = past_cp[e];
+      x[i] = xn;
+    }
+    if (full) {
+      *reinterpret_cast<float4*>(cp + e0) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(m + e0) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + e0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+      for (int i = 0; i < 4 && e0 + i < n; ++i) { cp[e0 + i] = x[i]; m[e0 + i] = mm[i]; v[e0 + i] = vv[i]; }
+    }
+  }
+}
+
+}  // namespace paule
+
+using namespace paule;
+
+extern "C" size_t paule_plan_loss_scratch_floats(int64_t T, int64_t B) {
+  return (size_t)(B * ceil_div(T, (int64_t)kTileT) * 3);
+}
+
+namespace paule {
+
+int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const float* tsv, const float* cp,
+                     float* terms, const int32_t* step_count, int slots, float* dmel, float* dsv, float* dcp_smooth,
+                     float* scratch, int64_t T, int64_t Tm, int64_t B, int64_t C, int64_t Cm, int64_t S,
+                     int objective, paule_stream_t stream) {
+  PAULE_REQUIRE(mel && tmel && cp && terms && dmel && dcp_smooth && scratch && slots >= 1);
+  PAULE_REQUIRE((sv == nullptr) == (tsv == nullptr));
+  PAULE_REQUIRE(T >= 13 && Tm >= 1 && B >= 1 && C >= 1 && C <= kMaxC && Cm >= 1 && S >= 1);
+  PAULE_REQUIRE(objective >= 0 && objective <= 2);
+  if (objective != PAULE_OBJ_ACOUSTIC) PAULE_REQUIRE(sv && tsv && dsv);
+  const int n_tiles = (int)ceil_div(T, (int64_t)kTileT);
+  smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, B, C,
+                                                                                 n_tiles);
+  PAULE_LAUNCH_CHECK("smooth_terms_kernel");
+  word_loss_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(mel, tmel, sv, tsv, scratch, n_tiles, terms,
+                                                               step_count, slots, dmel, dsv, T, Tm, B, C, Cm, S,
+                                                               objective);
+  PAULE_LAUNCH_CHECK("word_loss_kernel");
+  return PAULE_OK;
+}
+
+int adam_clamp_logged(float* cp, const float* g_a, const float* g_b, float* m, float* v, const int32_t* step_count,
+                      float lr, float beta1, float beta2, float eps, float clamp, int smiling, const float* past_cp,
+                      int64_t past_T, float* grad_out, int64_t T, int64_t B, int64_t C, paule_stream_t stream) {
+  PAULE_REQUIRE(cp && g_a && m && v && step_count && T >= 0 && B > 0 && C > 0);
+  PAULE_REQUIRE(past_T >= 0 && past_T <= T && (past_T == 0 || past_cp));
+  PAULE_REQUIRE(!smiling || C > 4);
+  const int64_t n = T * B * C;
+  if (n == 0) return PAULE_OK;
+  PAULE_REQUIRE((reinterpret_cast<uintptr_t>(cp) | reinterpret_cast<uintptr_t>(g_a) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g_b)) % 16 == 0);
+  int64_t blocks = ceil_div(n, (int64_t)256 * 4);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adam_clamp_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cp, g_a, g_b, m, v, step_count, lr, beta1, beta2,
+                                                                     eps, clamp, smiling, past_T ? past_cp : nullptr,
+                                                                     past_T * B * C, grad_out, n, (int)C);
+  PAULE_LAUNCH_CHECK("adam_clamp_kernel");
+  return PAULE_OK;
+}
+
+}  // namespace paule
+
+extern "C" int paule_plan_loss_f32(const float* mel, const float* tmel, const float* sv, const float* tsv,
+                                   const float* cp, float* terms, float* dmel, float* dsv, float* dcp_smooth,
+                                   float* scratch, int64_t T, int64_t Tm, int64_t B, int64_t C, int64_t Cm,
+                                   int64_t S, int objective, paule_stream_t stream) {
+  return plan_loss_logged(mel, tmel, sv, tsv, cp, terms, nullptr, 1, dmel, dsv, dcp_smooth, scratch, T, Tm, B, C, Cm,
+                          S, objective, stream);
+}
+
+extern "C" int paule_step_tick(int32_t* step_count, paule_stream_t stream) {
+  PAULE_REQUIRE(step_count);
+  step_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_count);
+  PAULE_LAUNCH_CHECK("step_tick_kernel");
+  return PAULE_OK;
+}
+
+extern "C" int paule_adam_clamp_f32(float* cp, const float* g_a, const float* g_b, float* m, float* v,
+                                    const int32_t* step_count, float lr, float beta1, float beta2, float eps,
+                                    float clamp, int smiling, const float* past_cp, int64_t past_T, int64_t T,
+                                    int64_t B, int64_t C, paule_stream_t stream) {
+  return adam_clamp_logged(cp, g_a, g_b, m, v, step_count, lr, beta1, beta2, eps, clamp, smiling, past_cp, past_T,
+                           nullptr, T, B, C, stream);
+}

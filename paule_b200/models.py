@@ -1,0 +1,223 @@
+"""B200-native counterparts of the reference's hot-path models (same names, constructor arguments,
+``forward`` signatures and ``state_dict`` keys as /root/reference/paule/models.py), running on the
+hand-written CUDA kernels of libpaule_b200.so.
+
+* ``ForwardModel``                         models.py:326-356   cp [B,T,30] -> log-mel [B,T//2,60]
+* ``EmbeddingModel``                       models.py:413-448   log-mel [B,Tm,60], lens -> semvec [B,300]
+* ``InverseModelMelTimeSmoothResidual``    models.py:177-247   log-mel [B,Tm,60] -> cp [B,2Tm,30] (no grad)
+* aliases named by BASELINE.json: ``InverseModel``, ``MelEmbeddingModel``
+
+The modules hold their parameters in ``torch.nn.LSTM`` / ``Linear`` / ``Conv1d`` containers purely so
+that initialisation and ``state_dict`` naming are identical to the reference (reference checkpoints
+load unchanged); the containers' own ``forward`` is never called.  Arithmetic is fp32 (BASELINE.json
+configs[0]); float64 parameters (the reference's shipped dtype) are converted when packed.
+``forward`` is differentiable with respect to its *input* (what planning needs, paule/paule.py:1052);
+parameters receive no gradient.  CPU tensors raise: there is no fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+
+
+def _versions(params: Sequence[torch.Tensor]) -> Tuple:
+    return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
+
+
+class _PackedLSTM:
+    """Caches the device operand pack of an nn.LSTM container; repacks when a parameter changes."""
+
+    def __init__(self, lstm: nn.LSTM):
+        self.lstm = lstm
+        self._key = None
+        self.layers: List[ops.LstmWeights] = []
+
+    def get(self) -> List[ops.LstmWeights]:
+        params = list(self.lstm.parameters())
+        key = _versions(params)
+        if key != self._key:
+            self.layers = []
+            for k in range(self.lstm.num_layers):
+                self.layers.append(ops.LstmWeights(getattr(self.lstm, f"weight_ih_l{k}"),
+                                                   getattr(self.lstm, f"weight_hh_l{k}"),
+                                                   getattr(self.lstm, f"bias_ih_l{k}"),
+                                                   getattr(self.lstm, f"bias_hh_l{k}")))
+            self._key = key
+        return self.layers
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _check_input(x: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise _lib.PauleB200Error(f"{name}: expected a CUDA tensor; paule_b200 has no CPU fallback")
+    _lib.require_device()
+    return x.float().contiguous()
+
+
+def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights]) -> torch.Tensor:
+    """x [B,T,I] batch-first -> top layer's h, TIME-MAJOR [T,B,H]."""
+    h = x
+    for k, L in enumerate(layers):
+        h, _, _ = ops.lstm_layer_fwd(h, k == 0, L.w_ih, L.w_hh, L.bias)
+    return h
+
+
+class ForwardModel(nn.Module):
+    """Predictive forward model, cp -> log-mel (reference: paule/models.py:326-356)."""
+
+    def __init__(self, input_size=30, output_size=60, hidden_size=180, num_lstm_layers=4, apply_half_sequence=True):
+        super().__init__()
+        self.apply_half_sequence = apply_half_sequence
+        if self.apply_half_sequence:
+            self.half_sequence = nn.AvgPool1d(2, stride=2)   # parameter-free; kept for attribute parity
+        self.lstm = nn.LSTM(input_size, hidden_size, num_layers=num_lstm_layers, batch_first=True)
+        self.post_linear = nn.Linear(hidden_size, output_size)
+        self._pack = _PackedLSTM(self.lstm)
+
+    def forward(self, x, *args):
+        x = _check_input(x, "ForwardModel.forward(x)")
+        h = lstm_stack(x, self._pack.get())
+        return ops.linear_tm(h, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias),
+                             bool(self.apply_half_sequence), True)
+
+
+class EmbeddingModel(nn.Module):
+    """Mel -> semantic-vector embedder (reference: paule/models.py:413-448)."""
+
+    def __init__(self, input_size=60, output_size=300, hidden_size=720, num_lstm_layers=1,
+                 post_activation=torch.nn.LeakyReLU(), post_upsampling_size=0, dropout=0):
+        super().__init__()
+        self.post_upsampling_size = post_upsampling_size
+        self.lstm = nn.LSTM(input_size, hidden_size, num_layers=num_lstm_layers, batch_first=True, dropout=dropout)
+        if post_upsampling_size > 0:
+            self.post_linear = nn.Linear(hidden_size, post_upsampling_size)
+            self.linear_mapping = nn.Linear(post_upsampling_size, output_size)
+            self.post_activation = post_activation
+        else:
+            self.linear_mapping = nn.Linear(hidden_size, output_size)
+        self._pack = _PackedLSTM(self.lstm)
+
+    def forward(self, x, lens, *args):
+        x = _check_input(x, "EmbeddingModel.forward(x)")
+        if self.training and self.lstm.dropout > 0 and self.lstm.num_layers > 1:
+            raise _lib.PauleB200Error("inter-layer LSTM dropout in training mode is not implemented on the CUDA path "
+                                      "(Paule's embedder uses dropout=0: paule/paule.py:167)")
+        h = lstm_stack(x, self._pack.get())                                  # [T,B,H]
+        B = x.shape[0]
+        idx = torch.as_tensor([int(l) - 1 for l in lens], device=x.device, dtype=torch.long)
+        if idx.numel() != B:
+            raise ValueError(f"lens has {idx.numel()} entries for a batch of {B}")
+        last = h[idx, torch.arange(B, device=x.device)].contiguous()          # models.py:442 (device gather)
+        last = last.unsqueeze(0)                                              # [1,B,H] time-major
+        if self.post_upsampling_size > 0:
+            z = ops.linear_tm(last, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias), False, False)
+            z = self.post_activation(z)
+            out = ops.linear_tm(z.contiguous(), _f32c(self.linear_mapping.weight), _f32c(self.linear_mapping.bias),
+                                False, False)
+        else:
+            out = ops.linear_tm(last, _f32c(self.linear_mapping.weight), _f32c(self.linear_mapping.bias), False, False)
+        return out[0]
+
+
+class _MelChannelConv1D(nn.Module):
+    """Parameter container with the reference's naming (models.py:142-151)."""
+
+    def __init__(self, input_units, filter_size_channel):
+        super().__init__()
+        self.filter_size_channel = filter_size_channel
+        assert input_units % filter_size_channel == 0, 'output_size has to devisible by %d' % filter_size_channel
+        output_units = int(input_units // filter_size_channel)
+        self.ConvLayers = nn.ModuleList(
+            [nn.Conv1d(input_units, output_units, 5, padding=2, groups=output_units) for _ in range(filter_size_channel)])
+
+    def packed(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        # channel c = fs*g + i uses ConvLayers[i].weight[g] on the mel rows c-1, c, c+1 (fs = 3)
+        w = torch.stack([_f32c(l.weight) for l in self.ConvLayers], dim=1)     # [G, fs, 3, 5]
+        b = torch.stack([_f32c(l.bias) for l in self.ConvLayers], dim=1)       # [G, fs]
+        return w.reshape(-1, w.shape[2], 5).contiguous(), b.reshape(-1).contiguous()
+
+
+class _TimeConvResBlock(nn.Module):
+    """Parameter container (models.py:114-129), filter size 5, channelwise."""
+
+    def __init__(self, units):
+        super().__init__()
+        self.band_conv1d_1 = nn.Conv1d(units, units, 5, padding=2, groups=units)
+        self.band_conv1d_2 = nn.Conv1d(units, units, 5, padding=2, groups=units)
+
+
+class InverseModelMelTimeSmoothResidual(nn.Module):
+    """Inverse model, log-mel -> initial cp (reference: paule/models.py:177-247).  Forward only.
+
+    Supported configuration = what ``Paule`` instantiates (paule/paule.py:146): identity activations,
+    ``mel_smooth_filter_size=3``, ``time_filter_size=5``, ``lstm_resid=True``."""
+
+    def __init__(self, input_size=60, output_size=30, hidden_size=180, num_lstm_layers=4, mel_smooth_layers=3,
+                 mel_smooth_filter_size=3, mel_resid_activation=torch.nn.Identity(), resid_blocks=5,
+                 time_filter_size=5, pre_resid_activation=torch.nn.Identity(),
+                 post_resid_activation=torch.nn.Identity(), output_activation=torch.nn.Identity(), lstm_resid=True):
+        super().__init__()
+        for act in (mel_resid_activation, pre_resid_activation, post_resid_activation, output_activation):
+            if not isinstance(act, torch.nn.Identity):
+                raise NotImplementedError("only the Identity activations Paule uses are implemented on the CUDA path")
+        if mel_smooth_filter_size != 3 or time_filter_size != 5 or not lstm_resid:
+            raise NotImplementedError("CUDA path supports mel_smooth_filter_size=3, time_filter_size=5, lstm_resid=True")
+        self.lstm_resid = lstm_resid
+        self.MelBlocks = nn.ModuleList([_MelChannelConv1D(input_size, mel_smooth_filter_size)
+                                        for _ in range(mel_smooth_layers)])
+        self.lstm = nn.LSTM(3 * input_size, hidden_size, num_layers=num_lstm_layers, batch_first=True)
+        self.post_linear = nn.Linear(hidden_size, output_size)
+        self.ResidualConvBlocks = nn.ModuleList([_TimeConvResBlock(output_size) for _ in range(resid_blocks)])
+        if self.lstm_resid and len(self.ResidualConvBlocks) > 0:
+            self.resid_weighting = nn.Conv1d(2 * output_size, output_size, time_filter_size, padding=2,
+                                             groups=output_size)
+        self._pack = _PackedLSTM(self.lstm)
+
+    @torch.no_grad()
+    def forward(self, x, *args):
+        x = _check_input(x, "InverseModel.forward(x)")
+        lib = _lib.load()
+        st = ops._stream()
+        B, Tm, Cm = x.shape
+        cur = x
+        for blk in self.MelBlocks:
+            w, b = blk.packed()
+            nxt = torch.empty_like(cur)
+            _lib.check(lib.paule_melconv_res_f32(cur.data_ptr(), w.data_ptr(), b.data_ptr(), nxt.data_ptr(), B, Tm, Cm,
+                                                 st), "paule_melconv_res_f32")
+            cur = nxt
+        feat = torch.empty((B, Tm, 3 * Cm), device=x.device, dtype=torch.float32)
+        _lib.check(lib.paule_vel_acc_f32(cur.data_ptr(), feat.data_ptr(), B, Tm, Cm, st), "paule_vel_acc_f32")
+        h = lstm_stack(feat, self._pack.get())                                         # [Tm,B,H]
+        y = ops.linear_tm(h, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias), False, True)  # [B,Tm,30]
+        Cc = y.shape[2]
+        nb = len(self.ResidualConvBlocks)
+        out = torch.empty((B, 2 * Tm, Cc), device=x.device, dtype=torch.float32)
+        scratch = torch.empty((3, B, 2 * Tm, Cc), device=x.device, dtype=torch.float32)
+        if nb > 0:
+            res_w = torch.stack([torch.stack((_f32c(r.band_conv1d_1.weight).reshape(Cc, 5),
+                                              _f32c(r.band_conv1d_2.weight).reshape(Cc, 5)))
+                                 for r in self.ResidualConvBlocks]).contiguous()       # [nb,2,C,5]
+            res_b = torch.stack([torch.stack((_f32c(r.band_conv1d_1.bias), _f32c(r.band_conv1d_2.bias)))
+                                 for r in self.ResidualConvBlocks]).contiguous()       # [nb,2,C]
+            mix_w = _f32c(self.resid_weighting.weight)                                 # [C,2,5]: [c][0]=smoothed, [c][1]=raw
+            mix_b = _f32c(self.resid_weighting.bias)
+            _lib.check(lib.paule_upsample_smooth_f32(y.data_ptr(), res_w.data_ptr(), res_b.data_ptr(), nb,
+                                                     mix_w.data_ptr(), mix_b.data_ptr(), out.data_ptr(),
+                                                     scratch.data_ptr(), B, Tm, Cc, st), "paule_upsample_smooth_f32")
+        else:
+            _lib.check(lib.paule_upsample_smooth_f32(y.data_ptr(), None, None, 0, None, None, out.data_ptr(),
+                                                     scratch.data_ptr(), B, Tm, Cc, st), "paule_upsample_smooth_f32")
+        return out
+
+
+# names used by BASELINE.json's north_star
+InverseModel = InverseModelMelTimeSmoothResidual
+MelEmbeddingModel = EmbeddingModel

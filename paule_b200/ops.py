@@ -1,0 +1,329 @@
+"""torch.library custom ops (namespace ``paule_b200::``) over the C ABI of libpaule_b200.so.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every op below passes raw
+device pointers to a hand-written sm_100a kernel.  CPU tensors are rejected -- there is no fallback.
+
+Operator surface:
+  lstm_layer_fwd / lstm_layer_bwd   one LSTM layer over a sequence (time-major), forward and input-gradient BPTT
+  linear_rows                       y = x W^T + b with mapped rows (batch-first <-> time-major, pair pooling)
+  plan_loss, adam_clamp_            criterion + analytic gradients; Adam + clamp (+ smiling / past_cp)
+  plan_step / plan_forward          the fused inner step on a registered PlanContext
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+MATH_FP32, MATH_BF16, MATH_BF16X3 = 0, 1, 2
+OBJECTIVES = {"acoustic_semvec": 0, "acoustic": 1, "semvec": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.PauleB200Error(f"{name} must be a CUDA tensor: paule_b200 has no CPU fallback "
+                                  f"(the CPU restatement lives in oracle/ and is test infrastructure only)")
+    if t.dtype != dtype:
+        raise _lib.PauleB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.PauleB200Error(f"{name} must be contiguous")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# raw wrappers (no autograd)
+# ------------------------------------------------------------------------------------------------
+def linear_rows_(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], M: int,
+                 a_map: Tuple[int, int, int], c_map: Tuple[int, int, int], a_pair: int = 0, accumulate: bool = False,
+                 a_offset: int = 0) -> None:
+    """out[cmap(r), :] (+)= a'[amap(r), :] @ w.T + bias; see paule_linear_f32 in include/paule_b200.h."""
+    lib = _lib.load()
+    N, K = w.shape
+    _lib.check(lib.paule_linear_f32(a.data_ptr() + 4 * a_offset, w.data_ptr(), _p(bias), out.data_ptr(), M, N, K,
+                                    a_map[0], a_map[1], a_map[2], a_pair, c_map[0], c_map[1], c_map[2],
+                                    1 if accumulate else 0, _stream()), "paule_linear_f32")
+
+
+def transpose_btc(x: torch.Tensor) -> torch.Tensor:
+    """[B,T,C] -> [T,B,C] (or back)."""
+    _chk(x, "x")
+    n0, n1, c = x.shape
+    out = torch.empty((n1, n0, c), device=x.device, dtype=x.dtype)
+    _lib.check(_lib.load().paule_transpose_btc(x.data_ptr(), out.data_ptr(), n0, n1, c, _stream()), "paule_transpose_btc")
+    return out
+
+
+class LstmWeights:
+    """Device-side operand pack of one LSTM layer (fp32 originals, transposes, summed bias, tcgen05 image).
+
+    Repacked whenever the source parameters change (continue-learning, paule/paule.py:1372-1377)."""
+
+    def __init__(self, w_ih: torch.Tensor, w_hh: torch.Tensor, b_ih: torch.Tensor, b_hh: torch.Tensor, tc: bool = False):
+        for n, t in (("w_ih", w_ih), ("w_hh", w_hh), ("b_ih", b_ih), ("b_hh", b_hh)):
+            if not t.is_cuda:
+                raise _lib.PauleB200Error(f"LSTM parameter {n} is on {t.device}: move the module to a CUDA device")
+        self.w_ih = w_ih.detach().float().contiguous()
+        self.w_hh = w_hh.detach().float().contiguous()
+        self.w_ih_t = self.w_ih.t().contiguous()
+        self.w_hh_t = self.w_hh.t().contiguous()
+        self.bias = (b_ih.detach().float() + b_hh.detach().float()).contiguous()
+        self.hidden = self.w_hh.shape[1]
+        self.input_size = self.w_ih.shape[1]
+        self.packed: Optional[torch.Tensor] = None
+        if tc:
+            self.pack_tc()
+
+    def pack_tc(self) -> None:
+        lib = _lib.load()
+        nbytes = lib.paule_tc_packed_lstm_bytes(self.hidden, self.input_size)
+        if nbytes == 0:
+            raise _lib.PauleB200Error("tensor-core path is not available for this layer shape")
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.w_hh.device)
+        _lib.check(lib.paule_tc_pack_lstm(self.w_ih.data_ptr(), self.w_hh.data_ptr(), self.packed.data_ptr(),
+                                          self.hidden, self.input_size, _stream()), "paule_tc_pack_lstm")
+
+    def as_struct(self) -> _lib.LstmLayer:
+        return _lib.LstmLayer(self.w_ih.data_ptr(), self.w_hh.data_ptr(), self.w_ih_t.data_ptr(),
+                              self.w_hh_t.data_ptr(), self.bias.data_ptr(), _p(self.packed), self.input_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# custom ops
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("paule_b200::lstm_layer_fwd", mutates_args=())
+def lstm_layer_fwd(x: torch.Tensor, batch_first_in: bool, w_ih: torch.Tensor, w_hh: torch.Tensor,
+                   bias: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x [B,T,I] (batch_first_in) or [T,B,I] -> (h [T,B,H], gates [T,B,4H] activated, c [T,B,H])."""
+    _chk(x, "x"); _chk(w_ih, "w_ih"); _chk(w_hh, "w_hh"); _chk(bias, "bias")
+    if batch_first_in:
+        B, T, I = x.shape
+        a_map = (B, I, T * I)
+    else:
+        T, B, I = x.shape
+        a_map = (1, I, 0)
+    H = w_hh.shape[1]
+    gates = torch.empty((T, B, 4 * H), device=x.device, dtype=torch.float32)
+    h = torch.empty((T, B, H), device=x.device, dtype=torch.float32)
+    c = torch.empty((T, B, H), device=x.device, dtype=torch.float32)
+    if T * B == 0:
+        return h, gates, c
+    linear_rows_(gates, x, w_ih, bias, T * B, a_map, (1, 4 * H, 0))
+    _lib.check(_lib.load().paule_lstm_seq_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), h.data_ptr(), c.data_ptr(),
+                                                  T, B, H, _stream()), "paule_lstm_seq_fwd_f32")
+    return h, gates, c
+
+
+@lstm_layer_fwd.register_fake
+def _(x, batch_first_in, w_ih, w_hh, bias):
+    if batch_first_in:
+        B, T, _ = x.shape
+    else:
+        T, B, _ = x.shape
+    H = w_hh.shape[1]
+    return x.new_empty((T, B, H)), x.new_empty((T, B, 4 * H)), x.new_empty((T, B, H))
+
+
+@torch.library.custom_op("paule_b200::lstm_layer_bwd", mutates_args=())
+def lstm_layer_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, w_ih_t: torch.Tensor,
+                   w_hh_t: torch.Tensor, batch_first_out: bool) -> torch.Tensor:
+    """Input-gradient BPTT: dh [T,B,H] -> dx [T,B,I] (or [B,T,I] if batch_first_out)."""
+    _chk(dh, "dh"); _chk(gates, "gates"); _chk(c, "c")
+    T, B, H = dh.shape
+    I = w_ih_t.shape[0]
+    da = gates.clone()                      # the kernel turns the stash into d(pre-activation) in place
+    scratch = torch.empty((B, H), device=dh.device, dtype=torch.float32)
+    dx = torch.empty((B, T, I) if batch_first_out else (T, B, I), device=dh.device, dtype=torch.float32)
+    if T * B == 0:
+        return dx
+    _lib.check(_lib.load().paule_lstm_seq_bwd_f32(da.data_ptr(), c.data_ptr(), w_hh_t.data_ptr(), dh.data_ptr(), 1,
+                                                  None, scratch.data_ptr(), T, B, H, _stream()),
+               "paule_lstm_seq_bwd_f32")
+    c_map = (B, I, T * I) if batch_first_out else (1, I, 0)
+    linear_rows_(dx, da, w_ih_t, None, T * B, (1, 4 * H, 0), c_map)
+    return dx
+
+
+@lstm_layer_bwd.register_fake
+def _(dh, gates, c, w_ih_t, w_hh_t, batch_first_out):
+    T, B, _ = dh.shape
+    I = w_ih_t.shape[0]
+    return dh.new_empty((B, T, I) if batch_first_out else (T, B, I))
+
+
+def _lstm_layer_setup(ctx, inputs, output):
+    x, batch_first_in, w_ih, w_hh, bias = inputs
+    h, gates, c = output
+    ctx.save_for_backward(gates, c, w_ih, w_hh)
+    ctx.batch_first_in = batch_first_in
+
+
+def _lstm_layer_backward(ctx, dh, dgates, dc):
+    gates, c, w_ih, w_hh = ctx.saved_tensors
+    if dh is None:
+        return None, None, None, None, None
+    dx = lstm_layer_bwd(dh.contiguous(), gates, c, w_ih.t().contiguous(), w_hh.t().contiguous(), ctx.batch_first_in)
+    return dx, None, None, None, None          # input gradients only: weight gradients are not needed to plan
+
+
+lstm_layer_fwd.register_autograd(_lstm_layer_backward, setup_context=_lstm_layer_setup)
+
+
+@torch.library.custom_op("paule_b200::linear_tm", mutates_args=())
+def linear_tm(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, pool_pairs: bool, batch_first_out: bool
+              ) -> torch.Tensor:
+    """x [T,B,K] time-major -> y = pool?(x) W^T + b as [T',B,N] or batch-first [B,T',N]; T' = T//2 if pool_pairs."""
+    _chk(x, "x"); _chk(w, "w"); _chk(bias, "bias")
+    T, B, K = x.shape
+    N = w.shape[0]
+    To = T // 2 if pool_pairs else T
+    y = torch.empty((B, To, N) if batch_first_out else (To, B, N), device=x.device, dtype=torch.float32)
+    if To * B == 0:
+        return y
+    a_map = (B, 2 * B * K, K) if pool_pairs else (1, K, 0)
+    c_map = (B, N, To * N) if batch_first_out else (1, N, 0)
+    linear_rows_(y, x, w, bias, To * B, a_map, c_map, a_pair=B * K if pool_pairs else 0)
+    return y
+
+
+@linear_tm.register_fake
+def _(x, w, bias, pool_pairs, batch_first_out):
+    T, B, _ = x.shape
+    To = T // 2 if pool_pairs else T
+    return x.new_empty((B, To, w.shape[0]) if batch_first_out else (To, B, w.shape[0]))
+
+
+@torch.library.custom_op("paule_b200::linear_tm_bwd", mutates_args=())
+def linear_tm_bwd(dy: torch.Tensor, w_t: torch.Tensor, T: int, pool_pairs: bool, batch_first_out: bool
+                  ) -> torch.Tensor:
+    """Adjoint of linear_tm wrt x: dy ([T',B,N] or [B,T',N]) -> dx [T,B,K]."""
+    _chk(dy, "dy"); _chk(w_t, "w_t")
+    if batch_first_out:
+        B, To, N = dy.shape
+        a_map = (B, N, To * N)
+    else:
+        To, B, N = dy.shape
+        a_map = (1, N, 0)
+    K = w_t.shape[0]
+    if not pool_pairs:
+        dx = torch.empty((T, B, K), device=dy.device, dtype=torch.float32)
+        if T * B:
+            linear_rows_(dx, dy, w_t, None, T * B, a_map, (1, K, 0))
+        return dx
+    dx = torch.zeros((T, B, K), device=dy.device, dtype=torch.float32)
+    if To * B:
+        half = dy * 0.5
+        # frame 2k and 2k+1 both receive 0.5 * dy[k] W
+        linear_rows_(dx, half, w_t, None, To * B, a_map, (B, 2 * B * K, K))
+        linear_rows_(dx[1:], half, w_t, None, To * B, a_map, (B, 2 * B * K, K))
+    return dx
+
+
+@linear_tm_bwd.register_fake
+def _(dy, w_t, T, pool_pairs, batch_first_out):
+    B = dy.shape[0] if batch_first_out else dy.shape[1]
+    return dy.new_empty((T, B, w_t.shape[0]))
+
+
+def _linear_tm_setup(ctx, inputs, output):
+    x, w, bias, pool_pairs, batch_first_out = inputs
+    ctx.save_for_backward(w)
+    ctx.T = x.shape[0]
+    ctx.pool_pairs = pool_pairs
+    ctx.batch_first_out = batch_first_out
+
+
+def _linear_tm_backward(ctx, dy):
+    (w,) = ctx.saved_tensors
+    dx = linear_tm_bwd(dy.contiguous(), w.t().contiguous(), ctx.T, ctx.pool_pairs, ctx.batch_first_out)
+    return dx, None, None, None, None
+
+
+linear_tm.register_autograd(_linear_tm_backward, setup_context=_linear_tm_setup)
+
+
+@torch.library.custom_op("paule_b200::plan_loss", mutates_args=())
+def plan_loss(mel: torch.Tensor, tmel: torch.Tensor, sv: torch.Tensor, tsv: torch.Tensor, cp: torch.Tensor,
+              objective: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Time-major inputs (mel/tmel [Tm,B,60], sv/tsv [B,300], cp [T,B,30]) ->
+    (terms [B,6] = total, mel, semvec, vel, jerk, local_linear; dmel; dsv; dcp_smooth)."""
+    for n, t in (("mel", mel), ("tmel", tmel), ("sv", sv), ("tsv", tsv), ("cp", cp)):
+        _chk(t, n)
+    lib = _lib.load()
+    Tm, B, Cm = mel.shape
+    T, _, Cc = cp.shape
+    S = sv.shape[1]
+    terms = torch.empty((B, 6), device=cp.device, dtype=torch.float32)
+    dmel, dsv, dcp = torch.empty_like(mel), torch.empty_like(sv), torch.empty_like(cp)
+    scratch = torch.empty(lib.paule_plan_loss_scratch_floats(T, B), device=cp.device, dtype=torch.float32)
+    _lib.check(lib.paule_plan_loss_f32(mel.data_ptr(), tmel.data_ptr(), sv.data_ptr(), tsv.data_ptr(), cp.data_ptr(),
+                                       terms.data_ptr(), dmel.data_ptr(), dsv.data_ptr(), dcp.data_ptr(),
+                                       scratch.data_ptr(), T, Tm, B, Cc, Cm, S, objective, _stream()),
+               "paule_plan_loss_f32")
+    return terms, dmel, dsv, dcp
+
+
+@plan_loss.register_fake
+def _(mel, tmel, sv, tsv, cp, objective):
+    return cp.new_empty((mel.shape[1], 6)), torch.empty_like(mel), torch.empty_like(sv), torch.empty_like(cp)
+
+
+@torch.library.custom_op("paule_b200::adam_clamp_", mutates_args=("cp", "m", "v", "step_count"))
+def adam_clamp_(cp: torch.Tensor, g_a: torch.Tensor, g_b: Optional[torch.Tensor], m: torch.Tensor, v: torch.Tensor,
+                step_count: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float, clamp: float,
+                smiling: bool, past_cp: Optional[torch.Tensor]) -> None:
+    """In-place Adam step + clamp on time-major cp [T,B,C]; advances the device step counter first."""
+    for n, t in (("cp", cp), ("g_a", g_a), ("m", m), ("v", v)):
+        _chk(t, n)
+    _chk(step_count, "step_count", torch.int32)
+    lib = _lib.load()
+    T, B, Cc = cp.shape
+    past_T = 0 if past_cp is None else past_cp.shape[0]
+    _lib.check(lib.paule_step_tick(step_count.data_ptr(), _stream()), "paule_step_tick")
+    _lib.check(lib.paule_adam_clamp_f32(cp.data_ptr(), g_a.data_ptr(), _p(g_b), m.data_ptr(), v.data_ptr(),
+                                        step_count.data_ptr(), lr, beta1, beta2, eps, clamp, 1 if smiling else 0,
+                                        _p(past_cp), past_T, T, B, Cc, _stream()), "paule_adam_clamp_f32")
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused planner step
+# ------------------------------------------------------------------------------------------------
+_PLAN_REGISTRY: Dict[int, "object"] = {}
+
+
+def register_plan(ctx_obj) -> int:
+    key = id(ctx_obj)
+    _PLAN_REGISTRY[key] = ctx_obj
+    return key
+
+
+def unregister_plan(key: int) -> None:
+    _PLAN_REGISTRY.pop(key, None)
+
+
+@torch.library.custom_op("paule_b200::plan_step",
+                         mutates_args=("cp", "adam_m", "adam_v", "step_count", "loss_log", "pred_mel", "pred_sv",
+                                       "workspace"))
+def plan_step(cp: torch.Tensor, adam_m: torch.Tensor, adam_v: torch.Tensor, step_count: torch.Tensor,
+              loss_log: torch.Tensor, pred_mel: torch.Tensor, pred_sv: torch.Tensor, workspace: torch.Tensor,
+              plan_key: int) -> None:
+    """One fused inner planning step (paule_plan_step) on the PlanContext registered under plan_key."""
+    ctx_obj = _PLAN_REGISTRY[plan_key]
+    _lib.check(_lib.load().paule_plan_step(ctx_obj.struct_ref(), _stream()), "paule_plan_step")
+
+
+@torch.library.custom_op("paule_b200::plan_forward", mutates_args=("pred_mel", "pred_sv", "workspace"))
+def plan_forward(cp: torch.Tensor, pred_mel: torch.Tensor, pred_sv: torch.Tensor, workspace: torch.Tensor,
+                 plan_key: int) -> None:
+    """no_grad forward of both models on the registered PlanContext (paule/paule.py:822-824, :1460-1464)."""
+    ctx_obj = _PLAN_REGISTRY[plan_key]
+    _lib.check(_lib.load().paule_plan_forward(ctx_obj.struct_ref(), _stream()), "paule_plan_forward")

@@ -1,0 +1,290 @@
+"""``Paule`` -- the reference's planner API (/root/reference/paule/paule.py:92-1551) over the B200 hot path.
+
+Drop-in scope: the gradient-planning inner loop of ``plan_resynth``
+(paule.py:910-1211) and the model calls around it (target semvec :533-535, inverse-model init :551-557,
+initial/final predictions :822-824, :1460-1464), batched over words.  Same keyword arguments, same
+``ValueError``s, same ``PlanningResults`` field list.
+
+Differences, all forced by the scope (BASELINE.json north_star):
+* VocalTractLab synthesis and librosa mel extraction stay host-side and outside this package: the
+  ``prod_*`` / ``*_sig`` fields are ``None`` (empty lists for the per-step ones), ``target_acoustic`` must be a
+  log-mel array, and continue-learning of the models on synthesised audio (paule.py:1243-1454) is not run.
+* ``target_acoustic`` may be ``[Tm,60]`` (one word, results shaped like the reference's) or ``[B,Tm,60]``
+  (a batch: every result gains a leading word axis, per-step losses become arrays of shape ``[B]``).
+* arithmetic is fp32 on the GPU (the reference ships fp64 CPU).
+"""
+from __future__ import annotations
+
+import os
+import random
+from collections import namedtuple
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .models import EmbeddingModel, ForwardModel, InverseModelMelTimeSmoothResidual
+from .planner import BatchPlanner
+
+DIR = os.path.dirname(__file__)
+
+# field list of paule/paule.py:57 (33 names)
+PlanningResults = namedtuple('PlanningResults', "planned_cp, initial_cp, initial_sig, initial_sr, initial_prod_mel,initial_pred_mel, target_sig, target_sr, target_mel, prod_sig, prod_sr, prod_mel, pred_mel, initial_prod_semvec, initial_pred_semvec, prod_semvec, pred_semvec, prod_loss_steps, planned_loss_steps, planned_mel_loss_steps, vel_loss_steps, jerk_loss_steps, pred_semvec_loss_steps, prod_semvec_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, inv_model_loss")
+BestSynthesisAcoustic = namedtuple('BestSynthesisAcoustic', "mel_loss, planned_cp, prod_sig, prod_mel, pred_mel")
+BestSynthesisSemantic = namedtuple('BestSynthesisSemantic', "semvec_loss, planned_cp, prod_sig, prod_semvec, pred_semvec")
+SubLosses = namedtuple('SubLosses', "mel_loss, semvec_loss, velocity_loss, jerk_loss, local_linear_loss, speech_classifier_loss, tube_mel_loss, tube_semvec_loss")
+
+_PRETRAINED = {   # file names of paule/paule.py:126,148,169
+    "pred": "pretrained_models/predictive/pred_model_common_voice_1_720_lr_0001_50_00001_50_000001_50_0000001_200.pt",
+    "inv": "pretrained_models/inverse/inv_model_common_voice_3_1_720_5_lr_0001_50_00001_50_000001_50_0000001_200.pt",
+    "emb": "pretrained_models/embedder/embed_model_common_voice_syn_rec_2_720_0_dropout_07_noise_6e05_rmse_lr_00001_200.pt",
+}
+
+
+def _load_pretrained(module, key, device):
+    path = os.path.join(DIR, _PRETRAINED[key])
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"pretrained weights {path} not found; pass the model explicitly "
+                                f"(Paule(pred_model=..., inv_model=..., embedder=...)) or place the reference's "
+                                f"pretrained_models/ directory next to {__file__}")
+    module.load_state_dict(torch.load(path, map_location=device, weights_only=True))
+    return module
+
+
+class Paule():
+    """State of the planner: predictive, inverse and embedder model (reference: paule/paule.py:92-318)."""
+
+    def __init__(self, *, pred_model=None, pred_optimizer=None, inv_model=None, inv_optimizer=None,
+                 embedder=None, cp_gen_model=None, mel_gen_model=None,
+                 use_somatosensory_feedback=False, cp_tube_model=None, tube_optimizer=None,
+                 tube_mel_model=None, tube_mel_optimizer=None, tube_embedder=None,
+                 continue_data=None, device=torch.device('cuda'), smiling=False,
+                 use_speech_classifier=False, speech_classifier=None, speech_classifier_optimizer=None,
+                 math=ops.MATH_FP32):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.PauleB200Error("paule_b200.Paule runs on a B200 (device='cuda'); there is no CPU fallback")
+        self.smiling = smiling
+        self.math = math
+        if use_somatosensory_feedback and use_speech_classifier:
+            raise NotImplementedError("at the moment you have to choose either to use `use_somatosenrosry_feedback=True` OR to use `use_speech_classifier=True` or none")
+        if use_somatosensory_feedback or use_speech_classifier:
+            raise NotImplementedError("the somatosensory and speech-classifier loss branches (paule/paule.py:210-273) "
+                                      "are outside the B200 hot path (SURVEY.md section 8f, row N4)")
+        self.use_somatosensory_feedback = False
+        self.use_speech_classifier = False
+
+        self.pred_model = pred_model if pred_model else _load_pretrained(
+            ForwardModel(num_lstm_layers=1, hidden_size=720), "pred", self.device)
+        self.pred_model = self.pred_model.to(self.device)
+        self.inv_model = inv_model if inv_model else _load_pretrained(
+            InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=720), "inv", self.device)
+        self.inv_model = self.inv_model.to(self.device)
+        self.embedder = embedder if embedder else _load_pretrained(
+            EmbeddingModel(num_lstm_layers=2, hidden_size=720), "emb", self.device)
+        self.embedder = self.embedder.to(self.device)
+        # generative models are only used for initialize_from='semvec' / missing acoustic targets (paule.py:515-522,
+        # :558-565); they are kept as injected (any torch module on the device), never constructed here.
+        self.cp_gen_model = cp_gen_model.to(self.device) if cp_gen_model is not None else None
+        self.mel_gen_model = mel_gen_model.to(self.device) if mel_gen_model is not None else None
+
+        self.continue_data = continue_data
+        self.continue_data_limit = 1000
+        self.pred_optimizer = pred_optimizer if pred_optimizer else torch.optim.Adam(self.pred_model.parameters(), lr=0.001)
+        self.inv_optimizer = inv_optimizer if inv_optimizer else torch.optim.Adam(self.inv_model.parameters(), lr=0.001)
+        self.best_synthesis_acoustic = None
+        self.best_synthesis_semantic = None
+        self.last_planner: Optional[BatchPlanner] = None
+
+    def plan_iterative(self, overlap=8):
+        """Empty stub in the reference as well (paule/paule.py:383-388)."""
+        pass
+
+    def plan_resynth(self, *, learning_rate_planning=0.01, learning_rate_learning=0.001,
+                     learning_rate_learning_inv=None,
+                     target_acoustic=None,
+                     target_semvec=None,
+                     target_seq_length=None,
+                     initial_cp=None,
+                     past_cp=None,
+                     initialize_from="acoustic",
+                     objective="acoustic",
+                     n_outer=5, n_inner=24,
+                     continue_learning=True,
+                     continue_learning_inv=False,
+                     continue_learning_tube=False,
+                     add_training_data_pred=False,
+                     add_training_data_inv=False,
+                     n_batches=3, batch_size=8, n_epochs=10,
+                     log_ii=1,
+                     log_semantics=True,
+                     log_gradients=False,
+                     log_signals=False,
+                     log_cps=False,
+                     plot=False,
+                     seed=None,
+                     verbose=True):
+        """Plans resynthesis cp trajectories (reference: paule/paule.py:391-1551) for one word or a batch."""
+        if seed:
+            torch.manual_seed(seed)
+            random.seed(seed)
+
+        if target_acoustic is None and target_semvec is None:
+            raise ValueError("Either target_acoustic or target_semvec has to be not None.")
+
+        if learning_rate_learning:
+            for param_group in self.pred_optimizer.param_groups:
+                param_group['lr'] = learning_rate_learning
+        if learning_rate_learning_inv:
+            for param_group in self.inv_optimizer.param_groups:
+                param_group['lr'] = learning_rate_learning_inv
+
+        if log_ii is None:
+            log_ii = n_inner
+        if log_ii > n_inner:
+            raise ValueError('results can only be logged between first and last planning step')
+
+        # ---- target parsing (paule.py:486-529).  Audio targets need librosa + VocalTractLab-side tooling
+        batched = False
+        target_mel = None
+        if isinstance(target_acoustic, str) or (isinstance(target_acoustic, (tuple, list)) and len(target_acoustic) == 2
+                                                and not isinstance(target_acoustic[0], (list, tuple, np.ndarray, torch.Tensor))
+                                                ):
+            raise NotImplementedError("audio targets (file name or (sig, sr)) need the host-side librosa mel front-end "
+                                      "(paule/util.py:115-146), which is outside the B200 hot path; pass the "
+                                      "normalised log-mel array instead")
+        elif target_acoustic is None:
+            pass
+        else:
+            if isinstance(target_acoustic, torch.Tensor):
+                target_mel = target_acoustic.detach().clone()
+            else:
+                target_mel = torch.from_numpy(np.ascontiguousarray(target_acoustic))
+            if target_mel.dim() == 2:
+                target_mel = target_mel.unsqueeze(0)
+            elif target_mel.dim() == 3:
+                batched = target_mel.shape[0] != 1 or (initial_cp is not None and np.ndim(initial_cp) == 3)
+            else:
+                raise ValueError("target_acoustic has to be torch.Tensor at this point")
+            target_seq_length = target_mel.shape[1]
+
+        if target_acoustic is None and (target_seq_length is None or target_semvec is None):
+            raise ValueError("if target_acoustic is None you need to give a target_seq_length and a target_semvec")
+        elif target_acoustic is None:
+            if self.mel_gen_model is None:
+                raise NotImplementedError("planning without an acoustic target needs mel_gen_model (paule.py:515-522)")
+            if not isinstance(target_semvec, torch.Tensor):
+                target_semvec = torch.tensor(np.asarray(target_semvec), device=self.device)
+            sv = target_semvec.reshape(-1, 300).detach().clone().to(self.device)
+            noise = torch.randn(sv.shape[0], 1, 100, device=self.device, dtype=sv.dtype)
+            target_mel = self.mel_gen_model(noise, target_seq_length, sv).detach().clone()
+            batched = sv.shape[0] != 1
+
+        target_mel = target_mel.to(self.device).float().contiguous()
+        B = target_mel.shape[0]
+
+        if target_semvec is not None:
+            if not isinstance(target_semvec, torch.Tensor):
+                target_semvec = torch.tensor(np.asarray(target_semvec), device=self.device)
+            target_semvec = target_semvec.reshape(B, 300).detach().clone().to(self.device).float()
+
+        # ---- 1.1 initial cp (paule.py:550-573)
+        if initial_cp is None:
+            if initialize_from == "acoustic":
+                with torch.no_grad():
+                    cp0 = self.inv_model(target_mel).clamp(min=-1, max=1)
+            elif initialize_from == "semvec":
+                if self.cp_gen_model is None:
+                    raise NotImplementedError("initialize_from='semvec' needs cp_gen_model (paule.py:558-565)")
+                if target_semvec is None:
+                    with torch.no_grad():
+                        target_semvec = self.embedder(target_mel, tuple(target_mel.shape[1] for _ in range(B)))
+                noise = torch.randn(B, 1, 100, device=self.device)
+                cp0 = self.cp_gen_model(noise, 2 * target_seq_length, target_semvec.reshape(B, 300)).detach().float()
+            else:
+                raise ValueError("initialize_from has to be either 'acoustic' or 'semvec'")
+        else:
+            if initialize_from is not None:
+                raise ValueError('one of initial_cp and initialize_from has to be None')
+            cp0 = initial_cp if isinstance(initial_cp, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(initial_cp))
+            if cp0.dim() == 2:
+                cp0 = cp0.unsqueeze(0)
+            if not cp0.shape[1] == (target_mel.shape[1] * 2):
+                raise ValueError(f"initial_cp {cp0.shape[1]}, target_mel {target_mel.shape[1] * 2}")
+            if cp0.shape[0] != B:
+                raise ValueError(f"initial_cp has {cp0.shape[0]} words, target_acoustic {B}")
+            cp0 = cp0.to(self.device).float()
+
+        if not past_cp is None and past_cp.shape[-2] % 2 != 0:
+            raise ValueError("past_cp have to be None or the sequence length has to be an even number")
+        if objective not in ('acoustic_semvec', 'acoustic', 'semvec'):
+            raise ValueError("objective has to be one of 'acoustic_semvec', 'acoustic' or 'semvec'")
+
+        past_t = None
+        if past_cp is not None:
+            past_t = past_cp if isinstance(past_cp, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(past_cp))
+            past_t = past_t.to(self.device).float()
+            if past_t.dim() == 2:
+                past_t = past_t.unsqueeze(0).expand(B, -1, -1)
+            cp0 = torch.cat((past_t, cp0), dim=1)                                   # paule.py:579
+            # the reference prepends the *produced* mel of the past cps to the target (paule.py:867-870); without
+            # VocalTractLab the predicted mel of the past cps is used instead
+            with torch.no_grad():
+                past_mel = self.pred_model(past_t.contiguous())
+            target_mel = torch.cat((past_mel, target_mel), dim=1).contiguous()
+        initial_cp_np = cp0.detach().cpu().numpy().copy()
+
+        n_steps = int(n_outer) * int(n_inner)
+        planner = BatchPlanner(self.pred_model, self.embedder, cp0, target_mel, target_semvec,
+                               lr=learning_rate_planning, objective=objective, smiling=self.smiling, past_cp=past_t,
+                               log_semantics=log_semantics, log_gradients=log_gradients,
+                               max_log_steps=max(n_steps, 1), math=self.math,
+                               use_cuda_graph=True)
+        self.last_planner = planner
+
+        def out(t):
+            a = t.detach().cpu().numpy()
+            return a if batched else a[0]
+
+        # initial predictions (paule.py:822-824)
+        initial_pred_mel, initial_pred_semvec = planner.forward()
+
+        cp_steps, grad_steps, pred_semvec_steps, pred_mel_steps = [], [], [], []
+        need_per_step = log_cps or log_gradients
+        for ii_outer in range(n_outer):
+            cp_steps_ii, pred_semvec_steps_ii, pred_mel_steps_ii = [], [], []
+            if not need_per_step:
+                planner.step(n_inner)                      # no host round trip inside the inner loop
+            else:
+                for ii in range(n_inner):
+                    if log_cps and (ii + 1) % log_ii == 0:
+                        cp_steps_ii.append(out(planner.planned_cp()))                # logged before the update (:1066)
+                    planner.step(1)
+                    if log_gradients:
+                        grad_steps.append(planner.last_grad().clone())              # :1062-1063
+            cp_steps.append(cp_steps_ii)
+            pred_semvec_steps.append(pred_semvec_steps_ii)
+            pred_mel_steps.append(pred_mel_steps_ii)
+            # continue-learning on synthesised audio (paule.py:1243-1454) needs VocalTractLab: not part of this path
+
+        # final predictions (paule.py:1456-1470)
+        planned_cp = planner.planned_cp()
+        pred_mel, pred_semvec = planner.forward()
+        logs = {k: v.detach().cpu().numpy() for k, v in planner.losses().items()}   # ONE device->host copy
+
+        def per_step(name):
+            rows = [logs[name][k] for k in range(n_steps) if (k % n_inner + 1) % log_ii == 0]
+            return [r if batched else float(r[0]) for r in rows]
+
+        sem_logged = objective in ('acoustic_semvec', 'semvec') or log_semantics
+        return PlanningResults(
+            out(planned_cp), initial_cp_np if batched else initial_cp_np[0], None, None, None, out(initial_pred_mel),
+            None, None, out(target_mel), None, None, None, out(pred_mel), None, out(initial_pred_semvec), None,
+            out(pred_semvec), list(), per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
+            per_step("semvec") if sem_logged else list(), list(), cp_steps, pred_semvec_steps, list(), grad_steps,
+            list(), list(), pred_mel_steps, list(), list())
+
+
+# BASELINE.json's north_star spells the class name in capitals
+PAULE = Paule

@@ -1,0 +1,214 @@
+"""Batched, device-resident driver of the planning inner loop (the new component SURVEY.md section 8
+asks for: the reference plans one word per call, paule/paule.py:539,826; words are independent, so a
+batch is B independent plans run in lock-step with per-word losses).
+
+``BatchPlanner`` owns (through PyTorch) every device buffer of one planning job -- cps, Adam state,
+targets, activation stash -- laid out time-major, and drives ``paule_plan_step`` (one C call per inner
+step, or one CUDA-graph replay).  No host synchronisation happens inside the loop: the loss terms of
+every step go to a device ring buffer that is copied out once at the end.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, ops
+from .models import EmbeddingModel, ForwardModel, _f32c
+
+
+class BatchPlanner:
+    """Plans B words at once on one GPU.
+
+    Parameters mirror what ``Paule.plan_resynth`` sets up before its loop (paule/paule.py:585-597,797):
+    ``initial_cp`` [B,T,30], ``target_mel`` [B,T//2,60], ``target_semvec`` [B,300] or None (then it is the
+    embedder's output on the target mel, :533-535), Adam(lr) with torch defaults, clamp 1.05.
+    """
+
+    def __init__(self, pred_model: ForwardModel, embedder: EmbeddingModel, initial_cp: torch.Tensor,
+                 target_mel: torch.Tensor, target_semvec: Optional[torch.Tensor] = None, *, lr: float = 0.01,
+                 objective: str = "acoustic_semvec", smiling: bool = False, past_cp: Optional[torch.Tensor] = None,
+                 log_semantics: bool = True, log_gradients: bool = False, max_log_steps: int = 1024,
+                 math: int = ops.MATH_FP32, use_cuda_graph: bool = True):
+        _lib.require_device()
+        if objective not in ops.OBJECTIVES:
+            raise ValueError("objective has to be one of 'acoustic_semvec', 'acoustic' or 'semvec'")
+        if pred_model.lstm.num_layers != 1 or embedder.lstm.num_layers != 2 or embedder.post_upsampling_size != 0:
+            raise NotImplementedError("the fused planner implements Paule's configuration: 1-layer ForwardModel, "
+                                      "2-layer EmbeddingModel without post-upsampling (paule/paule.py:124,167)")
+        if not pred_model.apply_half_sequence:
+            raise NotImplementedError("the fused planner expects apply_half_sequence=True")
+        dev = initial_cp.device
+        if dev.type != "cuda":
+            raise _lib.PauleB200Error("BatchPlanner needs CUDA tensors: there is no CPU fallback")
+        self.device = dev
+        B, T, C = initial_cp.shape
+        Tm = T // 2
+        if target_mel.shape[0] != B or target_mel.shape[1] != Tm:
+            raise ValueError(f"initial_cp {tuple(initial_cp.shape)} does not match target_mel {tuple(target_mel.shape)}")
+        if T < 13:
+            raise ValueError("cp trajectories need at least 13 frames (three nested 5-point stencils, util.py:634-636)")
+        H = pred_model.lstm.hidden_size
+        if embedder.lstm.hidden_size != H:
+            raise NotImplementedError("pred_model and embedder must share the hidden size")
+        Cm, S = target_mel.shape[2], embedder.linear_mapping.out_features
+        self.B, self.T, self.Tm, self.H, self.C, self.Cm, self.S = B, T, Tm, H, C, Cm, S
+        self.objective, self.math = objective, math
+        tc = math != ops.MATH_FP32
+        # ---- weights (replicated per GPU; repacked by refresh_weights() after continue-learning)
+        self._pred, self._emb = pred_model, embedder
+        self._tc = tc
+        self.refresh_weights()
+        # ---- state, time-major
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.cp = ops.transpose_btc(initial_cp.float().contiguous())                  # [T,B,C]
+        self.adam_m = torch.zeros_like(self.cp)
+        self.adam_v = torch.zeros_like(self.cp)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.target_mel = ops.transpose_btc(target_mel.float().contiguous())          # [Tm,B,Cm]
+        self.past_cp = None
+        if past_cp is not None:
+            pc = past_cp.float().contiguous()
+            if pc.dim() == 2:
+                pc = pc.unsqueeze(0).expand(B, -1, -1).contiguous()
+            self.past_cp = ops.transpose_btc(pc)
+        self.max_log_steps = int(max_log_steps)
+        self.loss_log = torch.zeros((self.max_log_steps, B, 6), **f32)
+        self.pred_mel = torch.empty((Tm, B, Cm), **f32)
+        self.pred_sv = torch.zeros((B, S), **f32)
+        self.grad_out = torch.empty_like(self.cp) if log_gradients else None
+        lib = _lib.load()
+        ws_bytes = lib.paule_plan_workspace_bytes(B, T, H, C, Cm, S, math)
+        self.workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        self.target_sv = torch.zeros((B, S), **f32)
+        self.hp = dict(lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8, clamp=1.05)
+        self.smiling, self.log_semantics = bool(smiling), bool(log_semantics)
+        self._struct = None
+        self._build_struct()
+        self._key = ops.register_plan(self)
+        self._graph = None
+        self._use_graph = bool(use_cuda_graph)
+        self.steps_done = 0
+        # target semvec = embedder(target_mel) under no_grad (paule/paule.py:533-535) unless given
+        if target_semvec is None:
+            self.target_sv.copy_(self.embed(self.target_mel))
+        else:
+            self.target_sv.copy_(target_semvec.to(dev).float().reshape(B, S))
+
+    # ------------------------------------------------------------------------------------------
+    def refresh_weights(self) -> None:
+        """(Re)pack the model weights; call after the models' parameters changed."""
+        p, e = self._pred, self._emb
+        self.w_fwd = ops.LstmWeights(p.lstm.weight_ih_l0, p.lstm.weight_hh_l0, p.lstm.bias_ih_l0, p.lstm.bias_hh_l0,
+                                     tc=self._tc)
+        self.w_e0 = ops.LstmWeights(e.lstm.weight_ih_l0, e.lstm.weight_hh_l0, e.lstm.bias_ih_l0, e.lstm.bias_hh_l0,
+                                    tc=self._tc)
+        self.w_e1 = ops.LstmWeights(e.lstm.weight_ih_l1, e.lstm.weight_hh_l1, e.lstm.bias_ih_l1, e.lstm.bias_hh_l1,
+                                    tc=self._tc)
+        self.post_w, self.post_b = _f32c(p.post_linear.weight), _f32c(p.post_linear.bias)
+        self.post_w_t = self.post_w.t().contiguous()
+        self.head_w, self.head_b = _f32c(e.linear_mapping.weight), _f32c(e.linear_mapping.bias)
+        self.head_w_t = self.head_w.t().contiguous()
+        if getattr(self, "_struct", None) is not None:
+            self._build_struct()
+            self._graph = None
+
+    def _build_struct(self) -> None:
+        s = _lib.Plan()
+        s.B, s.T, s.H, s.C, s.Cm, s.S = self.B, self.T, self.H, self.C, self.Cm, self.S
+        s.objective, s.math = ops.OBJECTIVES[self.objective], self.math
+        s.smiling, s.log_slot_count = int(self.smiling), self.max_log_steps
+        s.log_semantics = int(self.log_semantics)
+        s.fwd, s.emb0, s.emb1 = self.w_fwd.as_struct(), self.w_e0.as_struct(), self.w_e1.as_struct()
+        s.post_w, s.post_w_t, s.post_b = self.post_w.data_ptr(), self.post_w_t.data_ptr(), self.post_b.data_ptr()
+        s.head_w, s.head_w_t, s.head_b = self.head_w.data_ptr(), self.head_w_t.data_ptr(), self.head_b.data_ptr()
+        s.cp, s.adam_m, s.adam_v = self.cp.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr()
+        s.step_count = self.step_count.data_ptr()
+        s.target_mel, s.target_sv = self.target_mel.data_ptr(), self.target_sv.data_ptr()
+        s.past_cp = None if self.past_cp is None else self.past_cp.data_ptr()
+        s.past_T = 0 if self.past_cp is None else self.past_cp.shape[0]
+        s.lr, s.beta1, s.beta2 = self.hp["lr"], self.hp["beta1"], self.hp["beta2"]
+        s.eps, s.clamp = self.hp["eps"], self.hp["clamp"]
+        s.loss_log, s.pred_mel, s.pred_sv = self.loss_log.data_ptr(), self.pred_mel.data_ptr(), self.pred_sv.data_ptr()
+        s.grad_out = None if self.grad_out is None else self.grad_out.data_ptr()
+        s.workspace, s.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        self._struct = s
+
+    def struct_ref(self):
+        return ctypes.byref(self._struct)
+
+    # ------------------------------------------------------------------------------------------
+    def embed(self, mel_tm: torch.Tensor) -> torch.Tensor:
+        """semvec of a time-major mel [Tm,B,Cm] through the planner's own embedder kernels (no grad)."""
+        with torch.no_grad():
+            h = mel_tm
+            for L in (self.w_e0, self.w_e1):
+                h, _, _ = ops.lstm_layer_fwd(h, False, L.w_ih, L.w_hh, L.bias)
+            return ops.linear_tm(h[-1:].contiguous(), self.head_w, self.head_b, False, False)[0]
+
+    def forward(self):
+        """no_grad predictions for the current cps -> (pred_mel [B,Tm,Cm], pred_semvec [B,S])."""
+        ops.plan_forward(self.cp, self.pred_mel, self.pred_sv, self.workspace, self._key)
+        return ops.transpose_btc(self.pred_mel), self.pred_sv.clone()
+
+    def _one_step(self) -> None:
+        ops.plan_step(self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log, self.pred_mel, self.pred_sv,
+                      self.workspace, self._key)
+
+    def step(self, n: int = 1) -> None:
+        """n inner steps (optimizer.zero_grad() ... clamp, paule/paule.py:911-1211), no host sync."""
+        if n <= 0:
+            return
+        if self.steps_done + n > self.max_log_steps:
+            raise ValueError(f"loss log holds {self.max_log_steps} steps; construct with a larger max_log_steps")
+        if self._use_graph and self._graph is None:
+            # warm up on a side stream, then capture one step; Adam's step counter and the log slot live on the
+            # device, so a replay is a full, correct step.
+            snap = [t.clone() for t in (self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log)]
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._one_step()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            for dst, src in zip((self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log), snap):
+                dst.copy_(src)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._one_step()
+            for dst, src in zip((self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log), snap):
+                dst.copy_(src)
+            self._graph = g
+        for _ in range(n):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._one_step()
+        self.steps_done += n
+
+    # ------------------------------------------------------------------------------------------
+    def planned_cp(self) -> torch.Tensor:
+        """current cps, batch-first [B,T,C]."""
+        return ops.transpose_btc(self.cp)
+
+    def set_cp(self, cp_bf: torch.Tensor) -> None:
+        self.cp.copy_(ops.transpose_btc(cp_bf.float().contiguous()))
+
+    def losses(self) -> Dict[str, torch.Tensor]:
+        """per-step, per-word loss terms logged BEFORE each update (paule/paule.py:988): tensors [steps,B]."""
+        log = self.loss_log[: self.steps_done]
+        return {"total": log[..., 0], "mel": log[..., 1], "semvec": log[..., 2], "velocity": log[..., 3],
+                "jerk": log[..., 4], "local_linear": log[..., 5]}
+
+    def last_grad(self) -> Optional[torch.Tensor]:
+        return None if self.grad_out is None else ops.transpose_btc(self.grad_out)
+
+    def close(self) -> None:
+        ops.unregister_plan(self._key)
+        self._graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

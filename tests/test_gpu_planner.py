@@ -1,0 +1,230 @@
+"""Step- and trajectory-level parity of the fused planner against the reference-generated golden vectors
+and the CPU oracle, plus the Paule API surface.  Run on the B200 box: python -m pytest tests -m gpu
+
+Tolerances (BASELINE.json north_star): per-step loss 1e-3 relative, final cp 1e-3 absolute in fp32 on the
+well-conditioned (iid) input; fp32 math is held to much tighter bounds here (1e-4 / 1e-5).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import paule_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MATHS = [0]   # PAULE_MATH_FP32; tensor-core modes are appended once paule_tc_* is available
+
+
+def _tc_available():
+    from paule_b200 import _lib
+    return _lib.load().paule_tc_packed_lstm_bytes(720, 30) > 0
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from paule_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def models(dev, golden):
+    import paule_b200 as P
+    torch.manual_seed(0)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=720)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=720)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=720)
+    assert [O.state_dict_digest(m) for m in (pred, emb, inv)] == list(golden["digest32"])
+    return pred.to(dev), emb.to(dev), inv.to(dev)
+
+
+def _np(t):
+    return t.detach().cpu().double().numpy()
+
+
+def math_params():
+    ps = [pytest.param(0, id="fp32")]
+    ps.append(pytest.param(1, id="bf16", marks=pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")))
+    return ps
+
+
+# tolerance per math mode: (loss rtol, grad rel-to-max, cp atol)
+TOL = {0: (1e-4, 2e-4, 1e-5), 1: (1e-3, 2e-2, 1e-3)}
+
+
+@pytest.mark.parametrize("math", math_params())
+def test_teacher_forced_steps_match_golden(dev, models, golden, math):
+    """Feed the oracle's cp of step k, compare loss terms, d(cp) and the post-Adam cp of that single step."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    cp0 = torch.from_numpy(golden["b3_cp0"]).to(dev)
+    tmel = torch.from_numpy(golden["b3_tmel"]).to(dev)
+    cps = golden["b3_cps"]            # [steps,B,T,30] cp BEFORE each update
+    grads = golden["b3_grads"]
+    n = cps.shape[0]
+    pl = BatchPlanner(pred, emb, cp0, tmel, None, log_gradients=True, max_log_steps=n, math=math,
+                      use_cuda_graph=False)
+    np.testing.assert_allclose(_np(pl.target_sv), golden["b3_tsv"], atol=5e-6)
+    lr, gr, ca = TOL[math]
+    for k in range(n):
+        pl.set_cp(torch.from_numpy(cps[k]).to(dev))
+        pl.step(1)
+        g = _np(pl.last_grad())
+        np.testing.assert_allclose(g, grads[k], rtol=gr, atol=gr * np.abs(grads[k]).max())
+        nxt = cps[k + 1] if k + 1 < n else golden["b3_planned_cp"]
+        np.testing.assert_allclose(_np(pl.planned_cp()), nxt, atol=ca)
+    L = pl.losses()
+    np.testing.assert_allclose(_np(L["total"]), golden["b3_loss"], rtol=lr)
+    np.testing.assert_allclose(_np(torch.stack([L["mel"], L["semvec"], L["velocity"], L["jerk"], L["local_linear"]], -1)),
+                               golden["b3_terms"], rtol=lr)
+
+
+@pytest.mark.parametrize("math", math_params())
+@pytest.mark.parametrize("graph", [False, True])
+def test_free_running_matches_golden(dev, models, golden, math, graph):
+    """Free-running 5 steps on the iid input: loss curve and final cps vs the reference-generated vectors."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    pl = BatchPlanner(pred, emb, torch.from_numpy(golden["b3_cp0"]).to(dev), torch.from_numpy(golden["b3_tmel"]).to(dev),
+                      None, max_log_steps=8, math=math, use_cuda_graph=graph)
+    pl.step(3)
+    pl.step(2)
+    lr, _, ca = TOL[math]
+    np.testing.assert_allclose(_np(pl.losses()["total"]), golden["b3_loss"], rtol=lr)
+    np.testing.assert_allclose(_np(pl.planned_cp()), golden["b3_planned_cp"], atol=ca)
+    mel, sv = pl.forward()
+    np.testing.assert_allclose(_np(mel), golden["b3_pred_mel"], atol=max(ca, 2e-5))
+    np.testing.assert_allclose(_np(sv), golden["b3_pred_semvec"], atol=max(ca, 2e-5))
+
+
+@pytest.mark.parametrize("tag,objective,smiling", [("real64", "acoustic_semvec", False), ("real64_ac", "acoustic", False),
+                                                   ("real64_sv", "semvec", True), ("real32", "acoustic_semvec", False)])
+def test_paule_plan_resynth_matches_the_real_reference(dev, models, golden, tag, objective, smiling):
+    """Paule.plan_resynth (our API) vs the REAL reference's plan_resynth outputs (fp64 / fp32 CPU), B=1."""
+    import paule_b200 as P
+    pred, emb, inv = models
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, smiling=smiling)
+    n = len(golden[f"{tag}_loss"])
+    res = pm.plan_resynth(target_acoustic=golden[f"{tag}_tmel"][0].astype(np.float32),
+                          initial_cp=golden[f"{tag}_cp0"][0].astype(np.float32), initialize_from=None,
+                          objective=objective, n_outer=1, n_inner=n, log_ii=1, continue_learning=False,
+                          verbose=False, log_semantics=False, log_cps=True)
+    assert len(res) == 33 and res._fields[0] == "planned_cp" and res._fields[-1] == "inv_model_loss"
+    np.testing.assert_allclose(res.planned_loss_steps, golden[f"{tag}_loss"], rtol=1e-4)
+    np.testing.assert_allclose(res.vel_loss_steps, golden[f"{tag}_vel"], rtol=1e-4)
+    np.testing.assert_allclose(res.jerk_loss_steps, golden[f"{tag}_jerk"], rtol=1e-4)
+    np.testing.assert_allclose(res.planned_mel_loss_steps, golden[f"{tag}_mel"], rtol=1e-4)
+    if objective != "acoustic":
+        np.testing.assert_allclose(res.pred_semvec_loss_steps, golden[f"{tag}_sem"], rtol=1e-4)
+    assert res.planned_cp.shape == golden[f"{tag}_planned_cp"].shape
+    np.testing.assert_allclose(res.planned_cp, golden[f"{tag}_planned_cp"], atol=1e-5)
+    if tag.startswith("real64"):
+        np.testing.assert_allclose(np.stack(res.cp_steps[0]), golden[f"{tag}_cp_steps"], atol=1e-5)
+        np.testing.assert_allclose(res.pred_mel, golden[f"{tag}_pred_mel"], atol=2e-5)
+        np.testing.assert_allclose(res.pred_semvec, golden[f"{tag}_pred_semvec"], atol=2e-5)
+    if smiling:
+        assert np.all(res.planned_cp[:, 4] == -1.0) and np.all(res.planned_cp[:, 1] == 1.0)
+
+
+def test_smooth_input_teacher_forced(dev, models, golden):
+    """Chaotic regime (smooth cps): only step-0 quantities are pinned tightly."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    pl = BatchPlanner(pred, emb, torch.from_numpy(golden["real32_smooth_cp0"]).to(dev),
+                      torch.from_numpy(golden["real32_smooth_tmel"]).to(dev), None, max_log_steps=8)
+    pl.step(6)
+    L = _np(pl.losses()["total"])[:, 0]
+    np.testing.assert_allclose(L[:2], golden["real32_smooth_loss"][:2], rtol=1e-4)
+    np.testing.assert_allclose(L, golden["real32_smooth_loss"], rtol=5e-2)
+
+
+def test_batched_equals_solo_and_past_cp(dev, models):
+    """B words batched == B solo runs (words are independent); past_cp prefix is frozen."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(4, 40, seed=21)
+    cp0, tmel = cp0.to(dev), tmel.to(dev)
+    pl = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=4)
+    pl.step(4)
+    full = pl.planned_cp()
+    for i in (0, 3):
+        solo = BatchPlanner(pred, emb, cp0[i:i + 1], tmel[i:i + 1], None, max_log_steps=4)
+        solo.step(4)
+        np.testing.assert_allclose(_np(solo.planned_cp()), _np(full[i:i + 1]), atol=2e-6)
+    past = cp0[:, :6].clone()
+    pl2 = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=4, past_cp=past)
+    pl2.step(3)
+    assert torch.equal(pl2.planned_cp()[:, :6], past)
+    # against the oracle
+    pr, em, _ = O.build_reference_models(0, 720, torch.float32, with_inverse=False)
+    r = O.plan_inner_loop(pr, em, cp0.cpu(), tmel.cpu(), 3, past_cp=past.cpu())
+    np.testing.assert_allclose(_np(pl2.planned_cp()), r["planned_cp"].double().numpy(), atol=1e-5)
+
+
+def test_value_errors_of_the_reference_api(dev, models):
+    """The 8 ValueErrors of the reference's tests/test_paule.py:31-62 (with a mel array as acoustic target)."""
+    import paule_b200 as P
+    pred, emb, inv = models
+    pm = P.PAULE(pred_model=pred, inv_model=inv, embedder=emb, device=dev)
+    mel = np.random.RandomState(0).rand(20, 60).astype(np.float32)
+    cp_11zeros = np.zeros((11, 30), dtype=np.float32)
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=None, target_semvec=None)
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=mel, target_semvec=None, n_inner=5, log_ii=10)
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=None, target_semvec=np.zeros((300,)))
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=mel, initialize_from='ERROR')
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=mel, initial_cp=cp_11zeros, initialize_from='ERROR')
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=mel, initial_cp=cp_11zeros)
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=mel, past_cp=cp_11zeros)
+    with pytest.raises(ValueError):
+        pm.plan_resynth(target_acoustic=mel, objective="ERROR")
+
+
+def test_inverse_init_batched_plan(dev, models):
+    """BASELINE config 3 in miniature: inverse-model initialisation + planning, batched, results with a word axis."""
+    import paule_b200 as P
+    pred, emb, inv = models
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev)
+    _, tmel = O.synthetic_inputs(3, 40, seed=31)
+    res = pm.plan_resynth(target_acoustic=tmel.numpy(), initialize_from="acoustic", objective="acoustic_semvec",
+                          n_outer=2, n_inner=3, continue_learning=False, verbose=False)
+    assert res.planned_cp.shape == (3, 40, 30) and res.initial_cp.shape == (3, 40, 30)
+    assert np.abs(res.initial_cp).max() <= 1.0 and np.abs(res.planned_cp).max() <= 1.05
+    assert len(res.planned_loss_steps) == 6 and res.planned_loss_steps[0].shape == (3,)
+    # oracle: same init (its fp32-capable inverse model), same loop
+    pr, em, iv = O.build_reference_models(0, 720, torch.float32)
+    with torch.no_grad():
+        init = iv(tmel).clamp(-1, 1)
+    np.testing.assert_allclose(res.initial_cp, init.numpy(), atol=5e-5)
+    r = O.plan_inner_loop(pr, em, torch.from_numpy(res.initial_cp), tmel, 6)
+    np.testing.assert_allclose(np.stack(res.planned_loss_steps), r["loss"].numpy(), rtol=1e-3)
+
+
+def test_full_size_properties_cfg2(dev, models):
+    """BASELINE config 2 shape (B=64, T=200): size-independent properties instead of an element-wise oracle run:
+    the loss falls monotonically on the iid input, stays finite, cps stay clamped, and word 7 of the batch
+    equals the same word planned alone."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(64, 200, seed=5)
+    cp0, tmel = cp0.to(dev), tmel.to(dev)
+    pl = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=10)
+    pl.step(10)
+    L = pl.losses()["total"]
+    assert torch.isfinite(L).all()
+    assert (L[1:] < L[:-1]).all(), "loss must fall monotonically on the well-conditioned input (SURVEY appendix B)"
+    assert pl.planned_cp().abs().max().item() <= 1.05 + 1e-6
+    solo = BatchPlanner(pred, emb, cp0[7:8], tmel[7:8], None, max_log_steps=10)
+    solo.step(10)
+    np.testing.assert_allclose(_np(solo.planned_cp()), _np(pl.planned_cp()[7:8]), atol=5e-6)
+    # the oracle on the same word: BASELINE tolerance
+    pr, em, _ = O.build_reference_models(0, 720, torch.float32, with_inverse=False)
+    r = O.plan_inner_loop(pr, em, cp0[7:8].cpu(), tmel[7:8].cpu(), 10)
+    np.testing.assert_allclose(_np(solo.losses()["total"]), r["loss"].double().numpy(), rtol=1e-3)
+    np.testing.assert_allclose(_np(solo.planned_cp()), r["planned_cp"].double().numpy(), atol=1e-3)
