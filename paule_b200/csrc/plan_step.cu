@@ -15,6 +15,8 @@ using namespace paule;
 
 namespace {
 
+constexpr bool kUseTcGemm = false;   // batched gate GEMMs still run on the fp32 FFMA kernel
+
 struct Workspace {
   float *gates_f, *h_f, *c_f;
   float *gates_0, *h_0, *c_0;
@@ -75,7 +77,7 @@ int layer_forward(const paule_plan* p, const paule_lstm_layer& L, const float* x
                   void* xchg, paule_stream_t s) {
   const int64_t B = p->B, H = p->H, M = steps * B;
   const bool tc = p->math != PAULE_MATH_FP32;
-  if (tc && L.input_size % 16 == 0 && L.input_size >= 256 && x_inner == 1 && x_outer_stride == L.input_size) {
+  if (kUseTcGemm && tc && L.input_size % 16 == 0 && L.input_size >= 256 && x_inner == 1 && x_outer_stride == L.input_size) {
     PAULE_TRY(paule_tc_gemm_nt(x, L.w_ih, L.bias, gates, M, 4 * H, L.input_size, p->math, 0, s));
   } else {
     PAULE_TRY(paule_linear_f32(x, L.w_ih, L.bias, gates, M, 4 * H, L.input_size, x_inner, x_outer_stride,
@@ -96,7 +98,7 @@ int layer_backward(const paule_plan* p, const paule_lstm_layer& L, float* gates,
 int input_grad(const paule_plan* p, const paule_lstm_layer& L, const float* da, float* dx, int64_t M, int accumulate,
                paule_stream_t s) {
   const int64_t H = p->H, I = L.input_size;
-  if (p->math != PAULE_MATH_FP32 && I % 16 == 0 && I >= 256)
+  if (kUseTcGemm && p->math != PAULE_MATH_FP32 && I % 16 == 0 && I >= 256)
     return paule_tc_gemm_nt(da, L.w_ih_t, nullptr, dx, M, I, 4 * H, p->math, accumulate, s);
   return paule_linear_f32(da, L.w_ih_t, nullptr, dx, M, I, 4 * H, 1, 4 * H, 0, 0, 1, I, 0, accumulate, s);
 }
