@@ -287,7 +287,7 @@ def dominant_kernel_roofline(planner, math, dev):
             _lib.check(lib.paule_lstm_seq_fwd_f32(gates.data_ptr(), L.w_hh.data_ptr(), h.data_ptr(), c.data_ptr(), T, B, H, st))
         else:
             _lib.check(lib.paule_tc_lstm_seq_fwd(gates.data_ptr(), L.packed.data_ptr(), h.data_ptr(), c.data_ptr(),
-                                                 xchg.data_ptr(), T, B, math, st))
+                                                 xchg.data_ptr(), None, T, B, math, st))
 
     def bwd():
         if math == 0:
@@ -295,7 +295,7 @@ def dominant_kernel_roofline(planner, math, dev):
                                                   scratch.data_ptr(), T, B, H, st))
         else:
             _lib.check(lib.paule_tc_lstm_seq_bwd(gates.data_ptr(), c.data_ptr(), L.packed.data_ptr(), dh.data_ptr(), 2, None,
-                                                 xchg.data_ptr(), T, B, math, st))
+                                                 xchg.data_ptr(), None, T, B, math, st))
 
     out = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):

@@ -48,8 +48,8 @@ enum { PAULE_OBJ_ACOUSTIC_SEMVEC = 0, PAULE_OBJ_ACOUSTIC = 1, PAULE_OBJ_SEMVEC =
 /* arithmetic of the recurrent / gate GEMMs */
 enum {
   PAULE_MATH_FP32 = 0,   /* FFMA, fp32 operands: the parity anchor */
-  PAULE_MATH_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM */
-  PAULE_MATH_BF16X3 = 2  /* tcgen05, hi/lo-split bf16 operands (3 MMAs), ~fp32 accuracy */
+  PAULE_MATH_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM, fp32 cell state */
+  PAULE_MATH_BF16X3 = 2  /* reserved: hi/lo-split bf16 operands (3 MMAs), ~fp32 accuracy; not implemented */
 };
 
 PAULE_API int paule_version(void);
@@ -161,30 +161,42 @@ PAULE_API int paule_upsample_smooth_f32(const float* x, const float* res_w, cons
  * Tensor-core path (sm_100a tcgen05 / TMEM / TMA), hidden size 720 only.
  * ------------------------------------------------------------------------------------------- */
 
-/* Bytes of the packed operand image paule_tc_pack_lstm writes for one LSTM layer. */
+/* "UMMA image": a bf16 matrix [rows, K] stored as K/64 k-blocks of rows x 128 B with the canonical SWIZZLE_128B
+ * K-major layout (see csrc/tc_common.cuh).  The tcgen05 kernels exchange activations through such images so that a
+ * consumer fetches a k-block with one TMA bulk copy and feeds it to tcgen05.mma unchanged. */
+
+/* Bytes of the packed W_hh images (forward slices + backward slices) paule_tc_pack_lstm writes for one layer. */
 PAULE_API size_t paule_tc_packed_lstm_bytes(int64_t H, int64_t I);
-/* Repack one layer's fp32 weights into the bf16 (hi, lo) UMMA shared-memory images the tcgen05 kernels
- * bulk-copy.  Required whenever the weights change (continue-learning, paule.py:1372-1377). */
+/* Repack one layer's fp32 W_hh into the bf16 UMMA images the persistent kernels keep resident in shared memory.
+ * Required whenever the weights change (continue-learning, paule.py:1372-1377).  w_ih is unused (see
+ * paule_tc_gemm_pack for the batched GEMM operands). */
 PAULE_API int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* packed, int64_t H, int64_t I,
                        paule_stream_t stream);
 
-/* C[M,N] = A[M,K] B[N,K]^T (+bias[N]) on tcgen05 -- the "gate GEMMs over all timesteps":
- * embedder layer-1 input projection (K5) and the dX GEMMs of BPTT (K8).  A, B fp32 in HBM, converted
- * to bf16 (math BF16) or hi/lo bf16 pairs (BF16X3) while staging; fp32 accumulate in TMEM.
- * M arbitrary, N % 16 == 0, K % 16 == 0. */
-PAULE_API int paule_tc_gemm_nt(const float* A, const float* B, const float* bias, float* C,
-                     int64_t M, int64_t N, int64_t K, int math, int accumulate, paule_stream_t stream);
+/* Batched gate GEMMs over all time steps on tcgen05 (K5 / K8 of SURVEY 2.2):
+ *   C[(t,b), n] (+)= sum_k A[(t,b), k] W[n, k] + bias[n],  C fp32 [steps, B, N] time-major.
+ * A = the image sequence a persistent kernel wrote: [ceil(B/64)][steps][nseg*12 k-blocks][64 rows][128 B]
+ *     (nseg = 1: h_t, K = 720 padded to 768; nseg = 4: the four gate images of dA_t, K = 4 x 768).
+ * W = fp32 [N, nseg*720] row-major, packed once by paule_tc_gemm_pack into bf16 images (N padded to 16). */
+PAULE_API size_t paule_tc_gemm_packed_bytes(int64_t N, int64_t nseg);
+PAULE_API int paule_tc_gemm_pack(const float* W, void* packed, int64_t N, int64_t nseg, paule_stream_t stream);
+PAULE_API int paule_tc_gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C,
+                      int64_t steps, int64_t B, int64_t N, int64_t nseg, int accumulate, paule_stream_t stream);
 
 /* Persistent-RNN forward / backward of one H=720 layer: W_hh slices stay resident in shared memory
- * for the whole sequence, one cooperative launch per layer, grid barrier per time step.
+ * for the whole sequence, one cooperative launch per layer and 64-word group, grid barrier per time step.
  * Same contract as paule_lstm_seq_fwd_f32 / _bwd_f32 plus:
- *   packed   image from paule_tc_pack_lstm
- *   xchg     >= paule_tc_rnn_xchg_bytes(B) bytes of scratch (h / d-gate exchange + barrier words) */
+ *   packed      image from paule_tc_pack_lstm
+ *   xchg        >= paule_tc_rnn_xchg_bytes(B) bytes of scratch (ping-pong exchange images + barrier words)
+ *   h_img_seq / da_img_seq   NULL, or >= paule_tc_img_seq_bytes(T, B, 1 / 4) bytes that were ZERO-FILLED once by
+ *               the owner: the kernel then keeps the bf16 image of every step there (A operand of
+ *               paule_tc_gemm_img) instead of ping-ponging inside xchg. */
 PAULE_API size_t paule_tc_rnn_xchg_bytes(int64_t B);
-PAULE_API int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h, float* c, void* xchg,
+PAULE_API size_t paule_tc_img_seq_bytes(int64_t T, int64_t B, int64_t images_per_step);
+PAULE_API int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq,
                           int64_t T, int64_t B, int math, paule_stream_t stream);
 PAULE_API int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* packed,
-                          const float* dh_seq, int dh_mode, const float* dh_last, void* xchg,
+                          const float* dh_seq, int dh_mode, const float* dh_last, void* xchg, void* da_img_seq,
                           int64_t T, int64_t B, int math, paule_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -198,6 +210,8 @@ typedef struct paule_lstm_layer {
   const float* w_hh_t;  /* [H, 4H]  */
   const float* bias;    /* [4H] = b_ih + b_hh */
   const void* packed;   /* paule_tc_pack_lstm image or NULL (fp32 math) */
+  const void* packed_ih;   /* paule_tc_gemm_pack(w_ih, 4H, 1) if input_size == H, else NULL */
+  const void* packed_ih_t; /* paule_tc_gemm_pack(w_ih_t, input_size, 4) or NULL */
   int64_t input_size;
 } paule_lstm_layer;
 

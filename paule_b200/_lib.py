@@ -19,7 +19,7 @@ i64, i32, f32, vp, sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
 class LstmLayer(C.Structure):
     """struct paule_lstm_layer"""
     _fields_ = [("w_ih", vp), ("w_hh", vp), ("w_ih_t", vp), ("w_hh_t", vp), ("bias", vp), ("packed", vp),
-                ("input_size", i64)]
+                ("packed_ih", vp), ("packed_ih_t", vp), ("input_size", i64)]
 
 
 class Plan(C.Structure):
@@ -58,10 +58,13 @@ SIGNATURES = {
     "paule_upsample_smooth_f32": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, i64, i64, i64, vp]),
     "paule_tc_packed_lstm_bytes": (sz, [i64, i64]),
     "paule_tc_pack_lstm": (C.c_int, [vp, vp, vp, i64, i64, vp]),
-    "paule_tc_gemm_nt": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, vp]),
+    "paule_tc_gemm_packed_bytes": (sz, [i64, i64]),
+    "paule_tc_gemm_pack": (C.c_int, [vp, vp, i64, i64, vp]),
+    "paule_tc_gemm_img": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, C.c_int, vp]),
     "paule_tc_rnn_xchg_bytes": (sz, [i64]),
-    "paule_tc_lstm_seq_fwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]),
-    "paule_tc_lstm_seq_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, i64, i64, C.c_int, vp]),
+    "paule_tc_img_seq_bytes": (sz, [i64, i64, i64]),
+    "paule_tc_lstm_seq_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]),
+    "paule_tc_lstm_seq_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, i64, i64, C.c_int, vp]),
     "paule_plan_workspace_bytes": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
     "paule_plan_forward": (C.c_int, [C.POINTER(Plan), vp]),
     "paule_plan_step": (C.c_int, [C.POINTER(Plan), vp]),

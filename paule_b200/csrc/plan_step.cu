@@ -6,6 +6,12 @@
 //   and back: dsv -> BPTT(l1) -> dX GEMM -> BPTT(l0) -> dX GEMM (+dmel of the mel loss) -> post_linear^T, un-pool
 //      -> BPTT(forward model) -> dX GEMM -> d(cp);  + smoothness gradients;  Adam + clamp (+ smiling, past_cp)
 //
+// math = FP32 : every GEMM / recurrence on the FFMA kernels (parity anchor).
+// math = BF16 : the three recurrences run as persistent tcgen05 kernels, the K = 720 input projection of embedder
+//               layer 1 and all dX GEMMs (K = 2880) as tcgen05 GEMMs fed by the bf16 images the recurrent kernels
+//               leave behind; only the skinny K = 30 / 60 / 300 projections stay on the FFMA kernel (they would be
+//               pure HBM traffic on tensor cores, and keeping cp / mel in fp32 there costs nothing).
+//
 // All launches go to one stream; there is no host synchronisation, no allocation and no host-visible state,
 // so the whole step can be captured in a CUDA graph and replayed.
 #include "common.cuh"
@@ -15,14 +21,12 @@ using namespace paule;
 
 namespace {
 
-constexpr bool kUseTcGemm = false;   // batched gate GEMMs still run on the fp32 FFMA kernel
-
 struct Workspace {
   float *gates_f, *h_f, *c_f;
   float *gates_0, *h_0, *c_0;
   float *gates_1, *h_1, *c_1;
   float *dmel, *dsv, *dh1_last, *dh0, *dhp, *dcp_lstm, *dcp_smooth, *dc, *partial;
-  void* xchg;
+  void *xchg, *h_img, *da_img;   // tensor-core path only; h_img / da_img must have been zero-filled once
   size_t floats;
 };
 
@@ -37,6 +41,7 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
     off += align_up((size_t)n, 64);  // 256-byte granularity keeps every buffer vector / bulk-copy aligned
     return p;
   };
+  auto take_bytes = [&](size_t nbytes) -> void* { return nbytes ? (void*)take((int64_t)((nbytes + 3) / 4)) : nullptr; };
   w.gates_f = take(T * B * 4 * H); w.h_f = take(T * B * H); w.c_f = take(T * B * H);
   w.gates_0 = take(Tm * B * 4 * H); w.h_0 = take(Tm * B * H); w.c_0 = take(Tm * B * H);
   w.gates_1 = take(Tm * B * 4 * H); w.h_1 = take(Tm * B * H); w.c_1 = take(Tm * B * H);
@@ -45,9 +50,11 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
   w.dcp_lstm = take(T * B * C); w.dcp_smooth = take(T * B * C);
   w.dc = take(B * H);
   w.partial = take((int64_t)paule_plan_loss_scratch_floats(T, B));
-  const size_t xb = (math != PAULE_MATH_FP32) ? paule_tc_rnn_xchg_bytes(B) : 0;
-  w.xchg = (base && xb) ? reinterpret_cast<void*>(reinterpret_cast<float*>(base) + off) : nullptr;
-  off += align_up((xb + 3) / 4, 64);
+  if (math != PAULE_MATH_FP32) {
+    w.xchg = take_bytes(paule_tc_rnn_xchg_bytes(B));
+    w.h_img = take_bytes(paule_tc_img_seq_bytes(Tm, B, 1));    // h_0 of every mel frame: A operand of Xp1 = h_0 W_ih1^T
+    w.da_img = take_bytes(paule_tc_img_seq_bytes(T, B, 4));    // dA of the layer being back-propagated (reused by all three)
+  }
   w.floats = off;
   return w;
 }
@@ -56,64 +63,64 @@ int check_plan(const paule_plan* p) {
   PAULE_REQUIRE(p != nullptr);
   PAULE_REQUIRE(p->B > 0 && p->T >= 13 && p->H > 0 && p->C > 0 && p->Cm > 0 && p->S > 0);
   PAULE_REQUIRE(p->objective >= 0 && p->objective <= 2);
-  PAULE_REQUIRE(p->math >= PAULE_MATH_FP32 && p->math <= PAULE_MATH_BF16X3);
+  PAULE_REQUIRE(p->math == PAULE_MATH_FP32 || p->math == PAULE_MATH_BF16);
   PAULE_REQUIRE(p->fwd.w_ih && p->fwd.w_hh && p->fwd.w_ih_t && p->fwd.w_hh_t && p->fwd.bias);
   PAULE_REQUIRE(p->emb0.w_ih && p->emb0.w_hh && p->emb0.w_ih_t && p->emb0.w_hh_t && p->emb0.bias);
   PAULE_REQUIRE(p->emb1.w_ih && p->emb1.w_hh && p->emb1.w_ih_t && p->emb1.w_hh_t && p->emb1.bias);
   PAULE_REQUIRE(p->fwd.input_size == p->C && p->emb0.input_size == p->Cm && p->emb1.input_size == p->H);
   PAULE_REQUIRE(p->post_w && p->post_w_t && p->post_b && p->head_w && p->head_w_t && p->head_b);
   PAULE_REQUIRE(p->cp && p->target_mel && p->pred_mel && p->pred_sv && p->workspace);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(p->workspace) % 256 == 0);
   PAULE_REQUIRE(p->workspace_bytes >= paule_plan_workspace_bytes(p->B, p->T, p->H, p->C, p->Cm, p->S, p->math));
   if (p->math != PAULE_MATH_FP32) {
-    PAULE_REQUIRE(p->fwd.packed && p->emb0.packed && p->emb1.packed);
     if (p->H != 720) return PAULE_ERR_UNSUPPORTED;
+    PAULE_REQUIRE(p->fwd.packed && p->emb0.packed && p->emb1.packed);
+    PAULE_REQUIRE(p->emb1.packed_ih && p->fwd.packed_ih_t && p->emb0.packed_ih_t && p->emb1.packed_ih_t);
   }
   return PAULE_OK;
 }
 
-// one LSTM layer forward on time-major data: input projection GEMM, then the recurrence
-int layer_forward(const paule_plan* p, const paule_lstm_layer& L, const float* x, int64_t x_inner,
-                  int64_t x_outer_stride, int64_t x_inner_stride, int64_t steps, float* gates, float* h, float* c,
-                  void* xchg, paule_stream_t s) {
-  const int64_t B = p->B, H = p->H, M = steps * B;
-  const bool tc = p->math != PAULE_MATH_FP32;
-  if (kUseTcGemm && tc && L.input_size % 16 == 0 && L.input_size >= 256 && x_inner == 1 && x_outer_stride == L.input_size) {
-    PAULE_TRY(paule_tc_gemm_nt(x, L.w_ih, L.bias, gates, M, 4 * H, L.input_size, p->math, 0, s));
-  } else {
-    PAULE_TRY(paule_linear_f32(x, L.w_ih, L.bias, gates, M, 4 * H, L.input_size, x_inner, x_outer_stride,
-                               x_inner_stride, 0, 1, 4 * H, 0, 0, s));
-  }
-  if (tc) return paule_tc_lstm_seq_fwd(gates, L.packed, h, c, xchg, steps, B, p->math, s);
-  return paule_lstm_seq_fwd_f32(gates, L.w_hh, h, c, steps, B, H, s);
+inline bool tc(const paule_plan* p) { return p->math != PAULE_MATH_FP32; }
+
+// recurrence of one layer on time-major data; gates already holds x W_ih^T + b
+int recur_forward(const paule_plan* p, const paule_lstm_layer& L, int64_t steps, float* gates, float* h, float* c,
+                  const Workspace& w, void* h_img, paule_stream_t s) {
+  if (tc(p)) return paule_tc_lstm_seq_fwd(gates, L.packed, h, c, w.xchg, h_img, steps, p->B, p->math, s);
+  return paule_lstm_seq_fwd_f32(gates, L.w_hh, h, c, steps, p->B, p->H, s);
 }
 
+// BPTT of one layer followed by dX = dA W_ih (dA [M,4H] x w_ih_t [I,4H]^T)
 int layer_backward(const paule_plan* p, const paule_lstm_layer& L, float* gates, const float* c, const float* dh_seq,
-                   int dh_mode, const float* dh_last, int64_t steps, const Workspace& w, paule_stream_t s) {
-  if (p->math != PAULE_MATH_FP32)
-    return paule_tc_lstm_seq_bwd(gates, c, L.packed, dh_seq, dh_mode, dh_last, w.xchg, steps, p->B, p->math, s);
-  return paule_lstm_seq_bwd_f32(gates, c, L.w_hh_t, dh_seq, dh_mode, dh_last, w.dc, steps, p->B, p->H, s);
-}
-
-// dX = dA W_ih  as  dA [M,4H] x w_ih_t[I,4H]^T
-int input_grad(const paule_plan* p, const paule_lstm_layer& L, const float* da, float* dx, int64_t M, int accumulate,
-               paule_stream_t s) {
-  const int64_t H = p->H, I = L.input_size;
-  if (kUseTcGemm && p->math != PAULE_MATH_FP32 && I % 16 == 0 && I >= 256)
-    return paule_tc_gemm_nt(da, L.w_ih_t, nullptr, dx, M, I, 4 * H, p->math, accumulate, s);
-  return paule_linear_f32(da, L.w_ih_t, nullptr, dx, M, I, 4 * H, 1, 4 * H, 0, 0, 1, I, 0, accumulate, s);
+                   int dh_mode, const float* dh_last, int64_t steps, float* dx, int accumulate, const Workspace& w,
+                   paule_stream_t s) {
+  const int64_t B = p->B, H = p->H, I = L.input_size;
+  if (tc(p)) {
+    PAULE_TRY(paule_tc_lstm_seq_bwd(gates, c, L.packed, dh_seq, dh_mode, dh_last, w.xchg, w.da_img, steps, B, p->math, s));
+    return paule_tc_gemm_img(w.da_img, L.packed_ih_t, nullptr, dx, steps, B, I, 4, accumulate, s);
+  }
+  PAULE_TRY(paule_lstm_seq_bwd_f32(gates, c, L.w_hh_t, dh_seq, dh_mode, dh_last, w.dc, steps, B, H, s));
+  return paule_linear_f32(gates, L.w_ih_t, nullptr, dx, steps * B, I, 4 * H, 1, 4 * H, 0, 0, 1, I, 0, accumulate, s);
 }
 
 int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s) {
   const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, C = p->C, Cm = p->Cm, S = p->S;
-  // ForwardModel (models.py:348-356)
-  PAULE_TRY(layer_forward(p, p->fwd, p->cp, 1, C, 0, T, w.gates_f, w.h_f, w.c_f, w.xchg, s));
+  // ForwardModel (models.py:348-356): K = 30 input projection, recurrence
+  PAULE_TRY(paule_linear_f32(p->cp, p->fwd.w_ih, p->fwd.bias, w.gates_f, T * B, 4 * H, C, 1, C, 0, 0, 1, 4 * H, 0, 0, s));
+  PAULE_TRY(recur_forward(p, p->fwd, T, w.gates_f, w.h_f, w.c_f, w, nullptr, s));
   // post_linear + AvgPool1d(2,2): pool the pair of frames on load (the pool commutes with the Linear)
   PAULE_TRY(paule_linear_f32(w.h_f, p->post_w, p->post_b, p->pred_mel, Tm * B, Cm, H, B, 2 * B * H, H, B * H, 1, Cm, 0,
                              0, s));
   if (!need_semvec) return PAULE_OK;
   // EmbeddingModel (models.py:440-448), lens = Tm for every word (paule.py:922-924)
-  PAULE_TRY(layer_forward(p, p->emb0, p->pred_mel, 1, Cm, 0, Tm, w.gates_0, w.h_0, w.c_0, w.xchg, s));
-  PAULE_TRY(layer_forward(p, p->emb1, w.h_0, 1, H, 0, Tm, w.gates_1, w.h_1, w.c_1, w.xchg, s));
+  PAULE_TRY(paule_linear_f32(p->pred_mel, p->emb0.w_ih, p->emb0.bias, w.gates_0, Tm * B, 4 * H, Cm, 1, Cm, 0, 0, 1, 4 * H,
+                             0, 0, s));
+  PAULE_TRY(recur_forward(p, p->emb0, Tm, w.gates_0, w.h_0, w.c_0, w, w.h_img, s));
+  if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
+    PAULE_TRY(paule_tc_gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, s));
+  } else {
+    PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
+  }
+  PAULE_TRY(recur_forward(p, p->emb1, Tm, w.gates_1, w.h_1, w.c_1, w, nullptr, s));
   PAULE_TRY(paule_linear_f32(w.h_1 + (Tm - 1) * B * H, p->head_w, p->head_b, p->pred_sv, B, S, H, 1, H, 0, 0, 1, S, 0,
                              0, s));
   return PAULE_OK;
@@ -150,15 +157,12 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
   if (use_sem) {                                                                   // discrepancy.backward(), :1052
     // head: dh1[Tm-1] = dsv W_head
     PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));
-    PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w, s));
-    PAULE_TRY(input_grad(p, p->emb1, w.gates_1, w.dh0, Tm * B, 0, s));
-    PAULE_TRY(layer_backward(p, p->emb0, w.gates_0, w.c_0, w.dh0, 1, nullptr, Tm, w, s));
-    PAULE_TRY(input_grad(p, p->emb0, w.gates_0, w.dmel, Tm * B, 1, s));           // += d(mel loss)/dmel
+    PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, s));
+    PAULE_TRY(layer_backward(p, p->emb0, w.gates_0, w.c_0, w.dh0, 1, nullptr, Tm, w.dmel, 1, w, s));  // += d(mel loss)/dmel
   }
   // post_linear^T; the un-pooling (x0.5 to both frames of a pair) is folded into the BPTT's dh load
   PAULE_TRY(paule_linear_f32(w.dmel, p->post_w_t, nullptr, w.dhp, Tm * B, H, Cm, 1, Cm, 0, 0, 1, H, 0, 0, s));
-  PAULE_TRY(layer_backward(p, p->fwd, w.gates_f, w.c_f, w.dhp, 2, nullptr, T, w, s));
-  PAULE_TRY(input_grad(p, p->fwd, w.gates_f, w.dcp_lstm, T * B, 0, s));
+  PAULE_TRY(layer_backward(p, p->fwd, w.gates_f, w.c_f, w.dhp, 2, nullptr, T, w.dcp_lstm, 0, w, s));
   // optimizer.step() + clamp + smiling + past_cp (paule.py:1199-1211)
   PAULE_TRY(adam_clamp_logged(p->cp, w.dcp_lstm, w.dcp_smooth, p->adam_m, p->adam_v, p->step_count, p->lr, p->beta1,
                               p->beta2, p->eps, p->clamp, p->smiling, p->past_cp, p->past_T, p->grad_out, T, B, C, s));

@@ -1,0 +1,234 @@
+// Batched gate GEMMs on tcgen05 (sm_100a): the "GEMMs over all timesteps" of the planning step.
+//
+//   C[(t, b), n] (+)= sum_k A[(t, b), k] * W[n, k] + bias[n]          M = steps x words, fp32 output
+//
+//   * embedder layer-1 input projection   Xp1 = h0 W_ih1^T + b      (K = 720,  N = 2880)     [K5 of SURVEY 2.2]
+//   * BPTT input gradients                dX  = dA  W_ih            (K = 2880, N = 720/60/30) [K8]
+//
+//   A is never re-laid-out: the persistent-RNN kernels already wrote h_t (forward) / dA_t (backward) as bf16 UMMA
+//   images, one per time step and 64-word group ([k-blocks][64 rows][128 B], SWIZZLE_128B).  An M = 128 tile is two
+//   consecutive time steps of one group, fetched with two 8 KB TMA bulk copies per 64-wide k-block; W comes from a
+//   pre-packed bf16 image.  Warp-specialised, persistent over output tiles:
+//     warp 0  TMA producer  (4-stage ring of {A 16 KB, B BN x 128 B}, full/empty mbarriers)
+//     warp 1  MMA issuer    (tcgen05.mma M=128, N=BN, K=16; tcgen05.commit frees the stage / publishes the accumulator)
+//     warps 2-5 epilogue    (tcgen05.ld 32 columns at a time, + bias, fp32 rows straight to HBM)
+//   with two TMEM accumulator buffers (2 x 256 columns) so that the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_lstm.cuh"
+
+namespace paule {
+namespace tc {
+
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kSegLen = kH;          // real columns per K segment
+constexpr int kSegPad = kKPad;       // padded columns per K segment (12 k-blocks)
+
+// largest tile width <= 256 that is a multiple of 16 and divides the padded N
+__host__ __device__ inline int pick_bn(int n_pad) {
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (n_pad % bn == 0) return bn;
+  return 16;
+}
+__host__ __device__ inline int pad_n(int n) { return (n + 15) / 16 * 16; }
+
+// W [N, nseg*720] fp32 row-major -> image [n_tile][kb (nseg*12)][BN rows][128 B], zero padded
+__global__ void pack_gemm_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int N, int nseg, int BN) {
+  const int KB = nseg * kNumKB;
+  const int nt = blockIdx.x;
+  const size_t tile_bytes = (size_t)KB * BN * 128;
+  for (int e = threadIdx.x; e < BN * nseg * kSegPad; e += blockDim.x) {
+    const int r = e / (nseg * kSegPad), kp = e % (nseg * kSegPad);
+    const int seg = kp / kSegPad, ks = kp % kSegPad;
+    const int n = nt * BN + r;
+    const float v = (n < N && ks < kSegLen) ? W[(size_t)n * (nseg * kSegLen) + seg * kSegLen + ks] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(img + (size_t)nt * tile_bytes + umma_offset(BN, r, kp)) = __float2bfloat16_rn(v);
+  }
+}
+
+struct GemmBars {
+  uint64_t full[kGemmStages];
+  uint64_t empty[kGemmStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, const float* __restrict__ bias,
+                   float* __restrict__ C, int steps, int B, int N, int KB, int BN, int accumulate) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = 16384u + (uint32_t)BN * 128u;   // A [128 x 128 B] + B [BN x 128 B]; BN % 8 == 0 keeps 1 KB alignment
+  GemmBars& bars = *reinterpret_cast<GemmBars*>(base + (size_t)kGemmStages * stage_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  volatile int dummy_err = 0;
+  volatile int* err = &dummy_err;
+
+  const int n_groups = (B + kRows - 1) / kRows;
+  const int n_pairs = (steps + 1) / 2;
+  const int n_nt = pad_n(N) / BN;
+  const int total = n_groups * n_pairs * n_nt;
+
+  if (tid == 0) {
+    for (int i = 0; i < kGemmStages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tmem_full[i], 1); mbar_init(&bars.tmem_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&bars.tmem_base);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int nt = tile % n_nt, rest = tile / n_nt, sp = rest % n_pairs, grp = rest / n_pairs;
+        const int t0 = 2 * sp;
+        const bool two = (t0 + 1 < steps);
+        const uint8_t* a0 = a_img + ((size_t)(grp * steps + t0) * KB) * (kRows * 128);
+        const uint8_t* bt = b_img + (size_t)nt * KB * BN * 128;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&bars.empty[s], ph ^ 1u, err);
+          uint8_t* sa = base + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&bars.full[s], (two ? 16384u : 8192u) + (uint32_t)BN * 128u);
+          bulk_g2s(sa, a0 + (size_t)kb * (kRows * 128), kRows * 128, &bars.full[s]);
+          if (two) bulk_g2s(sa + 8192, a0 + ((size_t)KB + kb) * (kRows * 128), kRows * 128, &bars.full[s]);
+          bulk_g2s(sa + 16384, bt + (size_t)kb * BN * 128, (uint32_t)BN * 128u, &bars.full[s]);
+          if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
+        const int ab = local & 1;
+        mbar_wait(&bars.tmem_empty[ab], (uint32_t)(((local >> 1) & 1) ^ 1), err);   // epilogue drained this buffer
+        tcgen05_fence_after();
+        const uint32_t d = tmem + (uint32_t)(ab * 256);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&bars.full[s], ph, err);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + 16384u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&bars.empty[s]);          // stage reusable once these MMAs have read it
+          if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(&bars.tmem_full[ab]);       // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> HBM =====================
+    const int lg = warp & 3;                     // TMEM lane group this warp may access
+    const int r = lg * 32 + lane;                // tile row: two time steps x 64 words
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
+      const int nt = tile % n_nt, rest = tile / n_nt, sp = rest % n_pairs, grp = rest / n_pairs;
+      const int ab = local & 1;
+      const int t = 2 * sp + (r >> 6), b = grp * kRows + (r & 63);
+      const bool valid = (t < steps) && (b < B);
+      mbar_wait(&bars.tmem_full[ab], (uint32_t)((local >> 1) & 1), err);
+      tcgen05_fence_after();
+      float* crow = C + ((size_t)t * B + (valid ? b : 0)) * N;
+      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * 256);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        if (BN - c0 >= 32) {
+          tmem_ld_x32(taddr + (uint32_t)c0, v);
+        } else {   // BN is a multiple of 16: one 16-column tail
+          float v16[16];
+          tmem_ld_x16(taddr + (uint32_t)c0, v16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0.f; }
+        }
+        if (valid) {
+          const int n0 = nt * BN + c0;
+          const int lim = (BN - c0 >= 32) ? 32 : 16;
+          if (n0 + lim <= N && (N & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (i >= lim) break;
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (bias) { o.x += __ldg(bias + n0 + i); o.y += __ldg(bias + n0 + i + 1); o.z += __ldg(bias + n0 + i + 2); o.w += __ldg(bias + n0 + i + 3); }
+              float4* dst = reinterpret_cast<float4*>(crow + n0 + i);
+              if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+              *dst = o;
+            }
+          } else {
+            for (int i = 0; i < lim; ++i) {
+              const int n = n0 + i;
+              if (n >= N) break;
+              float o = v[i] + (bias ? __ldg(bias + n) : 0.f);
+              if (accumulate) o += crow[n];
+              crow[n] = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.tmem_empty[ab]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace tc
+}  // namespace paule
+
+using namespace paule;
+using namespace paule::tc;
+
+extern "C" size_t paule_tc_gemm_packed_bytes(int64_t N, int64_t nseg) {
+  if (N <= 0 || nseg <= 0) return 0;
+  return (size_t)pad_n((int)N) * (size_t)nseg * kSegPad * 2;
+}
+
+extern "C" int paule_tc_gemm_pack(const float* W, void* packed, int64_t N, int64_t nseg, paule_stream_t stream) {
+  PAULE_REQUIRE(W && packed && N > 0 && nseg > 0 && nseg <= 4);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0);
+  const int np = pad_n((int)N), bn = pick_bn(np);
+  pack_gemm_b_kernel<<<np / bn, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed), (int)N, (int)nseg, bn);
+  PAULE_LAUNCH_CHECK("pack_gemm_b_kernel");
+  return PAULE_OK;
+}
+
+extern "C" int paule_tc_gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps,
+                                 int64_t B, int64_t N, int64_t nseg, int accumulate, paule_stream_t stream) {
+  PAULE_REQUIRE(a_img && packed_b && C && steps >= 0 && B > 0 && N > 0 && nseg > 0 && nseg <= 4);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(a_img) % 16 == 0 && reinterpret_cast<uintptr_t>(packed_b) % 16 == 0);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(C) % 16 == 0);
+  if (steps == 0) return PAULE_OK;
+  const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
+  const int n_groups = (int)((B + kRows - 1) / kRows), n_pairs = (int)((steps + 1) / 2);
+  const int64_t total = (int64_t)n_groups * n_pairs * (np / bn);
+  const int smem = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  const int grid = (int)((total < (int64_t)sm_count()) ? total : (int64_t)sm_count());
+  tc_gemm_img_kernel<<<grid, kGemmThreads, (size_t)smem, as_stream(stream)>>>(
+      reinterpret_cast<const uint8_t*>(a_img), reinterpret_cast<const uint8_t*>(packed_b), bias, C, (int)steps, (int)B,
+      (int)N, KB, bn, accumulate);
+  PAULE_LAUNCH_CHECK("tc_gemm_img_kernel");
+  return PAULE_OK;
+}

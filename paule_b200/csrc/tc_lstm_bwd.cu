@@ -57,7 +57,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed_bwd,
                    const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
-                   uint8_t* __restrict__ xchg, int T, int B, int Bs) {
+                   uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int B, int Bs) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,7 +65,10 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
   const int ug = blockIdx.x >> 2;                  // unit group: hidden units [32ug, 32ug+32)
   unsigned int* counter = reinterpret_cast<unsigned int*>(xchg);
   volatile int* err = reinterpret_cast<volatile int*>(xchg + 4);
-  uint8_t* img = xchg + kXchgHeader;               // [2][4 gates] UMMA images
+  // dA_t images, four (one per gate) per step: kept for every step when the caller wants them (A operand of the dX
+  // GEMM), otherwise two ping-pong sets inside the exchange buffer
+  uint8_t* img = img_seq ? img_seq : xchg + kXchgHeader;
+  const int img_mask = img_seq ? 0x7fffffff : 1;
 
   if (tid == 0) {
     for (int i = 0; i < kNumKB; ++i) mbar_init(&S.full[i], 1);
@@ -94,7 +97,7 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
       __syncwarp();
       if (lane < kNumKB) {
         fence_proxy_async();
-        const uint8_t* src = img + (size_t)(((t + 1) & 1) * 4 + g) * kXchgImageBytes;
+        const uint8_t* src = img + (size_t)(((t + 1) & img_mask) * 4 + g) * kXchgImageBytes;
         mbar_arrive_expect_tx(&S.full[kb], kRows * 128);
         bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[kb]);
       }
@@ -194,14 +197,16 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
         dc[0] = dc0 * s_f.x;
         dc[1] = dc1 * s_f.y;
       }
-      if (t > 0) {
+      if (t > 0 || img_seq != nullptr) {
         if (valid) {   // bf16 da_t into the four gate images: on the critical path of the next step
-          uint8_t* dst = img + (size_t)((t & 1) * 4) * kXchgImageBytes + xo;
+          uint8_t* dst = img + (size_t)((t & img_mask) * 4) * kXchgImageBytes + xo;
           *reinterpret_cast<__nv_bfloat162*>(dst + 0 * (size_t)kXchgImageBytes) = __floats2bfloat162_rn(d_i.x, d_i.y);
           *reinterpret_cast<__nv_bfloat162*>(dst + 1 * (size_t)kXchgImageBytes) = __floats2bfloat162_rn(d_f.x, d_f.y);
           *reinterpret_cast<__nv_bfloat162*>(dst + 2 * (size_t)kXchgImageBytes) = __floats2bfloat162_rn(d_g.x, d_g.y);
           *reinterpret_cast<__nv_bfloat162*>(dst + 3 * (size_t)kXchgImageBytes) = __floats2bfloat162_rn(d_o.x, d_o.y);
         }
+      }
+      if (t > 0) {
         named_bar_sync(1, kBwdEpiThreads);
         if (tid == 0) {
           fence_proxy_async();
@@ -229,8 +234,8 @@ using namespace paule;
 using namespace paule::tc;
 
 extern "C" int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* packed, const float* dh_seq,
-                                     int dh_mode, const float* dh_last, void* xchg, int64_t T, int64_t B, int math,
-                                     paule_stream_t stream) {
+                                     int dh_mode, const float* dh_last, void* xchg, void* da_img_seq, int64_t T,
+                                     int64_t B, int math, paule_stream_t stream) {
   PAULE_REQUIRE(gates && c && packed && xchg && T >= 0 && B > 0);
   PAULE_REQUIRE(dh_mode == 0 || ((dh_mode == 1 || dh_mode == 2) && dh_seq));
   PAULE_REQUIRE(math == PAULE_MATH_BF16);
@@ -268,14 +273,16 @@ extern "C" int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* p
   cfg.attrs = attrs;
   cfg.numAttrs = coop_ok ? 2 : 1;
   uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, (int)T, Bi, (int)B);
+  uint8_t* is = da_img_seq ? reinterpret_cast<uint8_t*>(da_img_seq) + (size_t)(r0 / kRows) * (size_t)T * 4 * kXchgImageBytes
+                           : nullptr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bi, (int)B);
   if (e != cudaSuccess && coop_ok) {
     // some driver/toolkit combinations reject cooperative + cluster launches: 92 CTAs (23 clusters) fit the 148 SMs
     // at one CTA per SM, so all CTAs are co-resident on an otherwise idle stream; the watchdog guards the rest.
     cudaGetLastError();
     coop_ok = 0;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, (int)T, Bi, (int)B);
+    e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bi, (int)B);
   }
   PAULE_CUDA(e);
   }

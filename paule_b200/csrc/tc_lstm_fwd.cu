@@ -81,13 +81,17 @@ constexpr int kFwdThreads = kEpiThreads + 32 + 32 * kMmaWarps;   // + producer w
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed, float* __restrict__ h_out,
-                   float* __restrict__ c_out, uint8_t* __restrict__ xchg, int T, int B, int Bs) {
+                   float* __restrict__ c_out, uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int B,
+                   int Bs) {
   extern __shared__ uint8_t smem_raw[];
   FwdSmem& S = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned int* counter = reinterpret_cast<unsigned int*>(xchg);
   volatile int* err = reinterpret_cast<volatile int*>(xchg + 4);
-  uint8_t* hbuf = xchg + kXchgHeader;     // two UMMA images [12][64][128 B]
+  // h_t images [12][64][128 B]: one per time step when the caller keeps them (they are the A operand of the next
+  // layer's input-projection GEMM), otherwise two ping-pong images inside the exchange buffer
+  uint8_t* hbuf = img_seq ? img_seq : xchg + kXchgHeader;
+  const int img_mask = img_seq ? 0x7fffffff : 1;
 
   if (tid == 0) {
     for (int i = 0; i < kNumKB; ++i) mbar_init(&S.full[i], 1);
@@ -118,7 +122,7 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
       TRACE(0)
       if (lane < kNumKB) {
         fence_proxy_async();
-        const uint8_t* src = hbuf + (size_t)((t - 1) & 1) * kXchgImageBytes;
+        const uint8_t* src = hbuf + (size_t)((t - 1) & img_mask) * kXchgImageBytes;
         mbar_arrive_expect_tx(&S.full[kb], kRows * 128);
         bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[kb]);
       }
@@ -225,7 +229,7 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
       }
       if (valid) {
         // h_t as bf16 into the UMMA image the next step bulk-copies: first, it is on the critical path
-        *reinterpret_cast<__nv_bfloat162*>(hbuf + (size_t)(t & 1) * kXchgImageBytes + xo) =
+        *reinterpret_cast<__nv_bfloat162*>(hbuf + (size_t)(t & img_mask) * kXchgImageBytes + xo) =
             __floats2bfloat162_rn(hv[0], hv[1]);
       }
       TRACE(2)
@@ -300,8 +304,13 @@ extern "C" size_t paule_tc_rnn_xchg_bytes(int64_t B) {
   return (size_t)kXchgHeader + (size_t)8 * kXchgImageBytes;
 }
 
-extern "C" int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h, float* c, void* xchg, int64_t T,
-                                     int64_t B, int math, paule_stream_t stream) {
+extern "C" size_t paule_tc_img_seq_bytes(int64_t T, int64_t B, int64_t images_per_step) {
+  if (T <= 0 || B <= 0 || images_per_step <= 0) return 0;
+  return (size_t)((B + kRows - 1) / kRows) * (size_t)T * (size_t)images_per_step * kXchgImageBytes;
+}
+
+extern "C" int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq,
+                                     int64_t T, int64_t B, int math, paule_stream_t stream) {
   PAULE_REQUIRE(gates && packed && h && c && xchg && T >= 0 && B > 0);
   PAULE_REQUIRE(math == PAULE_MATH_BF16);
   if (T == 0) return PAULE_OK;
@@ -322,8 +331,10 @@ extern "C" int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h,
     float* hp = h + r0 * kH;
     float* cp = c + r0 * kH;
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
+    uint8_t* is = h_img_seq ? reinterpret_cast<uint8_t*>(h_img_seq) + (size_t)(r0 / kRows) * (size_t)T * kXchgImageBytes
+                            : nullptr;
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
-    void* args[] = {&gp, &pk, &hp, &cp, &xc, &Ti, &Bi, &Bsi};
+    void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bi, &Bsi};
     PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd_kernel, dim3(kFwdCtas), dim3(kFwdThreads), args,
                                            (size_t)smem, s));
   }

@@ -79,7 +79,9 @@ class LstmWeights:
         self.bias = (b_ih.detach().float() + b_hh.detach().float()).contiguous()
         self.hidden = self.w_hh.shape[1]
         self.input_size = self.w_ih.shape[1]
-        self.packed: Optional[torch.Tensor] = None
+        self.packed: Optional[torch.Tensor] = None        # W_hh images of the persistent-RNN kernels
+        self.packed_ih: Optional[torch.Tensor] = None     # W_ih image   (input-projection GEMM, only if I == H)
+        self.packed_ih_t: Optional[torch.Tensor] = None   # W_ih^T image (dX GEMM)
         if tc:
             self.pack_tc()
 
@@ -91,10 +93,19 @@ class LstmWeights:
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.w_hh.device)
         _lib.check(lib.paule_tc_pack_lstm(self.w_ih.data_ptr(), self.w_hh.data_ptr(), self.packed.data_ptr(),
                                           self.hidden, self.input_size, _stream()), "paule_tc_pack_lstm")
+        dev = self.w_hh.device
+        if self.input_size == self.hidden:
+            self.packed_ih = torch.empty(lib.paule_tc_gemm_packed_bytes(4 * self.hidden, 1), dtype=torch.uint8, device=dev)
+            _lib.check(lib.paule_tc_gemm_pack(self.w_ih.data_ptr(), self.packed_ih.data_ptr(), 4 * self.hidden, 1,
+                                              _stream()), "paule_tc_gemm_pack")
+        self.packed_ih_t = torch.empty(lib.paule_tc_gemm_packed_bytes(self.input_size, 4), dtype=torch.uint8, device=dev)
+        _lib.check(lib.paule_tc_gemm_pack(self.w_ih_t.data_ptr(), self.packed_ih_t.data_ptr(), self.input_size, 4,
+                                          _stream()), "paule_tc_gemm_pack")
 
     def as_struct(self) -> _lib.LstmLayer:
         return _lib.LstmLayer(self.w_ih.data_ptr(), self.w_hh.data_ptr(), self.w_ih_t.data_ptr(),
-                              self.w_hh_t.data_ptr(), self.bias.data_ptr(), _p(self.packed), self.input_size)
+                              self.w_hh_t.data_ptr(), self.bias.data_ptr(), _p(self.packed), _p(self.packed_ih),
+                              _p(self.packed_ih_t), self.input_size)
 
 
 # ------------------------------------------------------------------------------------------------

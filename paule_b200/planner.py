@@ -80,7 +80,8 @@ class BatchPlanner:
         self.grad_out = torch.empty_like(self.cp) if log_gradients else None
         lib = _lib.load()
         ws_bytes = lib.paule_plan_workspace_bytes(B, T, H, C, Cm, S, math)
-        self.workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        # zero-filled ONCE: the pad rows / pad columns of the bf16 operand images inside must be exact zeros
+        self.workspace = torch.zeros(ws_bytes, device=dev, dtype=torch.uint8)
         self.target_sv = torch.zeros((B, S), **f32)
         self.hp = dict(lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8, clamp=1.05)
         self.smiling, self.log_semantics = bool(smiling), bool(log_semantics)

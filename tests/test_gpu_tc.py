@@ -40,7 +40,7 @@ def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
     g1, h1, c1 = xp.clone(), torch.zeros(T, B, H, device=dev), torch.zeros(T, B, H, device=dev)
     xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
     _lib.check(lib.paule_tc_lstm_seq_fwd(g1.data_ptr(), w.packed.data_ptr(), h1.data_ptr(), c1.data_ptr(),
-                                         xchg.data_ptr(), T, B, 1, st))
+                                         xchg.data_ptr(), None, T, B, 1,st))
     torch.cuda.synchronize()
     assert _status(xchg) == 0, "persistent kernel watchdog fired"
     np.testing.assert_allclose(h1.cpu().numpy(), h0.cpu().numpy(), atol=2e-3)
@@ -55,7 +55,7 @@ def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
                                           dh_last.data_ptr(), scratch.data_ptr(), T, B, H, st))
     d1 = g0.clone()
     _lib.check(lib.paule_tc_lstm_seq_bwd(d1.data_ptr(), c0.data_ptr(), w.packed.data_ptr(), dh_seq.data_ptr(), 2,
-                                         dh_last.data_ptr(), xchg.data_ptr(), T, B, 1, st))
+                                         dh_last.data_ptr(), xchg.data_ptr(), None, T, B, 1,st))
     torch.cuda.synchronize()
     assert _status(xchg) == 0, "persistent kernel watchdog fired"
     scale = d0.abs().max().item()
@@ -66,7 +66,7 @@ def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
     _lib.check(lib.paule_lstm_seq_bwd_f32(d0.data_ptr(), c0.data_ptr(), w.w_hh_t.data_ptr(), dh_full.data_ptr(), 1, None,
                                           scratch.data_ptr(), T, B, H, st))
     _lib.check(lib.paule_tc_lstm_seq_bwd(d1.data_ptr(), c0.data_ptr(), w.packed.data_ptr(), dh_full.data_ptr(), 1, None,
-                                         xchg.data_ptr(), T, B, 1, st))
+                                         xchg.data_ptr(), None, T, B, 1,st))
     torch.cuda.synchronize()
     np.testing.assert_allclose(d1.cpu().numpy(), d0.cpu().numpy(), atol=2e-2 * d0.abs().max().item())
 
@@ -82,7 +82,53 @@ def test_tc_is_deterministic_and_repeatable(setup):
         g1, h1, c1 = xp.clone(), torch.zeros(T, B, H, device=dev), torch.zeros(T, B, H, device=dev)
         xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
         _lib.check(lib.paule_tc_lstm_seq_fwd(g1.data_ptr(), w.packed.data_ptr(), h1.data_ptr(), c1.data_ptr(),
-                                             xchg.data_ptr(), T, B, 1, ops._stream()))
+                                             xchg.data_ptr(), None, T, B, 1,ops._stream()))
         torch.cuda.synchronize()
         outs.append(h1)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("B,T", [(64, 10), (37, 7), (100, 5)])
+def test_tc_gemm_over_image_sequences(setup, B, T):
+    """paule_tc_gemm_img on the bf16 images a persistent kernel left behind == fp32 GEMM on the fp32 tensors
+    (K = 720 input projection with bias; K = 2880 dX with N = 720 / 60 / 30, overwrite and accumulate)."""
+    from paule_b200 import _lib, ops
+    dev, lib, w = setup
+    H = 720
+    g = torch.Generator(device="cpu").manual_seed(B + T)
+    st = ops._stream()
+    # forward images of h
+    xp = (torch.randn(T, B, 4 * H, generator=g) * 0.5).to(dev)
+    gates, h, c = xp.clone(), torch.zeros(T, B, H, device=dev), torch.zeros(T, B, H, device=dev)
+    xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
+    himg = torch.zeros(lib.paule_tc_img_seq_bytes(T, B, 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.paule_tc_lstm_seq_fwd(gates.data_ptr(), w.packed.data_ptr(), h.data_ptr(), c.data_ptr(),
+                                         xchg.data_ptr(), himg.data_ptr(), T, B, 1, st))
+    W = (torch.randn(4 * H, H, generator=g) / H ** 0.5).to(dev)
+    bias = torch.randn(4 * H, generator=g).to(dev)
+    pk = torch.empty(lib.paule_tc_gemm_packed_bytes(4 * H, 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.paule_tc_gemm_pack(W.data_ptr(), pk.data_ptr(), 4 * H, 1, st))
+    out = torch.full((T, B, 4 * H), float("nan"), device=dev)
+    _lib.check(lib.paule_tc_gemm_img(himg.data_ptr(), pk.data_ptr(), bias.data_ptr(), out.data_ptr(), T, B, 4 * H, 1, 0, st))
+    torch.cuda.synchronize()
+    ref = h.double() @ W.double().t() + bias.double()
+    np.testing.assert_allclose(out.cpu().double().numpy(), ref.cpu().numpy(), atol=1e-2, rtol=1e-2)
+    # backward images of dA, three widths of W_ih^T
+    dh = (torch.randn(T, B, H, generator=g) * 1e-2).to(dev)
+    da = gates.clone()
+    daimg = torch.zeros(lib.paule_tc_img_seq_bytes(T, B, 4), dtype=torch.uint8, device=dev)
+    _lib.check(lib.paule_tc_lstm_seq_bwd(da.data_ptr(), c.data_ptr(), w.packed.data_ptr(), dh.data_ptr(), 1, None,
+                                         xchg.data_ptr(), daimg.data_ptr(), T, B, 1, st))
+    for N in (720, 60, 30):
+        Wt = (torch.randn(N, 4 * H, generator=g) / H ** 0.5).to(dev)
+        pk2 = torch.empty(lib.paule_tc_gemm_packed_bytes(N, 4), dtype=torch.uint8, device=dev)
+        _lib.check(lib.paule_tc_gemm_pack(Wt.data_ptr(), pk2.data_ptr(), N, 4, st))
+        base = torch.randn(T, B, N, generator=g).to(dev)
+        o1, o2 = torch.full((T, B, N), float("nan"), device=dev), base.clone()
+        _lib.check(lib.paule_tc_gemm_img(daimg.data_ptr(), pk2.data_ptr(), None, o1.data_ptr(), T, B, N, 4, 0, st))
+        _lib.check(lib.paule_tc_gemm_img(daimg.data_ptr(), pk2.data_ptr(), None, o2.data_ptr(), T, B, N, 4, 1, st))
+        torch.cuda.synchronize()
+        ref = da.double() @ Wt.double().t()
+        scale = ref.abs().max().item()
+        np.testing.assert_allclose(o1.cpu().double().numpy(), ref.cpu().numpy(), atol=1e-2 * scale)
+        np.testing.assert_allclose(o2.cpu().double().numpy(), (ref + base.double()).cpu().numpy(), atol=1e-2 * scale + 1e-6)

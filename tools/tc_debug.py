@@ -25,7 +25,7 @@ def fp32_fwd():
 def tc_fwd():
     g = xp.clone(); h = torch.zeros(T, B, H, device=dev); c = torch.zeros(T, B, H, device=dev)
     xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
-    rc = lib.paule_tc_lstm_seq_fwd(g.data_ptr(), w.packed.data_ptr(), h.data_ptr(), c.data_ptr(), xchg.data_ptr(), T, B, 1, st)
+    rc = lib.paule_tc_lstm_seq_fwd(g.data_ptr(), w.packed.data_ptr(), h.data_ptr(), c.data_ptr(), xchg.data_ptr(), None, T, B, 1, st)
     torch.cuda.synchronize()
     print("tc fwd rc", rc, lib.paule_last_cuda_error(), "err flag", xchg[4:8].view(torch.int32).item(), "counter", xchg[0:4].view(torch.int32).item())
     return g, h, c
@@ -50,7 +50,7 @@ def fp32_bwd():
 def tc_bwd():
     da = g0.clone()
     xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
-    rc = lib.paule_tc_lstm_seq_bwd(da.data_ptr(), c0.data_ptr(), w.packed.data_ptr(), dh_seq.data_ptr(), 1, dh_last.data_ptr(), xchg.data_ptr(), T, B, 1, st)
+    rc = lib.paule_tc_lstm_seq_bwd(da.data_ptr(), c0.data_ptr(), w.packed.data_ptr(), dh_seq.data_ptr(), 1, dh_last.data_ptr(), xchg.data_ptr(), None, T, B, 1, st)
     torch.cuda.synchronize()
     print("tc bwd rc", rc, lib.paule_last_cuda_error(), "err flag", xchg[4:8].view(torch.int32).item(), "counter", xchg[0:4].view(torch.int32).item())
     return da
@@ -71,8 +71,8 @@ for name in ("fwd", "bwd"):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         if name == "fwd":
-            lib.paule_tc_lstm_seq_fwd(xpb.data_ptr(), w.packed.data_ptr(), hb.data_ptr(), cb.data_ptr(), xchg.data_ptr(), Tb, 64, 1, st)
+            lib.paule_tc_lstm_seq_fwd(xpb.data_ptr(), w.packed.data_ptr(), hb.data_ptr(), cb.data_ptr(), xchg.data_ptr(), None, Tb, 64, 1, st)
         else:
-            lib.paule_tc_lstm_seq_bwd(xpb.data_ptr(), cb.data_ptr(), w.packed.data_ptr(), dhb.data_ptr(), 1, None, xchg.data_ptr(), Tb, 64, 1, st)
+            lib.paule_tc_lstm_seq_bwd(xpb.data_ptr(), cb.data_ptr(), w.packed.data_ptr(), dhb.data_ptr(), 1, None, xchg.data_ptr(), None, Tb, 64, 1, st)
         e1.record(); torch.cuda.synchronize()
         print(f"tc {name} T={Tb} B=64: {e0.elapsed_time(e1)*1e3/Tb:.2f} us per step; err flag", xchg[4:8].view(torch.int32).item())

@@ -12,7 +12,7 @@ xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(64), dtype=torch.uint8, device=de
 for rep in range(2):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    lib.paule_tc_lstm_seq_fwd(xpb.data_ptr(), w.packed.data_ptr(), hb.data_ptr(), cb.data_ptr(), xchg.data_ptr(), Tb, 64, 1, st)
+    lib.paule_tc_lstm_seq_fwd(xpb.data_ptr(), w.packed.data_ptr(), hb.data_ptr(), cb.data_ptr(), xchg.data_ptr(), None, Tb, 64, 1, st)
     e1.record(); torch.cuda.synchronize()
     print(f"fwd {e0.elapsed_time(e1)*1e3/Tb:.2f} us/step, err", xchg[4:8].view(torch.int32).item())
     tr = xchg[64:64 + 24 * 8].view(torch.int64).cpu().tolist()
