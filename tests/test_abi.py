@@ -18,7 +18,7 @@ def declared_symbols():
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for must in ("paule_plan_step", "paule_plan_forward", "paule_lstm_seq_fwd_f32", "paule_lstm_seq_bwd_f32",
-                 "paule_plan_loss_f32", "paule_adam_clamp_f32", "paule_linear_f32", "paule_tc_gemm_nt",
+                 "paule_plan_loss_f32", "paule_adam_clamp_f32", "paule_linear_f32", "paule_tc_gemm_img", "paule_tc_gemm_pack",
                  "paule_tc_lstm_seq_fwd", "paule_tc_lstm_seq_bwd", "paule_upsample_smooth_f32"):
         assert must in syms
     assert len(syms) >= 24
