@@ -249,7 +249,9 @@ extern "C" int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* p
     attr_set = true;
   }
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + (size_t)kFwdCtas * kFwdSliceBytes;
-  static int coop_ok = 1;   // cooperative + cluster launch accepted by this driver?
+  // cooperative + cluster launch accepted by this driver?  (Nsight Compute rejects the combination with LaunchFailed;
+  // PAULE_NO_COOP_CLUSTER=1 launches with the cluster attribute only -- 92 CTAs always fit the 148 SMs.)
+  static int coop_ok = getenv("PAULE_NO_COOP_CLUSTER") ? 0 : 1;
   // words are independent: batches larger than the UMMA M tile run as consecutive 64-word groups
   for (int64_t r0 = 0; r0 < B; r0 += kRows) {
   PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader + (size_t)8 * kXchgImageBytes, s));
