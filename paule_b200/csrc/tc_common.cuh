@@ -98,6 +98,16 @@ __device__ __forceinline__ void tmem_ld_x16_issue(uint32_t taddr, uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// zero 16 columns of this warp's 32 TMEM lanes (used to re-arm accumulator tiles that several MMA issuers add into)
+__device__ __forceinline__ void tmem_zero_x16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // sum of kTiles accumulator tiles (32 columns apart), 16 columns each, loads batched four at a time
 template <int kTiles>
 __device__ __forceinline__ void tmem_ld_sum_x16(uint32_t taddr, float (&acc)[16]) {
@@ -190,7 +200,38 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// multicast variant: the same bytes land at the same shared-memory offset of every CTA in `cta_mask` of the cluster,
+// and complete_tx is signalled on the mbarrier at the same offset in each of them (one L2 read feeds all).
+__device__ __forceinline__ void bulk_g2s_mcast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank_u32() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Orders this thread's generic-proxy view of GLOBAL memory (the acquire that observed the producers' release) before
+// its subsequent async-proxy (TMA) reads of global memory.  PAULE_PROXY_FENCE: 0 none, 1 .global (default), 2 full.
+#ifndef PAULE_PROXY_FENCE
+#define PAULE_PROXY_FENCE 1
+#endif
+__device__ __forceinline__ void fence_proxy_async_global() {
+#if PAULE_PROXY_FENCE == 1
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+#elif PAULE_PROXY_FENCE == 2
+  asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
 
 // ---- grid barrier: monotonic arrival counter in global memory (zeroed by the host before the launch)
 __device__ __forceinline__ void grid_arrive(unsigned int* counter) {

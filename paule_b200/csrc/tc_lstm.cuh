@@ -24,7 +24,9 @@ constexpr int kBwdCtas = kBwdGroups * 4;              // 92
 constexpr int kBwdSliceBytes = kNumKB * kBwdN * 128;  // 49152
 
 // exchange buffer: header + UMMA images [12][64 rows][128 B]
-constexpr int kXchgHeader = 1024;
+constexpr int kXchgHeader = 4096;   // 12 barrier counters (one 128-byte line per k-block), error flag, trace words
+constexpr int kXchgErrOff = 2048;    // int: 0 ok, 1 grid-barrier watchdog fired, 2 mbarrier watchdog fired
+constexpr int kXchgTraceOff = 3072;  // PAULE_TC_TRACE builds only
 constexpr int kXchgImageBytes = kNumKB * kRows * 128;  // 98304
 
 }  // namespace tc

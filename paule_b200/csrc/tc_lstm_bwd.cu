@@ -63,8 +63,8 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = (int)cluster_ctarank();            // gate handled by this CTA's K slice
   const int ug = blockIdx.x >> 2;                  // unit group: hidden units [32ug, 32ug+32)
-  unsigned int* counter = reinterpret_cast<unsigned int*>(xchg);
-  volatile int* err = reinterpret_cast<volatile int*>(xchg + 4);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(xchg);      // counters[32 * kb]: one 128-byte line per k-block
+  volatile int* err = reinterpret_cast<volatile int*>(xchg + kXchgErrOff);
   // dA_t images, four (one per gate) per step: kept for every step when the caller wants them (A operand of the dX
   // GEMM), otherwise two ping-pong sets inside the exchange buffer
   uint8_t* img = img_seq ? img_seq : xchg + kXchgHeader;
@@ -76,27 +76,27 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
     mbar_init(&S.w_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(&S.tmem_base);    // 12 accumulator tiles x 32 columns
+  if (warp == 9) tmem_alloc<32>(&S.tmem_base);     // ONE accumulator tile that all 12 issuers add into
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = S.tmem_base;
   cluster_sync_all();   // every CTA of the cluster is resident before any DSMEM traffic
 
-  const int q = (int)blockIdx.x;                   // rotation of the k-block order (spreads the L2 reads)
   if (warp == 8) {
     // ===================== producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(&S.w_ready, kBwdSliceBytes);
       bulk_g2s(S.w, packed_bwd + (size_t)blockIdx.x * kBwdSliceBytes, kBwdSliceBytes, &S.w_ready);
     }
-    const int kb = (lane + q) % kNumKB;
+    const int kb = lane;
+    // k-block kb of every gate image is written by the CTAs of unit groups 2kb and 2kb+1 (the last one by group 22 only)
+    const unsigned int owners = (unsigned int)((2 * kb + 1 < kBwdGroups) ? 8 : 4);
     for (int it = 1; it < T; ++it) {
       const int t = T - 1 - it;
-      if (lane == 0) grid_wait(counter, (unsigned int)(it * gridDim.x), err);   // da_{t+1} complete in the images
-      __syncwarp();
       if (lane < kNumKB) {
-        fence_proxy_async();
+        grid_wait(counters + 32 * kb, (unsigned int)it * owners, err);   // k-block kb of da_{t+1} is complete
+        fence_proxy_async_global();                                            // generic-proxy writes -> async-proxy read
         const uint8_t* src = img + (size_t)(((t + 1) & img_mask) * 4 + g) * kXchgImageBytes;
         mbar_arrive_expect_tx(&S.full[kb], kRows * 128);
         bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[kb]);
@@ -105,9 +105,8 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
       cluster_sync_all();
     }
   } else if (warp >= 9) {
-    // ===================== MMA issuers: warp 9+m owns k-block (m + q) % 12 and accumulator tile m =====================
-    const int mw = warp - 9;
-    const int kb = (mw + q) % kNumKB;
+    // ===================== MMA issuers: warp 9+kb adds k-block kb into the shared accumulator tile =====================
+    const int kb = warp - 9;
     const uint32_t idesc = make_idesc_bf16(kRows, kBwdN);
     if (lane == 0) mbar_wait(&S.w_ready, 0, err);
     __syncwarp();
@@ -118,7 +117,7 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
         const uint64_t da = make_smem_desc_sw128(smem_u32(S.a[kb]));
         const uint64_t db = make_smem_desc_sw128(smem_u32(S.w + (size_t)kb * kBwdN * 128));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + (uint32_t)(mw * 32), da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, 1u);   // the tile was pre-zeroed
         umma_commit(&S.mma_done);
       }
       __syncwarp();
@@ -140,6 +139,10 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
     const bool valid = (row < B) && (j < kH);
     const size_t xo = umma_offset(kRows, row, j);
     float dc[2] = {0.f, 0.f};
+    unsigned int* my_counter = counters + 32 * (ug >> 1);   // this CTA's units live in k-block ug / 2
+    tmem_zero_x16(taddr);
+    tmem_st_wait();
+    tcgen05_fence_before();
 
     for (int it = 0; it < T; ++it) {
       const int t = T - 1 - it;
@@ -169,7 +172,9 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
         mbar_wait(&S.mma_done, (uint32_t)((it - 1) & 1), err);
         tcgen05_fence_after();
         float p[16];
-        tmem_ld_sum_x16<kBwdMmaWarps>(taddr, p);
+        tmem_ld_x16(taddr, p);
+        tmem_zero_x16(taddr);   // re-arm the accumulator: every MMA of the next step adds into it
+        tmem_st_wait();
         if (lane < 16) {   // push the partial sums to the siblings that finalise these units
           st_cluster_v4(red_dst0, make_float4(p[0], p[1], p[2], p[3]));
           st_cluster_v4(red_dst0 + 16, make_float4(p[4], p[5], p[6], p[7]));
@@ -208,10 +213,7 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
       }
       if (t > 0) {
         named_bar_sync(1, kBwdEpiThreads);
-        if (tid == 0) {
-          fence_proxy_async();
-          grid_arrive(counter);
-        }
+        if (tid == 0) grid_arrive(my_counter);   // release-add, cumulative over the stores the barrier ordered
       }
       if (valid) {   // fp32 da_t over the stash (operand of the dX GEMM): off the critical path
         *reinterpret_cast<float2*>(grow + 0 * kH + j) = d_i;
@@ -223,7 +225,7 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<32>(tmem);
   cluster_sync_all();   // no CTA exits while a sibling may still address its shared memory
 }
 

@@ -1,15 +1,19 @@
 // Persistent-RNN forward of one H=720 LSTM layer on tcgen05 (sm_100a).
 //
-//   grid  = 90 CTAs (one per SM), CTA q owns hidden units [8q, 8q+8): its 32 gate rows of W_hh (bf16, K padded to
-//           768) stay resident in shared memory for the whole sequence as the B operand [N=32, K=768].
-//   roles = warps 0-7 epilogue (cell), warp 8 producer (grid barrier + TMA bulk copies), warp 9 MMA issuer.
-//   step t: the producer waits on the grid barrier and pulls h_{t-1} (all 64 batch rows x 768, bf16, 96 KB) from the
-//           L2-resident exchange image with 12 bulk copies (one per 64-wide k-block, each landing on its own
-//           mbarrier); the MMA thread issues 48 tcgen05.mma (M=64, N=32, K=16) as the k-blocks arrive, accumulating
-//           [64 x 32] fp32 in TMEM, and commits to an mbarrier; the epilogue warps read TMEM, add the pre-computed
-//           input projection x_t W_ih^T + b (prefetched before the wait), apply the cell, store h_t / c_t /
-//           activated gates (fp32 stash for BPTT) and write h_t as bf16 straight into the UMMA image of the other
-//           exchange buffer; a release-add on a global counter is the grid barrier for the next step.
+//   grid  = 90 CTAs (one per SM, cooperative launch), CTA q owns hidden units [8q, 8q+8): its 32 gate rows of W_hh
+//           (bf16, K padded to 768) stay resident in shared memory for the whole sequence as the B operand
+//           [N=32, K=768].
+//   roles = warps 0-7 epilogue (the LSTM cell), warp 8 producer (barrier polling + TMA bulk copies),
+//           warps 9-20 MMA issuers (one per 64-wide k-block).
+//   step t: producer lane kb polls the arrival counter of k-block kb (the 8 CTAs that own hidden units 64kb..64kb+63)
+//           and pulls that k-block of h_{t-1} (64 batch rows x 64 units, bf16, 8 KB) from the L2-resident exchange
+//           image with one TMA bulk copy onto its own mbarrier; MMA warp kb issues the four tcgen05.mma
+//           (M=64, N=32, K=16) of its k-block as soon as it lands -- a tcgen05.mma issue costs ~60 ns of the issuing
+//           thread (measured), so the 48 instructions of a step are issued from 12 threads in parallel -- all adding
+//           into ONE fp32 accumulator tile [64 x 32] in TMEM that the epilogue re-zeroes after reading it; the epilogue
+//           warps add the pre-computed input projection x_t W_ih^T + b (prefetched before the wait), apply the cell,
+//           write h_t as bf16 straight into the UMMA image of the other exchange buffer, signal the k-block's counter
+//           (one release-add per CTA) and only then store h_t / c_t / the activated gates (fp32 stash for BPTT).
 //   Reference operator replaced: torch.nn.LSTM's recurrence (/root/reference/paule/models.py:349, :441).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -18,15 +22,11 @@
 #ifdef PAULE_TC_TRACE
 #define TRACE_DECL uint64_t tr_last = globaltimer_ns(); uint64_t tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define TRACE(i) { const uint64_t _n = globaltimer_ns(); tr_acc[i] += _n - tr_last; tr_last = _n; }
-#define TRACE_DUMP(base) { uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + 64) + (base); for (int _i = 0; _i < 8; ++_i) _o[_i] = tr_acc[_i]; }
+#define TRACE_DUMP(base) { uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + kXchgTraceOff) + (base); for (int _i = 0; _i < 8; ++_i) _o[_i] = tr_acc[_i]; }
 #else
 #define TRACE_DECL
 #define TRACE(i) {}
 #define TRACE_DUMP(base) {}
-#endif
-
-#ifndef PAULE_FWD_ARRIVALS
-#define PAULE_FWD_ARRIVALS 1   // grid-barrier arrivals per CTA and step: 1 (after a CTA barrier) or 8 (one per epilogue warp)
 #endif
 
 namespace paule {
@@ -65,19 +65,15 @@ __global__ void pack_bwd_kernel(const float* __restrict__ w_hh, uint8_t* __restr
 struct FwdSmem {
   uint8_t w[kFwdSliceBytes];            // B operand, resident        (48 KB, 1024-aligned)
   uint8_t a[kNumKB][kRows * 128];       // A operand k-blocks of h_{t-1} (12 x 8 KB)
-  uint8_t a_slack[kRows * 128];         // an M=128 descriptor on the last k-block reads 64 rows past it (ignored rows)
   uint64_t full[kNumKB];                // k-block landed
-  uint64_t mma_done;                    // accumulator ready
+  uint64_t mma_done;                    // accumulator complete (one arrival per MMA warp)
   uint64_t w_ready;
   uint32_t tmem_base;
 };
 
 constexpr int kEpiThreads = 256;
-// One tcgen05.mma issue costs ~60 ns of the issuing thread regardless of tile size (measured), so a 48-instruction
-// K loop from one thread is a 2.9 us serial chain.  Issue from 12 warps in parallel instead: warp 9+m owns k-block
-// (m + q) % 12 and its own fp32 accumulator tile in TMEM; the epilogue sums the 12 tiles.
-constexpr int kMmaWarps = 12;
-constexpr int kFwdThreads = kEpiThreads + 32 + 32 * kMmaWarps;   // + producer warp + MMA warps
+constexpr int kMmaWarps = kNumKB;                                 // one issuer per k-block
+constexpr int kFwdThreads = kEpiThreads + 32 + 32 * kMmaWarps;   // + producer warp + MMA warps = 672
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed, float* __restrict__ h_out,
@@ -86,8 +82,8 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
   extern __shared__ uint8_t smem_raw[];
   FwdSmem& S = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned int* counter = reinterpret_cast<unsigned int*>(xchg);
-  volatile int* err = reinterpret_cast<volatile int*>(xchg + 4);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(xchg);          // counters[32 * kb]: one 128-byte line each
+  volatile int* err = reinterpret_cast<volatile int*>(xchg + kXchgErrOff);
   // h_t images [12][64][128 B]: one per time step when the caller keeps them (they are the A operand of the next
   // layer's input-projection GEMM), otherwise two ping-pong images inside the exchange buffer
   uint8_t* hbuf = img_seq ? img_seq : xchg + kXchgHeader;
@@ -99,77 +95,54 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
     mbar_init(&S.w_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(&S.tmem_base);   // 12 tiles x 32 columns, rounded up to a power of two
+  if (warp == 9) tmem_alloc<32>(&S.tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 8) {
-    // ===================== producer: grid barrier + bulk copies of h_{t-1} =====================
-    // lane l < 12 owns k-block (l + q) % 12: the 12 copies are issued in parallel, and the 90 CTAs start on
-    // different k-blocks so that they do not all hit the same L2 lines at the same moment.
+    // ===================== producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(&S.w_ready, kFwdSliceBytes);      // resident weights: one 48 KB bulk copy
       bulk_g2s(S.w, packed + (size_t)q * kFwdSliceBytes, kFwdSliceBytes, &S.w_ready);
     }
-    const int kb = (lane + q) % kNumKB;
-    TRACE_DECL
-    for (int t = 1; t < T; ++t) {
-      // all 90 slices of h_{t-1} are in the image
-      if (lane == 0) grid_wait(counter, (unsigned int)(t * gridDim.x * PAULE_FWD_ARRIVALS), err);
-      __syncwarp();
-      TRACE(0)
-      if (lane < kNumKB) {
-        fence_proxy_async();
+    if (lane < kNumKB) {
+      const int kb = lane;
+      // CTAs 8kb .. 8kb+7 own the hidden units of k-block kb (the last k-block has only CTAs 88, 89)
+      const unsigned int owners = (unsigned int)(((kb + 1) * 8 <= kFwdCtas) ? 8 : kFwdCtas - kb * 8);
+      TRACE_DECL
+      for (int t = 1; t < T; ++t) {
+        grid_wait(counters + 32 * kb, (unsigned int)t * owners, err);     // k-block kb of h_{t-1} is complete
+        TRACE(0)
+        fence_proxy_async_global();                                            // generic-proxy writes -> async-proxy read
         const uint8_t* src = hbuf + (size_t)((t - 1) & img_mask) * kXchgImageBytes;
         mbar_arrive_expect_tx(&S.full[kb], kRows * 128);
         bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[kb]);
+        TRACE(1)
       }
-      TRACE(1)
+      if (q == 0 && lane == 0) TRACE_DUMP(0)
     }
-    if (q == 0 && lane == 0) TRACE_DUMP(0)
     __syncwarp();
   } else if (warp >= 9) {
-    // ===================== MMA issuers: warp 9+m takes k-blocks i = m, m+4, m+8 into accumulator tile m =====================
-    const int mw = warp - 9;
+    // ===================== MMA issuers: warp 9+kb adds k-block kb into the shared accumulator tile =====================
+    const int kb = warp - 9;
     if (lane == 0) {
-#ifndef EXP_M
-#define EXP_M kRows
-#endif
-      const uint32_t idesc = make_idesc_bf16(EXP_M, kFwdN);
+      const uint32_t idesc = make_idesc_bf16(kRows, kFwdN);
       mbar_wait(&S.w_ready, 0, err);
+      const uint64_t da = make_smem_desc_sw128(smem_u32(S.a[kb]));
+      const uint64_t db = make_smem_desc_sw128(smem_u32(S.w + (size_t)kb * kFwdN * 128));
       TRACE_DECL
       for (int t = 1; t < T; ++t) {
-        const uint32_t par = (uint32_t)((t - 1) & 1);
-#ifdef PAULE_TC_TRACE_SPLIT
-        for (int i = 0; i < kNumKB; ++i) {
-          mbar_wait(&S.full[(i + q) % kNumKB], par, err);
-          if (i == 0) TRACE(0)
-        }
-        TRACE(2)   // all k-blocks landed
-#endif
-#pragma unroll 1
-        for (int i = mw; i < kNumKB; i += kMmaWarps) {
-          const int kb = (i + q) % kNumKB;     // same rotation as the producer
-          mbar_wait(&S.full[kb], par, err);
-#ifndef PAULE_TC_TRACE_SPLIT
-          if (i == 0) TRACE(0)
-#endif
-          tcgen05_fence_after();
-          const uint64_t da = make_smem_desc_sw128(smem_u32(S.a[kb]));
-          const uint64_t db = make_smem_desc_sw128(smem_u32(S.w + (size_t)kb * kFwdN * 128));
+        mbar_wait(&S.full[kb], (uint32_t)((t - 1) & 1), err);
+        TRACE(0)
+        tcgen05_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + (uint32_t)(mw * 32), da + 2 * k, db + 2 * k, idesc, ((i - mw) | k) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, 1u);   // the tile was pre-zeroed
         umma_commit(&S.mma_done);
         TRACE(1)
-#ifdef PAULE_TC_TRACE_SPLIT
-        mbar_wait(&S.mma_done, par, err);
-        TRACE(3)   // MMA execution after the last issue
-#endif
       }
-      if (q == 0 && mw == 0) TRACE_DUMP(8)
+      if (q == 0 && kb == 0) TRACE_DUMP(8)
     }
     __syncwarp();
   } else {
@@ -184,6 +157,7 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
     const bool valid = row < B;
     const uint32_t taddr = tmem + ((uint32_t)(rowgrp * 32) << 16) + (uint32_t)(half * 16);
     const size_t xo = umma_offset(kRows, row, j);          // position of (row, j) in an exchange image
+    unsigned int* my_counter = counters + 32 * (q >> 3);   // this CTA's units live in k-block q / 8
     float c_prev[2] = {0.f, 0.f};
     TRACE_DECL
 
@@ -200,13 +174,17 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
         mbar_wait(&S.mma_done, (uint32_t)((t - 1) & 1), err);
         TRACE(0)
         tcgen05_fence_after();
-        tmem_ld_sum_x16<kMmaWarps>(taddr, acc);   // the K range is split over kMmaWarps accumulator tiles
-        tcgen05_fence_before();
-        TRACE(1)
+        tmem_ld_x16(taddr, acc);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.f;
       }
+      if (t + 1 < T) {   // re-arm the accumulator: every MMA of the next step adds into it
+        tmem_zero_x16(taddr);
+        tmem_st_wait();
+      }
+      tcgen05_fence_before();
+      TRACE(1)
       // columns of this half: gate*4 + uu.  Lanes 16..31 fetch units 2,3 from lane-16.
       float pre[4][2];
 #pragma unroll
@@ -234,25 +212,10 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
       }
       TRACE(2)
       if (t + 1 < T) {
-#if PAULE_FWD_ARRIVALS == 8
-        // publish per warp: no CTA-wide barrier, each warp releases its own 32 rows x 2 units as soon as they are out
-        __syncwarp();
-        if (lane == 0) {
-#ifndef PAULE_NO_WRITER_PROXY_FENCE
-          fence_proxy_async();
-#endif
-          grid_arrive(counter);          // red.release.gpu: cumulative over the warp's stores ordered by __syncwarp
-        }
-#else
-        // publish: CTA-wide barrier, then ONE gpu-scope release (cumulative over the CTA's stores)
+        // publish: CTA-wide barrier, then ONE gpu-scope release-add (cumulative over the stores the barrier ordered).
+        // The consumer side issues fence.proxy.async between its acquire and its TMA read.
         named_bar_sync(1, kEpiThreads);
-        if (tid == 0) {
-#ifndef PAULE_NO_WRITER_PROXY_FENCE
-          fence_proxy_async();
-#endif
-          grid_arrive(counter);          // red.release.gpu: cumulative over the stores ordered by the barrier above
-        }
-#endif
+        if (tid == 0) grid_arrive(my_counter);
       }
       TRACE(3)
       if (valid) {   // stash + outputs: off the critical path (the next step's barrier is already signalled)
@@ -270,7 +233,7 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<32>(tmem);
 }
 
 }  // namespace tc
@@ -300,7 +263,7 @@ extern "C" int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* pa
 
 extern "C" size_t paule_tc_rnn_xchg_bytes(int64_t B) {
   (void)B;
-  // header (counter, error flag) + forward: 2 h images; backward: 2 x 4 gate images (sized for the larger user)
+  // header (barrier counters, error flag) + forward: 2 h images; backward: 2 x 4 gate images (sized for the larger user)
   return (size_t)kXchgHeader + (size_t)8 * kXchgImageBytes;
 }
 
@@ -315,6 +278,7 @@ extern "C" int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h,
   PAULE_REQUIRE(math == PAULE_MATH_BF16);
   if (T == 0) return PAULE_OK;
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(xchg) % 16 == 0);   // bulk copies need 16-byte aligned global addresses
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(h_img_seq) % 16 == 0);
   cudaStream_t s = as_stream(stream);
   static bool attr_set = false;
   const int smem = (int)sizeof(FwdSmem) + 1024;
@@ -324,8 +288,8 @@ extern "C" int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h,
   }
   // words are independent: batches larger than the UMMA M tile run as consecutive 64-word groups
   for (int64_t r0 = 0; r0 < B; r0 += kRows) {
-    // zero the barrier words and both exchange images (pad columns / pad rows must be exact zeros)
-    PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader + (size_t)2 * kXchgImageBytes, s));
+    // zero the barrier words (and, without an image sequence, both ping-pong images: pad rows / columns must be 0)
+    PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader + (h_img_seq ? 0 : (size_t)2 * kXchgImageBytes), s));
     int Ti = (int)T, Bi = (int)((B - r0 < kRows) ? (B - r0) : kRows), Bsi = (int)B;
     float* gp = gates + r0 * 4 * kH;
     float* hp = h + r0 * kH;

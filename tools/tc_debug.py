@@ -27,7 +27,7 @@ def tc_fwd():
     xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
     rc = lib.paule_tc_lstm_seq_fwd(g.data_ptr(), w.packed.data_ptr(), h.data_ptr(), c.data_ptr(), xchg.data_ptr(), None, T, B, 1, st)
     torch.cuda.synchronize()
-    print("tc fwd rc", rc, lib.paule_last_cuda_error(), "err flag", xchg[4:8].view(torch.int32).item(), "counter", xchg[0:4].view(torch.int32).item())
+    print("tc fwd rc", rc, lib.paule_last_cuda_error(), "err flag", xchg[2048:2052].view(torch.int32).item(), "counter", xchg[0:4].view(torch.int32).item())
     return g, h, c
 
 g0, h0, c0 = fp32_fwd()
@@ -52,7 +52,7 @@ def tc_bwd():
     xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
     rc = lib.paule_tc_lstm_seq_bwd(da.data_ptr(), c0.data_ptr(), w.packed.data_ptr(), dh_seq.data_ptr(), 1, dh_last.data_ptr(), xchg.data_ptr(), None, T, B, 1, st)
     torch.cuda.synchronize()
-    print("tc bwd rc", rc, lib.paule_last_cuda_error(), "err flag", xchg[4:8].view(torch.int32).item(), "counter", xchg[0:4].view(torch.int32).item())
+    print("tc bwd rc", rc, lib.paule_last_cuda_error(), "err flag", xchg[2048:2052].view(torch.int32).item(), "counter", xchg[0:4].view(torch.int32).item())
     return da
 d0 = fp32_bwd(); d1 = tc_bwd()
 for t in reversed(range(T)):
@@ -75,4 +75,4 @@ for name in ("fwd", "bwd"):
         else:
             lib.paule_tc_lstm_seq_bwd(xpb.data_ptr(), cb.data_ptr(), w.packed.data_ptr(), dhb.data_ptr(), 1, None, xchg.data_ptr(), None, Tb, 64, 1, st)
         e1.record(); torch.cuda.synchronize()
-        print(f"tc {name} T={Tb} B=64: {e0.elapsed_time(e1)*1e3/Tb:.2f} us per step; err flag", xchg[4:8].view(torch.int32).item())
+        print(f"tc {name} T={Tb} B=64: {e0.elapsed_time(e1)*1e3/Tb:.2f} us per step; err flag", xchg[2048:2052].view(torch.int32).item())

@@ -14,8 +14,8 @@ for rep in range(2):
     e0.record()
     lib.paule_tc_lstm_seq_fwd(xpb.data_ptr(), w.packed.data_ptr(), hb.data_ptr(), cb.data_ptr(), xchg.data_ptr(), None, Tb, 64, 1, st)
     e1.record(); torch.cuda.synchronize()
-    print(f"fwd {e0.elapsed_time(e1)*1e3/Tb:.2f} us/step, err", xchg[4:8].view(torch.int32).item())
-    tr = xchg[64:64 + 24 * 8].view(torch.int64).cpu().tolist()
-    for who, base, names in (("producer", 0, ["grid wait", "copy issue"]), ("mma", 8, ["wait kb0", "issue 48 mma + commit", "wait kb1..11 (all landed)", "mma execution"]),
+    print(f"fwd {e0.elapsed_time(e1)*1e3/Tb:.2f} us/step, err", xchg[2048:2052].view(torch.int32).item())
+    tr = xchg[3072:3072 + 24 * 8].view(torch.int64).cpu().tolist()
+    for who, base, names in (("producer", 0, ["kblock wait", "copy issue"]), ("mma", 8, ["wait kblock", "issue 4 mma + commit"]),
                              ("epilogue", 16, ["wait mma_done", "tmem ld", "cell + h store", "bar + arrive", "stash stores"])):
         print(" ", who, {n: round(v / Tb / 1e3, 3) for n, v in zip(names, tr[base:base + 8])})
