@@ -227,6 +227,8 @@ typedef struct paule_plan {
   const float* post_w;        /* [Cm, H] post_linear.weight   */
   const float* post_w_t;      /* [H, Cm]                      */
   const float* post_b;        /* [Cm]                         */
+  const void* post_packed;    /* paule_tc_gemm_pack([0.5 W_post | 0.5 W_post] as [Cm, 2*720], Cm, 2): pooled post_linear
+                                 on tcgen05 (the two frames of a pair are two K segments), or NULL */
   paule_lstm_layer emb0, emb1;/* EmbeddingModel.lstm l0, l1   */
   const float* head_w;        /* [S, H] linear_mapping.weight */
   const float* head_w_t;      /* [H, S]                       */

@@ -28,7 +28,7 @@ class Plan(C.Structure):
         ("B", i64), ("T", i64), ("H", i64), ("C", i64), ("Cm", i64), ("S", i64),
         ("objective", i32), ("math", i32), ("smiling", i32), ("log_slot_count", i32),
         ("log_semantics", i32), ("reserved0", i32),
-        ("fwd", LstmLayer), ("post_w", vp), ("post_w_t", vp), ("post_b", vp),
+        ("fwd", LstmLayer), ("post_w", vp), ("post_w_t", vp), ("post_b", vp), ("post_packed", vp),
         ("emb0", LstmLayer), ("emb1", LstmLayer), ("head_w", vp), ("head_w_t", vp), ("head_b", vp),
         ("cp", vp), ("adam_m", vp), ("adam_v", vp), ("step_count", vp),
         ("target_mel", vp), ("target_sv", vp), ("past_cp", vp), ("past_T", i64),

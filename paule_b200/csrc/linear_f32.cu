@@ -119,7 +119,13 @@ extern "C" int paule_linear_f32(const float* A, const float* W, const float* bia
   PAULE_REQUIRE(M >= 0 && N > 0 && K > 0 && a_inner > 0 && c_inner > 0);
   if (M == 0) return PAULE_OK;
   RowMap am{a_inner, a_outer_stride, a_inner_stride}, cm{c_inner, c_outer_stride, c_inner_stride};
-  if (N <= 32) {
+  if (M <= 64 && N > 32) {
+    // few rows (heads: M = words): narrow column tiles so that the grid still covers many SMs
+    constexpr int BM = 64, BN = 16, BK = 16, TM = 4, TN = 1;
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
+    linear_f32_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, as_stream(stream)>>>(
+        A, W, bias, C, M, N, K, am, a_pair_stride, cm, accumulate);
+  } else if (N <= 32) {
     constexpr int BM = 128, BN = 32, BK = 16, TM = 4, TN = 4;
     dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
     linear_f32_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, as_stream(stream)>>>(

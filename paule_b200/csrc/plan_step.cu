@@ -26,7 +26,7 @@ struct Workspace {
   float *gates_0, *h_0, *c_0;
   float *gates_1, *h_1, *c_1;
   float *dmel, *dsv, *dh1_last, *dh0, *dhp, *dcp_lstm, *dcp_smooth, *dc, *partial;
-  void *xchg, *h_img, *da_img;   // tensor-core path only; h_img / da_img must have been zero-filled once
+  void *xchg, *h_img, *hf_img, *da_img;   // tensor-core path only; the image buffers must have been zero-filled once
   size_t floats;
 };
 
@@ -53,6 +53,7 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
   if (math != PAULE_MATH_FP32) {
     w.xchg = take_bytes(paule_tc_rnn_xchg_bytes(B));
     w.h_img = take_bytes(paule_tc_img_seq_bytes(Tm, B, 1));    // h_0 of every mel frame: A operand of Xp1 = h_0 W_ih1^T
+    w.hf_img = take_bytes(paule_tc_img_seq_bytes(T, B, 1));    // forward model's h_t: A operand of the pooled post_linear
     w.da_img = take_bytes(paule_tc_img_seq_bytes(T, B, 4));    // dA of the layer being back-propagated (reused by all three)
   }
   w.floats = off;
@@ -106,10 +107,16 @@ int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, pa
   const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, C = p->C, Cm = p->Cm, S = p->S;
   // ForwardModel (models.py:348-356): K = 30 input projection, recurrence
   PAULE_TRY(paule_linear_f32(p->cp, p->fwd.w_ih, p->fwd.bias, w.gates_f, T * B, 4 * H, C, 1, C, 0, 0, 1, 4 * H, 0, 0, s));
-  PAULE_TRY(recur_forward(p, p->fwd, T, w.gates_f, w.h_f, w.c_f, w, nullptr, s));
-  // post_linear + AvgPool1d(2,2): pool the pair of frames on load (the pool commutes with the Linear)
-  PAULE_TRY(paule_linear_f32(w.h_f, p->post_w, p->post_b, p->pred_mel, Tm * B, Cm, H, B, 2 * B * H, H, B * H, 1, Cm, 0,
-                             0, s));
+  const bool tc_post = tc(p) && p->post_packed != nullptr && (T % 2 == 0);
+  PAULE_TRY(recur_forward(p, p->fwd, T, w.gates_f, w.h_f, w.c_f, w, tc_post ? w.hf_img : nullptr, s));
+  // post_linear + AvgPool1d(2,2) (the pool commutes with the Linear)
+  if (tc_post) {
+    // on tcgen05: frames 2k and 2k+1 are consecutive images = two K segments of row (k, b); weights [0.5 W | 0.5 W]
+    PAULE_TRY(paule_tc_gemm_img(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, 0, s));
+  } else {   // pool the pair of frames on load
+    PAULE_TRY(paule_linear_f32(w.h_f, p->post_w, p->post_b, p->pred_mel, Tm * B, Cm, H, B, 2 * B * H, H, B * H, 1, Cm,
+                               0, 0, s));
+  }
   if (!need_semvec) return PAULE_OK;
   // EmbeddingModel (models.py:440-448), lens = Tm for every word (paule.py:922-924)
   PAULE_TRY(paule_linear_f32(p->pred_mel, p->emb0.w_ih, p->emb0.bias, w.gates_0, Tm * B, 4 * H, Cm, 1, Cm, 0, 0, 1, 4 * H,

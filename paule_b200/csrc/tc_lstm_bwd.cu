@@ -29,7 +29,7 @@ struct BwdSmem {
   uint8_t w[kBwdSliceBytes];            // B operand, resident (48 KB)
   uint8_t a[kNumKB][kRows * 128];       // A operand: gate g's image of da_{t+1} (96 KB)
   float red[4][kRows][8];               // partial sums from the 4 gate CTAs for this CTA's 8 units (8 KB)
-  uint64_t full[kNumKB];
+  uint64_t full[2][kNumKB];             // two sets so that the next step's barrier is armed early
   uint64_t mma_done;
   uint64_t w_ready;
   uint32_t tmem_base;
@@ -71,7 +71,7 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
   const int img_mask = img_seq ? 0x7fffffff : 1;
 
   if (tid == 0) {
-    for (int i = 0; i < kNumKB; ++i) mbar_init(&S.full[i], 1);
+    for (int i = 0; i < kNumKB; ++i) { mbar_init(&S.full[0][i], 1); mbar_init(&S.full[1][i], 1); }
     mbar_init(&S.mma_done, kBwdMmaWarps);
     mbar_init(&S.w_ready, 1);
     fence_mbar_init();
@@ -92,14 +92,15 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
     const int kb = lane;
     // k-block kb of every gate image is written by the CTAs of unit groups 2kb and 2kb+1 (the last one by group 22 only)
     const unsigned int owners = (unsigned int)((2 * kb + 1 < kBwdGroups) ? 8 : 4);
+    if (lane < kNumKB && T > 1) mbar_arrive_expect_tx(&S.full[0][kb], kRows * 128);   // armed one step ahead of the copy
     for (int it = 1; it < T; ++it) {
       const int t = T - 1 - it;
       if (lane < kNumKB) {
         grid_wait(counters + 32 * kb, (unsigned int)it * owners, err);   // k-block kb of da_{t+1} is complete
         fence_proxy_async_global();                                            // generic-proxy writes -> async-proxy read
         const uint8_t* src = img + (size_t)(((t + 1) & img_mask) * 4 + g) * kXchgImageBytes;
-        mbar_arrive_expect_tx(&S.full[kb], kRows * 128);
-        bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[kb]);
+        bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[(it - 1) & 1][kb]);
+        if (it + 1 < T) mbar_arrive_expect_tx(&S.full[it & 1][kb], kRows * 128);   // next step's barrier (other set)
       }
       __syncwarp();
       cluster_sync_all();
@@ -112,7 +113,7 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
     __syncwarp();
     for (int it = 1; it < T; ++it) {
       if (lane == 0) {
-        mbar_wait(&S.full[kb], (uint32_t)((it - 1) & 1), err);
+        mbar_wait(&S.full[(it - 1) & 1][kb], (uint32_t)(((it - 1) >> 1) & 1), err);
         tcgen05_fence_after();
         const uint64_t da = make_smem_desc_sw128(smem_u32(S.a[kb]));
         const uint64_t db = make_smem_desc_sw128(smem_u32(S.w + (size_t)kb * kBwdN * 128));

@@ -65,7 +65,7 @@ __global__ void pack_bwd_kernel(const float* __restrict__ w_hh, uint8_t* __restr
 struct FwdSmem {
   uint8_t w[kFwdSliceBytes];            // B operand, resident        (48 KB, 1024-aligned)
   uint8_t a[kNumKB][kRows * 128];       // A operand k-blocks of h_{t-1} (12 x 8 KB)
-  uint64_t full[kNumKB];                // k-block landed
+  uint64_t full[2][kNumKB];             // k-block landed; two sets so that the next step's barrier is armed early
   uint64_t mma_done;                    // accumulator complete (one arrival per MMA warp)
   uint64_t w_ready;
   uint32_t tmem_base;
@@ -90,7 +90,7 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
   const int img_mask = img_seq ? 0x7fffffff : 1;
 
   if (tid == 0) {
-    for (int i = 0; i < kNumKB; ++i) mbar_init(&S.full[i], 1);
+    for (int i = 0; i < kNumKB; ++i) { mbar_init(&S.full[0][i], 1); mbar_init(&S.full[1][i], 1); }
     mbar_init(&S.mma_done, kMmaWarps);
     mbar_init(&S.w_ready, 1);
     fence_mbar_init();
@@ -111,14 +111,15 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
       const int kb = lane;
       // CTAs 8kb .. 8kb+7 own the hidden units of k-block kb (the last k-block has only CTAs 88, 89)
       const unsigned int owners = (unsigned int)(((kb + 1) * 8 <= kFwdCtas) ? 8 : kFwdCtas - kb * 8);
+      if (T > 1) mbar_arrive_expect_tx(&S.full[0][kb], kRows * 128);        // armed one step ahead of the copy
       TRACE_DECL
       for (int t = 1; t < T; ++t) {
         grid_wait(counters + 32 * kb, (unsigned int)t * owners, err);     // k-block kb of h_{t-1} is complete
         TRACE(0)
         fence_proxy_async_global();                                            // generic-proxy writes -> async-proxy read
         const uint8_t* src = hbuf + (size_t)((t - 1) & img_mask) * kXchgImageBytes;
-        mbar_arrive_expect_tx(&S.full[kb], kRows * 128);
-        bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[kb]);
+        bulk_g2s(S.a[kb], src + (size_t)kb * kRows * 128, kRows * 128, &S.full[(t - 1) & 1][kb]);
+        if (t + 1 < T) mbar_arrive_expect_tx(&S.full[t & 1][kb], kRows * 128);   // next step's barrier (other set)
         TRACE(1)
       }
       if (q == 0 && lane == 0) TRACE_DUMP(0)
@@ -134,7 +135,7 @@ tc_lstm_fwd_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed
       const uint64_t db = make_smem_desc_sw128(smem_u32(S.w + (size_t)kb * kFwdN * 128));
       TRACE_DECL
       for (int t = 1; t < T; ++t) {
-        mbar_wait(&S.full[kb], (uint32_t)((t - 1) & 1), err);
+        mbar_wait(&S.full[(t - 1) & 1][kb], (uint32_t)(((t - 1) >> 1) & 1), err);
         TRACE(0)
         tcgen05_fence_after();
 #pragma unroll

@@ -109,6 +109,16 @@ class BatchPlanner:
                                     tc=self._tc)
         self.post_w, self.post_b = _f32c(p.post_linear.weight), _f32c(p.post_linear.bias)
         self.post_w_t = self.post_w.t().contiguous()
+        self.post_packed = None
+        if self._tc:
+            # AvgPool1d(2,2) o Linear == one GEMM over K = 2 x 720 with the weights [0.5 W | 0.5 W]: the two frames of
+            # a pair are the two K segments of one row, so the pooled projection runs on the h_t images unchanged
+            lib = _lib.load()
+            w2 = torch.cat((0.5 * self.post_w, 0.5 * self.post_w), dim=1).contiguous()
+            n_out = w2.shape[0]
+            self.post_packed = torch.empty(lib.paule_tc_gemm_packed_bytes(n_out, 2), dtype=torch.uint8, device=w2.device)
+            _lib.check(lib.paule_tc_gemm_pack(w2.data_ptr(), self.post_packed.data_ptr(), n_out, 2, ops._stream()),
+                       "paule_tc_gemm_pack")
         self.head_w, self.head_b = _f32c(e.linear_mapping.weight), _f32c(e.linear_mapping.bias)
         self.head_w_t = self.head_w.t().contiguous()
         if getattr(self, "_struct", None) is not None:
@@ -123,6 +133,7 @@ class BatchPlanner:
         s.log_semantics = int(self.log_semantics)
         s.fwd, s.emb0, s.emb1 = self.w_fwd.as_struct(), self.w_e0.as_struct(), self.w_e1.as_struct()
         s.post_w, s.post_w_t, s.post_b = self.post_w.data_ptr(), self.post_w_t.data_ptr(), self.post_b.data_ptr()
+        s.post_packed = None if self.post_packed is None else self.post_packed.data_ptr()
         s.head_w, s.head_w_t, s.head_b = self.head_w.data_ptr(), self.head_w_t.data_ptr(), self.head_b.data_ptr()
         s.cp, s.adam_m, s.adam_v = self.cp.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr()
         s.step_count = self.step_count.data_ptr()

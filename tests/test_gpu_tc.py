@@ -71,8 +71,9 @@ def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
     np.testing.assert_allclose(d1.cpu().numpy(), d0.cpu().numpy(), atol=2e-2 * d0.abs().max().item())
 
 
-def test_tc_is_deterministic_and_repeatable(setup):
-    """Same inputs -> bit-identical outputs across launches (no atomics on the data path; the barrier orders everything)."""
+def test_tc_is_repeatable(setup):
+    """Same inputs -> the same outputs across launches up to fp32 summation order: the 12 MMA issuers of a step add their
+    k-blocks into one shared TMEM accumulator in arrival order, so the last bits may differ (like a split-K GEMM)."""
     from paule_b200 import _lib, ops
     dev, lib, w = setup
     H, B, T = 720, 64, 40
@@ -85,7 +86,7 @@ def test_tc_is_deterministic_and_repeatable(setup):
                                              xchg.data_ptr(), None, T, B, 1,ops._stream()))
         torch.cuda.synchronize()
         outs.append(h1)
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-5 and (outs[0] - outs[2]).abs().max().item() < 1e-5
 
 
 @pytest.mark.parametrize("B,T", [(64, 10), (37, 7), (100, 5)])
