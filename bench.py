@@ -210,6 +210,21 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- the only cross-GPU traffic of a planning job: one final gather of the planned cps + loss log (NCCL)
+    gather_ms = None
+    if world > 1:
+        from paule_b200 import distributed as D
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.gather_words(planner.planned_cp(), world * B)          # warm-up (NCCL communicator setup)
+        barrier()
+        g0.record()
+        full_cp = D.gather_words(planner.planned_cp(), world * B)
+        full_loss = D.gather_words(planner.losses()["total"].transpose(0, 1).contiguous(), world * B)
+        g1.record()
+        barrier()
+        assert full_cp.shape == (world * B, T, 30) and full_loss.shape[0] == world * B
+        gather_ms = g0.elapsed_time(g1)
+
     # ---- the dominant kernel alone (live CUDA-event timing of the recurrent step kernels)
     roof = dominant_kernel_roofline(planner, math, dev)
 
@@ -242,6 +257,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": B * T * 30 * 4, "d2h_bytes_per_step": B * T * 30 * 4 + B * 6 * 4,
                     "steps": Ke, "how": "cps in pinned host memory: H2D cps -> one inner step -> D2H cps + loss terms, every step"},
             "gpu_launches": launches_per_step(T, math) * K,
+            "final_gather_ms": gather_ms,
             "roofline": roof,
             "cpu_baseline": cpu,
             "tflops_algorithmic": flops_per_word_step(T) * world * B * K / (ms_max * 1e-3) / 1e12,
@@ -259,8 +275,8 @@ def launches_per_step(T, math):
     if math == 0:
         rec = 2 * (T + Tm + Tm)                       # one launch per time step, forward + backward
     else:
-        rec = 2 * 3                                   # one persistent launch per layer and direction
-    return 1 + gemms + rec + 2 + 1                    # tick, GEMMs, recurrences, loss (2), Adam
+        rec = 2 * 3                                   # one persistent launch per layer and direction (per 64-word group)
+    return 1 + gemms + rec + 2 + 1                    # tick, GEMMs, recurrences, loss (2), Adam  (= 20 for the tcgen05 path)
 
 
 def dominant_kernel_roofline(planner, math, dev):
