@@ -206,25 +206,73 @@ def test_inverse_init_batched_plan(dev, models):
     np.testing.assert_allclose(np.stack(res.planned_loss_steps), r["loss"].numpy(), rtol=1e-3)
 
 
-def test_full_size_properties_cfg2(dev, models):
-    """BASELINE config 2 shape (B=64, T=200): size-independent properties instead of an element-wise oracle run:
-    the loss falls monotonically on the iid input, stays finite, cps stay clamped, and word 7 of the batch
-    equals the same word planned alone."""
+def _full_size_check(dev, pred, emb, cp0, tmel, n_steps, math, probe):
+    """Size-independent properties at a BASELINE shape instead of an element-wise oracle run over the whole batch:
+    the loss falls monotonically on the iid input and stays finite, the cps stay clamped, word `probe` of the batch
+    equals the same word planned alone, and that word matches the CPU oracle within the BASELINE tolerance."""
     from paule_b200 import BatchPlanner
-    pred, emb, _ = models
-    cp0, tmel = O.synthetic_inputs(64, 200, seed=5)
     cp0, tmel = cp0.to(dev), tmel.to(dev)
-    pl = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=10)
-    pl.step(10)
+    pl = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=n_steps, math=math)
+    pl.step(n_steps)
     L = pl.losses()["total"]
     assert torch.isfinite(L).all()
     assert (L[1:] < L[:-1]).all(), "loss must fall monotonically on the well-conditioned input (SURVEY appendix B)"
     assert pl.planned_cp().abs().max().item() <= 1.05 + 1e-6
-    solo = BatchPlanner(pred, emb, cp0[7:8], tmel[7:8], None, max_log_steps=10)
-    solo.step(10)
-    np.testing.assert_allclose(_np(solo.planned_cp()), _np(pl.planned_cp()[7:8]), atol=5e-6)
-    # the oracle on the same word: BASELINE tolerance
+    batch_cp = pl.planned_cp()[probe:probe + 1].clone()
+    batch_loss = L[:, probe:probe + 1].clone()
+    pl.close()
+    del pl
+    solo = BatchPlanner(pred, emb, cp0[probe:probe + 1], tmel[probe:probe + 1], None, max_log_steps=n_steps, math=math)
+    solo.step(n_steps)
+    np.testing.assert_allclose(_np(solo.planned_cp()), _np(batch_cp), atol=5e-6 if math == 0 else 2e-5)
+    np.testing.assert_allclose(_np(solo.losses()["total"]), _np(batch_loss), rtol=1e-5 if math == 0 else 1e-4)
     pr, em, _ = O.build_reference_models(0, 720, torch.float32, with_inverse=False)
-    r = O.plan_inner_loop(pr, em, cp0[7:8].cpu(), tmel[7:8].cpu(), 10)
+    r = O.plan_inner_loop(pr, em, cp0[probe:probe + 1].cpu(), tmel[probe:probe + 1].cpu(), n_steps)
     np.testing.assert_allclose(_np(solo.losses()["total"]), r["loss"].double().numpy(), rtol=1e-3)
     np.testing.assert_allclose(_np(solo.planned_cp()), r["planned_cp"].double().numpy(), atol=1e-3)
+
+
+@pytest.mark.parametrize("math", math_params())
+def test_full_size_properties_cfg2(dev, models, math):
+    """BASELINE config 2: B=64 words, 0.5 s utterances (T=200)."""
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(64, 200, seed=5)
+    _full_size_check(dev, pred, emb, cp0, tmel, 10, math, probe=7)
+
+
+@pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
+def test_full_size_properties_cfg3_inverse_init(dev, models):
+    """BASELINE config 3: InverseModel initialisation + planning, B=256, 1 s utterances (T=400), through Paule.plan_resynth.
+    The smooth inverse-model init is the chaotic regime: the initial cps are pinned against the oracle's
+    inverse model, the planning itself through batch == solo and finiteness."""
+    import paule_b200 as P
+    pred, emb, inv = models
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, math=1)
+    _, tmel = O.synthetic_inputs(256, 400, seed=41)
+    res = pm.plan_resynth(target_acoustic=tmel.numpy(), initialize_from="acoustic", objective="acoustic_semvec",
+                          n_outer=1, n_inner=3, continue_learning=False, verbose=False)
+    assert res.planned_cp.shape == (256, 400, 30) and np.isfinite(res.planned_cp).all()
+    assert np.abs(res.initial_cp).max() <= 1.0 and np.abs(res.planned_cp).max() <= 1.05 + 1e-6
+    _, _, iv = O.build_reference_models(0, 720, torch.float32)
+    with torch.no_grad():
+        init = iv(tmel[100:103]).clamp(-1, 1)
+    np.testing.assert_allclose(res.initial_cp[100:103], init.numpy(), atol=1e-4)
+    solo = pm.plan_resynth(target_acoustic=tmel[101].numpy(), initial_cp=res.initial_cp[101], initialize_from=None,
+                           objective="acoustic_semvec", n_outer=1, n_inner=3, continue_learning=False, verbose=False)
+    np.testing.assert_allclose(np.array(solo.planned_loss_steps), np.stack(res.planned_loss_steps)[:, 101], rtol=2e-3)
+
+
+@pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
+def test_full_size_properties_cfg4_shard(dev, models):
+    """BASELINE config 4 as one rank of 8 sees it: 256 of the 2048 words, 1 s utterances (T=400)."""
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(256, 400, seed=43)
+    _full_size_check(dev, pred, emb, cp0, tmel, 4, 1, probe=201)
+
+
+@pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
+def test_full_size_properties_cfg5_long_utterance_shard(dev, models):
+    """BASELINE config 5 as one rank of 8 sees it: 64 of the 512 words, 3 s utterances (T=1200, deep BPTT)."""
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(64, 1200, seed=47)
+    _full_size_check(dev, pred, emb, cp0, tmel, 3, 1, probe=33)
