@@ -53,6 +53,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// A operand in tensor memory ("TS"): [M = 128 lanes, K] bf16, 32-bit column c of lane m holds k = 2c (low half) and 2c+1;
+// one instruction consumes K = 16 = 8 columns.  Measured (tools/mma_bench.cu): 12 warps x 4 MMAs (M=128, N=16) into one
+// accumulator complete in 653 cycles with A in TMEM against 2082 with A streamed from shared memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -61,6 +75,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// One elected lane of a converged warp.  Inside `if (elect_one_sync())` the compiler knows the region is warp-uniform, so
+// descriptors computed from uniform values stay in uniform registers and tcgen05.mma / tcgen05.commit issue directly;
+// under a plain `if (lane == 0)` every UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~90 ns each).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler treats as warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 // ---- TMEM
 template <int kCols>
@@ -97,6 +128,28 @@ __device__ __forceinline__ void tmem_ld_x16_issue(uint32_t taddr, uint32_t (&r)[
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 bit, 8 consecutive columns
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x),
+               "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_zero_x8(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+               : "memory");
+}
 
 // zero 16 columns of this warp's 32 TMEM lanes (used to re-arm accumulator tiles that several MMA issuers add into)
 __device__ __forceinline__ void tmem_zero_x16(uint32_t taddr) {
@@ -253,6 +306,29 @@ __device__ __forceinline__ bool grid_wait(const unsigned int* counter, unsigned 
     }
   }
 }
+
+// ---- self-validating exchange of bf16 operands between CTAs.  Every exchanged value satisfies |x| < 2 (h is a product of
+// a sigmoid and a tanh; gradients are clamped), so bit 14 of its bf16 encoding -- the top exponent bit -- is always 0
+// and is free to carry a phase bit.  Consecutive occupants of a ping-pong buffer are steps t-2 and t, which differ in
+// (t >> 1) & 1: a reader that finds the expected phase bit in a 2-byte value holds that step's value.  No flag word, no
+// fence on the writer, no acquire on the reader, any access width; buffers start as 0x40 bytes (phase bit set, the
+// first occupants carry phase 0).
+constexpr uint32_t kPhaseMask = 0x40004000u;
+__device__ __forceinline__ uint32_t phase_bits(int step) { return ((step >> 1) & 1) ? kPhaseMask : 0u; }
+__device__ __forceinline__ void xchg_store(void* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t xchg_load(const void* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 xchg_load4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // named barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -1,6 +1,8 @@
 // Shapes of the H=720 persistent-RNN kernels (forward: tc_lstm_fwd.cu, backward: tc_lstm_bwd.cu).
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace paule {
 namespace tc {
@@ -28,6 +30,115 @@ constexpr int kXchgHeader = 4096;   // 12 barrier counters (one 128-byte line pe
 constexpr int kXchgErrOff = 2048;    // int: 0 ok, 1 grid-barrier watchdog fired, 2 mbarrier watchdog fired
 constexpr int kXchgTraceOff = 3072;  // PAULE_TC_TRACE builds only
 constexpr int kXchgImageBytes = kNumKB * kRows * 128;  // 98304
+
+// ---- v2 persistent kernels (tc_lstm_fwd2.cu / tc_lstm_bwd2.cu): weights are the resident A operand (M = 128 rows),
+// 16 words are the N dimension, and the recurrent state travels between CTAs as 8-byte {bf16x2, step tag} elements
+// that carry their own validity (no counters, no release/acquire chain, no TMA on the exchange).
+constexpr int kWq = 16;                              // words per CTA ("word quarter" of a 64-word group)
+constexpr int kMaxQ = 6;                             // word quarters per launch: 23 x 6 = 138 / 24 x 6 = 144 CTAs <= 148 SMs
+constexpr int kV2M = 128;                            // UMMA M: gate rows (forward) / hidden units (backward) per CTA
+constexpr int kV2SliceBytes = kNumKB * kV2M * 128;   // 196608: resident A operand [128, 768] bf16 = 384 TMEM columns
+constexpr int kV2WCols = kKPad / 2;                  // 384 32-bit TMEM columns (two bf16 per column)
+constexpr int kV2AccCol = 0;                         // accumulator [128 lanes, 16 columns]
+constexpr int kV2WCol = 64;                          // first column of the resident weights
+constexpr int kV2BBytes = kNumKB * kWq * 128;        // 24576: B operand [16 words, 768] bf16
+constexpr int kFwd2Groups = (kH + 31) / 32;          // 23 CTAs per word quarter, 32 hidden units each
+constexpr int kBwd2Groups = (kH + 127) / 128;        // 6 clusters of 4 (one CTA per gate) per word quarter, 128 units each
+// exchange block per (quarter, parity[, gate]): dense bf16 [12 kb][16 words][64 units], phase bit in bit 14 of every value
+constexpr int kLLBlockBytes = kNumKB * kWq * 128;     // 24576
+constexpr size_t kLLBytes = (size_t)kMaxQ * 2 * 4 * kLLBlockBytes;   // backward: 4 gate images per (quarter, parity)
+
+// offsets of the v2 weight images inside the packed buffer of one layer
+constexpr size_t kPackedV1Bytes = (size_t)kFwdCtas * kFwdSliceBytes + (size_t)kBwdCtas * kBwdSliceBytes;
+constexpr size_t kPackedFwd2Off = kPackedV1Bytes;
+constexpr size_t kPackedBwd2Off = kPackedFwd2Off + (size_t)kFwd2Groups * kV2SliceBytes;
+constexpr size_t kPackedBytes = kPackedBwd2Off + (size_t)kBwd2Groups * 4 * kV2SliceBytes;
+
+
+#ifdef __CUDACC__
+// Weight image of one CTA as tcgen05.st wants it: [48 column octets][128 rows][8 x u32]; u32 column c of row m holds the
+// bf16 pair (k = 2c, 2c+1).  Warp w (lanes 32w..32w+31) copies its rows with one 32-byte load + one x8 store per octet.
+__device__ __forceinline__ void load_weights_to_tmem(const uint8_t* __restrict__ slice, uint32_t tmem, int warp, int lane) {
+  const uint4* src = reinterpret_cast<const uint4*>(slice) + (size_t)(warp * 32 + lane) * 2;
+  const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)kV2WCol;
+#pragma unroll 4
+  for (int c8 = 0; c8 < kV2WCols / 8; ++c8) {
+    const uint4 a = __ldg(src + (size_t)c8 * kV2M * 2), b = __ldg(src + (size_t)c8 * kV2M * 2 + 1);
+    tmem_st_x8(dst + (uint32_t)(c8 * 8), a, b);
+  }
+  tmem_st_wait();
+}
+
+// Pulls k-block kb of a [16 words x 768] bf16 operand (2 KB: [16 rows][128 B]) out of an exchange block into the swizzled
+// UMMA layout at `dst`, waiting until every value carries phase bit `phase`.  Called by one full warp.  Lanes 0..15
+// first poll ONE value of each of the 16 writer warps of the k-block (`probe_off`: byte offset of this lane's probe; a
+// warp's values leave the SM with one store instruction, so they become visible together), then the block is read once
+// with 16-byte loads; stragglers are re-read.  Returns false when the watchdog fired.
+__device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int kb,
+                                                  uint32_t phase, int lane, uint32_t probe_off, bool prober,
+                                                  int rows, volatile int* err, uint64_t* trace = nullptr) {
+  // k-block 11 holds units 704..767: only 704..735 have a writer (chunks 0..3), the rest stays zero in shared memory;
+  // only the first `rows` rows (valid words of this quarter) are published and read
+  const int c = lane & 7;
+  const bool active = (kb < kNumKB - 1) || (c < 4);
+  uint32_t pending = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pending |= (4 * i < rows) ? (1u << i) : 0u;
+  {
+    const uint8_t* pp = src + probe_off;
+    uint64_t t0 = 0;
+    bool ok = !prober;
+    for (unsigned int spin = 0;; ++spin) {
+      if (!ok) ok = (xchg_load(pp) & kPhaseMask) == phase;
+      if (__all_sync(0xffffffffu, ok)) break;
+      if ((spin & 1023u) == 1023u) {
+        if (t0 == 0) t0 = globaltimer_ns();
+        if (*err != 0) return false;
+        if (globaltimer_ns() - t0 > kWatchdogNs) { *err = 1; return false; }
+      }
+    }
+  }
+  uint64_t t0 = 0;
+  if (trace) { trace[0] = globaltimer_ns(); }
+  for (unsigned int spin = 0; pending != 0u; ++spin) {
+    if (trace) trace[1] += 1;
+    uint4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (((pending >> i) & 1u) && active && 4 * i + (lane >> 3) < rows) v[i] = xchg_load4(src + (size_t)(i * 32 + lane) * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((pending >> i) & 1u) {
+        const bool ok = !active || 4 * i + (lane >> 3) >= rows || (((v[i].x & kPhaseMask) == phase) && ((v[i].y & kPhaseMask) == phase) &&
+                                    ((v[i].z & kPhaseMask) == phase) && ((v[i].w & kPhaseMask) == phase));
+        if (__all_sync(0xffffffffu, ok)) {
+          pending &= ~(1u << i);
+          const int row = 4 * i + (lane >> 3);
+          if (active && row < rows) {
+            *reinterpret_cast<uint4*>(dst + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4)) =
+                make_uint4(v[i].x & ~kPhaseMask, v[i].y & ~kPhaseMask, v[i].z & ~kPhaseMask, v[i].w & ~kPhaseMask);
+          }
+        }
+      }
+    }
+    if ((spin & 255u) == 255u) {
+      if (t0 == 0) t0 = globaltimer_ns();
+      if (*err != 0) return false;
+      if (globaltimer_ns() - t0 > kWatchdogNs) { *err = 1; return false; }
+    }
+  }
+  return true;
+}
+#endif  // __CUDACC__
+
+// host entry points of the v2 kernels (dispatched from paule_tc_lstm_seq_fwd / _bwd; PAULE_RNN_V1=1 keeps the v1 kernels)
+int pack_v2(const float* w_hh, uint8_t* packed, cudaStream_t s);
+int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
+                  cudaStream_t s);
+int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s);
+inline bool use_v1_fwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_FWD_V1") != nullptr; return v; }
+inline bool use_v1_bwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_BWD_V1") != nullptr; return v; }
 
 }  // namespace tc
 }  // namespace paule

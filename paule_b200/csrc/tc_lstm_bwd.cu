@@ -245,6 +245,7 @@ extern "C" int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* p
   if (T == 0) return PAULE_OK;
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(xchg) % 16 == 0);   // bulk copies need 16-byte aligned global addresses
   cudaStream_t s = as_stream(stream);
+  if (!use_v1_bwd()) return lstm_seq_bwd2(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
   static bool attr_set = false;
   const int smem = (int)sizeof(BwdSmem) + 1024;
   if (!attr_set) {

@@ -1,0 +1,309 @@
+// Persistent reverse-time BPTT (input gradients only) of one H=720 LSTM layer on tcgen05 (sm_100a), latency-optimised
+// layout ("v2"; see tc_lstm_fwd2.cu for the two ideas: weights as the resident A operand with 16 words as N, and the
+// recurrent operand exchanged as self-validating 8-byte {bf16x2, step tag} elements).
+//
+//   dh_t[b,j] = dh_ext_t[b,j] + sum_{g<4} sum_{k<720} da^g_{t+1}[b,k] W_hh[g*720 + k, j];   da_t = cell adjoint(dh_t, ...)
+//
+//   grid = (6 unit groups of 128 hidden units) x (4 gates) x ceil(words / 16) CTAs in clusters of 4: K = 2880 is split
+//   over the gates inside a cluster.  CTA (ugb, g) keeps A[m, k] = W_hh[g*720 + k, 128 ugb + m] resident (192 KB), pulls
+//   gate g's da_{t+1} of its 16 words out of the exchange (24 KB of payload), runs 48 tcgen05.mma (M=128, N=16, K=16;
+//   12 issuers, one TMEM accumulator) and owns the finalisation of hidden units 128 ugb + 32 g .. +31: TMEM lane group
+//   lg of every CTA holds the partial sums of the units that sibling lg finalises, so each epilogue warp pushes its
+//   lanes straight into sibling lg's shared memory (st.shared::cluster) and arrives on its mbarrier (release.cluster);
+//   no cluster-wide barrier in the loop.
+//   Reference operator replaced: autograd through aten::lstm (discrepancy.backward(), paule/paule.py:1052).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_lstm.cuh"
+
+namespace paule {
+namespace tc {
+
+struct Bwd2Smem {
+  uint8_t b[kV2BBytes];         // B operand: gate g's da_{t+1} of this CTA's 16 words (24 KB)
+  float red[4][kWq][32];        // partial sums from the 4 gate CTAs for this CTA's 32 units (8 KB)
+  uint64_t mma_done;
+  uint64_t acc_free;
+  uint64_t red_full;            // 8 arrivals per step: two warps of each of the four CTAs of the cluster
+  uint32_t tmem_base;
+};
+
+constexpr int kB2EpiWarps = 8;
+constexpr int kB2Threads = 32 * (kB2EpiWarps + kNumKB);   // 640
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile int* err_flag) {
+  uint64_t t0 = 0;
+  for (unsigned int spin = 0;; ++spin) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    if ((spin & 63u) == 63u) {
+      if (t0 == 0) t0 = globaltimer_ns();
+      if (*err_flag != 0) return false;
+      if (globaltimer_ns() - t0 > kWatchdogNs) { *err_flag = 2; return false; }
+    }
+  }
+}
+// bf16x2 of a gradient pair for the exchange: |x| < 2 keeps bit 14 of the encoding free for the phase bit (a NaN / Inf /
+// huge gradient is clamped on the recurrent path only; the fp32 stash and the dX images keep the raw value)
+__device__ __forceinline__ uint32_t xchg_clamped(float2 v) {
+  const float a = fabsf(v.x) < 1.5f ? v.x : copysignf(1.5f, v.x), b = fabsf(v.y) < 1.5f ? v.y : copysignf(1.5f, v.y);
+  const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ void cluster_sync_all2() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kB2Threads, 1)
+tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed,
+                    const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
+                    uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0) {
+  extern __shared__ uint8_t smem_raw[];
+  Bwd2Smem& S = *reinterpret_cast<Bwd2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int g = (int)cluster_ctarank_u32();                 // gate handled by this CTA's K slice
+  const int cl = blockIdx.x >> 2;
+  const int ugb = cl % kBwd2Groups, qs = cl / kBwd2Groups;  // unit group (128 hidden units), word quarter
+  volatile int* err = reinterpret_cast<volatile int*>(xchg + kXchgErrOff);
+  uint8_t* ll = xchg + kXchgHeader + (size_t)qs * 2 * 4 * kLLBlockBytes;   // [parity][gate] blocks of this quarter
+
+  if (tid == 0) {
+    mbar_init(&S.mma_done, kNumKB);
+    mbar_init(&S.acc_free, kB2EpiWarps);
+    mbar_init(&S.red_full, 8);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < kV2BBytes / 16; i += kB2Threads) reinterpret_cast<uint4*>(S.b)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_shared();
+  if (warp == kB2EpiWarps) tmem_alloc<512>(&S.tmem_base);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  // resident weights: A[m, k] = W_hh[g*720 + k, 128 ugb + m] goes into tensor memory once (384 columns)
+  if (warp < 4) load_weights_to_tmem(packed + (size_t)(ugb * 4 + g) * kV2SliceBytes, tmem, warp, lane);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  cluster_sync_all2();   // every sibling's mbarriers are initialised before any remote arrive / DSMEM store
+
+  if (warp >= kB2EpiWarps) {
+    // ===================== loader + MMA issuer of k-block kb =====================
+    const int kb = warp - kB2EpiWarps;
+    const uint32_t idesc = make_idesc_bf16(kV2M, kWq);
+    const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);
+    const uint64_t db = make_smem_desc_sw128(smem_u32(S.b + (size_t)kb * kWq * 128));
+    // probes: lane p < 16 watches cell warp p&7 (rows 2(p&7), 2(p&7)+1) of writer CTA p>>3 of the k-block's two
+    const uint32_t probe_off = (uint32_t)(((lane & 7) * 2 * 64 + ((lane >> 3) & 1) * 32) * 2);
+    const int rows = min(kWq, Bv - qs * kWq);   // valid words of this quarter: only their rows travel
+    const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 7) * 2 < rows);
+    for (int it = 1; it < T; ++it) {
+      const uint8_t* src = ll + (size_t)(((it - 1) & 1) * 4 + g) * kLLBlockBytes + (size_t)kb * (kWq * 128);
+      if (!xchg_fetch_kblock(src, S.b + (size_t)kb * kWq * 128, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err)) break;
+      fence_proxy_async_shared();
+      __syncwarp();
+      mbar_wait(&S.acc_free, (uint32_t)((it - 1) & 1), err);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + kV2AccCol, ta + 8 * k, db + 2 * k, idesc, 1u);
+        umma_commit(&S.mma_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== cell adjoint =====================
+    // TMEM read role: lane group lg = the 32 units sibling lg finalises, column half ch = 8 words
+    const int lg = warp & 3, ch = warp >> 2;
+    const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(kV2AccCol + ch * 8);
+    const uint32_t red_dst = mapa_u32(smem_u32(&S.red[g][ch * 8][lane]), (uint32_t)lg);
+    const uint32_t bar_dst = mapa_u32(smem_u32(&S.red_full), (uint32_t)lg);
+    // cell role: unit pair a (units j, j+1) of word w
+    const int a = lane & 15, w = (lane >> 4) + 2 * warp;
+    const int j = ugb * kV2M + g * 32 + 2 * a;
+    const int wp = qs * kWq + w;
+    const bool valid = (wp < Bv) && (j < kH);
+    const int wg = w0 + wp;
+    const size_t ll_off = ((size_t)((j >> 6) * kWq + w) * 64 + (size_t)(j & 63)) * 2;
+    const bool publish = (j < kH + 16) && (wp < Bv);   // k-block 11: pairs 0..15 (units 704..735) are read, zeros beyond H
+    uint8_t* img_dst = img_seq ? img_seq + (size_t)(wg / kRows) * (size_t)T * 4 * kXchgImageBytes + umma_offset(kRows, wg % kRows, j < kKPad ? j : 0)
+                               : nullptr;
+    float dc[2] = {0.f, 0.f};
+    tmem_zero_x8(taddr);
+    tmem_st_wait();
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.acc_free);
+
+    for (int it = 0; it < T; ++it) {
+      const int t = T - 1 - it;
+      // (1) everything that does not depend on da_{t+1}: stash, cell states, external gradient
+      float2 s_i, s_f, s_g, s_o, ct, cp, dh;
+      s_i = s_f = s_g = s_o = ct = cp = dh = make_float2(0.f, 0.f);
+      float* grow = gates + ((size_t)t * Bs + (valid ? wp : 0)) * (4 * kH);
+      if (valid) {
+        s_i = *reinterpret_cast<const float2*>(grow + 0 * kH + j);
+        s_f = *reinterpret_cast<const float2*>(grow + 1 * kH + j);
+        s_g = *reinterpret_cast<const float2*>(grow + 2 * kH + j);
+        s_o = *reinterpret_cast<const float2*>(grow + 3 * kH + j);
+        ct = *reinterpret_cast<const float2*>(c_seq + ((size_t)t * Bs + wp) * kH + j);
+        if (t > 0) cp = *reinterpret_cast<const float2*>(c_seq + ((size_t)(t - 1) * Bs + wp) * kH + j);
+        if (dh_mode == 1) {
+          dh = *reinterpret_cast<const float2*>(dh_seq + ((size_t)t * Bs + wp) * kH + j);
+        } else if (dh_mode == 2 && (t >> 1) < (T >> 1)) {
+          const float2 v = *reinterpret_cast<const float2*>(dh_seq + ((size_t)(t >> 1) * Bs + wp) * kH + j);
+          dh = make_float2(0.5f * v.x, 0.5f * v.y);
+        }
+        if (dh_last != nullptr && t == T - 1) {
+          const float2 v = *reinterpret_cast<const float2*>(dh_last + (size_t)wp * kH + j);
+          dh.x += v.x; dh.y += v.y;
+        }
+      }
+      if (it > 0) {
+        float p[8];
+        mbar_wait(&S.mma_done, (uint32_t)((it - 1) & 1), err);
+        tcgen05_fence_after();
+        tmem_ld_x8(taddr, p);
+        if (it + 1 < T) {   // re-arm the accumulator: every MMA of the next step adds into it
+          tmem_zero_x8(taddr);
+          tmem_st_wait();
+        }
+        tcgen05_fence_before();
+        // push this warp's partial sums (unit = lane of sibling lg's 32, words 8ch..8ch+7) and signal the sibling
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st_cluster_f32(red_dst + (uint32_t)(i * 32 * 4), p[i]);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&S.acc_free);
+          mbar_arrive_remote_release(bar_dst);
+        }
+        mbar_wait_cluster(&S.red_full, (uint32_t)((it - 1) & 1), err);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const float2 v = *reinterpret_cast<const float2*>(&S.red[s][w][2 * a]);
+          dh.x += v.x; dh.y += v.y;
+        }
+      }
+      // (2) cell adjoint (oracle: manual_lstm_backward_input)
+      float2 d_i, d_f, d_g, d_o;
+      {
+        const float tc0 = fast_tanh(fminf(fmaxf(ct.x, -15.f), 15.f)), tc1 = fast_tanh(fminf(fmaxf(ct.y, -15.f), 15.f));
+        const float do0 = dh.x * tc0, do1 = dh.y * tc1;
+        const float dc0 = dc[0] + dh.x * s_o.x * (1.f - tc0 * tc0), dc1 = dc[1] + dh.y * s_o.y * (1.f - tc1 * tc1);
+        d_i = make_float2(dc0 * s_g.x * s_i.x * (1.f - s_i.x), dc1 * s_g.y * s_i.y * (1.f - s_i.y));
+        d_f = make_float2(dc0 * cp.x * s_f.x * (1.f - s_f.x), dc1 * cp.y * s_f.y * (1.f - s_f.y));
+        d_g = make_float2(dc0 * s_i.x * (1.f - s_g.x * s_g.x), dc1 * s_i.y * (1.f - s_g.y * s_g.y));
+        d_o = make_float2(do0 * s_o.x * (1.f - s_o.x), do1 * s_o.y * (1.f - s_o.y));
+        dc[0] = dc0 * s_f.x;
+        dc[1] = dc1 * s_f.y;
+      }
+      const __nv_bfloat162 b_i = __floats2bfloat162_rn(d_i.x, d_i.y), b_f = __floats2bfloat162_rn(d_f.x, d_f.y);
+      const __nv_bfloat162 b_g = __floats2bfloat162_rn(d_g.x, d_g.y), b_o = __floats2bfloat162_rn(d_o.x, d_o.y);
+      const uint32_t p_i = *reinterpret_cast<const uint32_t*>(&b_i), p_f = *reinterpret_cast<const uint32_t*>(&b_f);
+      const uint32_t p_g = *reinterpret_cast<const uint32_t*>(&b_g), p_o = *reinterpret_cast<const uint32_t*>(&b_o);
+      if (t > 0 && publish) {   // da_t into the four gate blocks of the exchange: critical path of the next step
+        uint8_t* dst = ll + (size_t)((it & 1) * 4) * kLLBlockBytes + ll_off;
+        const uint32_t ph = phase_bits(it);
+        xchg_store(dst + 0 * (size_t)kLLBlockBytes, xchg_clamped(d_i) | ph);
+        xchg_store(dst + 1 * (size_t)kLLBlockBytes, xchg_clamped(d_f) | ph);
+        xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
+        xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
+      }
+      if (valid) {   // off the critical path: bf16 images (A operand of the dX GEMM) and fp32 da_t over the stash
+        if (img_seq != nullptr) {
+          uint8_t* d = img_dst + (size_t)t * 4 * kXchgImageBytes;
+          *reinterpret_cast<uint32_t*>(d + 0 * (size_t)kXchgImageBytes) = p_i;
+          *reinterpret_cast<uint32_t*>(d + 1 * (size_t)kXchgImageBytes) = p_f;
+          *reinterpret_cast<uint32_t*>(d + 2 * (size_t)kXchgImageBytes) = p_g;
+          *reinterpret_cast<uint32_t*>(d + 3 * (size_t)kXchgImageBytes) = p_o;
+        }
+        *reinterpret_cast<float2*>(grow + 0 * kH + j) = d_i;
+        *reinterpret_cast<float2*>(grow + 1 * kH + j) = d_f;
+        *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
+        *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kB2EpiWarps) tmem_dealloc<512>(tmem);
+  cluster_sync_all2();   // no CTA exits while a sibling may still address its shared memory
+}
+
+int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+  static bool attr_set = false;
+  const int smem = (int)sizeof(Bwd2Smem) + 1024;
+  if (!attr_set) {
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  // cooperative + cluster launch accepted by this driver?  (Nsight Compute rejects the combination with LaunchFailed;
+  // PAULE_NO_COOP_CLUSTER=1 launches with the cluster attribute only -- at most 144 CTAs always fit the 148 SMs.)
+  static int coop_ok = getenv("PAULE_NO_COOP_CLUSTER") ? 0 : 1;
+  const int64_t pass_words = (int64_t)kMaxQ * kWq;
+  for (int64_t r0 = 0; r0 < B; r0 += pass_words) {
+    const int Bv = (int)((B - r0 < pass_words) ? (B - r0) : pass_words);
+    const int nq = (Bv + kWq - 1) / kWq;
+    PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));
+    PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)nq * 2 * 4 * kLLBlockBytes, s));
+    float* gp = gates + r0 * 4 * kH;
+    const float* cp = c + r0 * kH;
+    const float* dsp = dh_seq ? dh_seq + r0 * kH : nullptr;
+    const float* dlp = dh_last ? dh_last + r0 * kH : nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kBwd2Groups * 4 * nq);
+    cfg.blockDim = dim3(kB2Threads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 4;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = coop_ok ? 2 : 1;
+    uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
+    uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
+    const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
+                                       (int)r0);
+    if (e != cudaSuccess && coop_ok) {
+      cudaGetLastError();
+      coop_ok = 0;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0);
+    }
+    PAULE_CUDA(e);
+  }
+  return PAULE_OK;
+}
+
+}  // namespace tc
+}  // namespace paule

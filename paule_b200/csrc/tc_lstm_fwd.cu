@@ -246,7 +246,7 @@ using namespace paule::tc;
 extern "C" size_t paule_tc_packed_lstm_bytes(int64_t H, int64_t I) {
   (void)I;
   if (H != kH) return 0;
-  return (size_t)kFwdCtas * kFwdSliceBytes + (size_t)kBwdCtas * kBwdSliceBytes;
+  return kPackedBytes;
 }
 
 extern "C" int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* packed, int64_t H, int64_t I,
@@ -259,13 +259,14 @@ extern "C" int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* pa
   pack_fwd_kernel<<<kFwdCtas, 256, 0, as_stream(stream)>>>(w_hh, img);
   pack_bwd_kernel<<<kBwdCtas, 256, 0, as_stream(stream)>>>(w_hh, img + (size_t)kFwdCtas * kFwdSliceBytes);
   PAULE_LAUNCH_CHECK("pack kernels");
-  return PAULE_OK;
+  return pack_v2(w_hh, img, as_stream(stream));
 }
 
 extern "C" size_t paule_tc_rnn_xchg_bytes(int64_t B) {
   (void)B;
   // header (barrier counters, error flag) + forward: 2 h images; backward: 2 x 4 gate images (sized for the larger user)
-  return (size_t)kXchgHeader + (size_t)8 * kXchgImageBytes;
+  const size_t v1 = (size_t)8 * kXchgImageBytes;
+  return (size_t)kXchgHeader + (v1 > kLLBytes ? v1 : kLLBytes);
 }
 
 extern "C" size_t paule_tc_img_seq_bytes(int64_t T, int64_t B, int64_t images_per_step) {
@@ -281,6 +282,7 @@ extern "C" int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h,
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(xchg) % 16 == 0);   // bulk copies need 16-byte aligned global addresses
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(h_img_seq) % 16 == 0);
   cudaStream_t s = as_stream(stream);
+  if (!use_v1_fwd()) return lstm_seq_fwd2(gates, packed, h, c, xchg, h_img_seq, T, B, s);
   static bool attr_set = false;
   const int smem = (int)sizeof(FwdSmem) + 1024;
   if (!attr_set) {
