@@ -62,7 +62,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = 16384u + (uint32_t)BN * 128u;   // A [128 x 128 B] + B [BN x 128 B]; BN % 8 == 0 keeps 1 KB alignment
   GemmBars& bars = *reinterpret_cast<GemmBars*>(base + (size_t)kGemmStages * stage_bytes);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   volatile int dummy_err = 0;
   volatile int* err = &dummy_err;
 
@@ -83,55 +83,57 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
   const uint32_t tmem = bars.tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int nt = tile % n_nt, rest = tile / n_nt, sp = rest % n_pairs, grp = rest / n_pairs;
-        const int t0 = 2 * sp;
-        const bool two = (t0 + 1 < steps);
-        const uint8_t* a0 = a_img + ((size_t)(grp * steps + t0) * KB) * (kRows * 128);
-        const uint8_t* bt = b_img + (size_t)nt * KB * BN * 128;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&bars.empty[s], ph ^ 1u, err);
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int nt = tile % n_nt, rest = tile / n_nt, sp = rest % n_pairs, grp = rest / n_pairs;
+      const int t0 = 2 * sp;
+      const bool two = (t0 + 1 < steps);
+      const uint8_t* a0 = a_img + ((size_t)(grp * steps + t0) * KB) * (kRows * 128);
+      const uint8_t* bt = b_img + (size_t)nt * KB * BN * 128;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&bars.empty[s], ph ^ 1u, err);
+        if (elect_one_sync()) {
           uint8_t* sa = base + (size_t)s * stage_bytes;
           mbar_arrive_expect_tx(&bars.full[s], (two ? 16384u : 8192u) + (uint32_t)BN * 128u);
           bulk_g2s(sa, a0 + (size_t)kb * (kRows * 128), kRows * 128, &bars.full[s]);
           if (two) bulk_g2s(sa + 8192, a0 + ((size_t)KB + kb) * (kRows * 128), kRows * 128, &bars.full[s]);
           bulk_g2s(sa + 16384, bt + (size_t)kb * BN * 128, (uint32_t)BN * 128u, &bars.full[s]);
-          if (++s == kGemmStages) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == kGemmStages) { s = 0; ph ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
-        const int ab = local & 1;
-        mbar_wait(&bars.tmem_empty[ab], (uint32_t)(((local >> 1) & 1) ^ 1), err);   // epilogue drained this buffer
+    // Warp-uniform control flow and elect.sync: descriptors stay in uniform registers, so the four UTCHMMA of a k-block
+    // issue back to back (under `if (lane == 0)` each one sits in an ELECT / R2UR / BRA.U.ANY loop, ~90 ns apiece).
+    const uint32_t idesc = make_idesc_bf16(128, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
+      const int ab = local & 1;
+      mbar_wait(&bars.tmem_empty[ab], (uint32_t)(((local >> 1) & 1) ^ 1), err);   // epilogue drained this buffer
+      tcgen05_fence_after();
+      const uint32_t d = tmem + (uint32_t)(ab * 256);
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&bars.full[s], ph, err);
         tcgen05_fence_after();
-        const uint32_t d = tmem + (uint32_t)(ab * 256);
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&bars.full[s], ph, err);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + 16384u);
+        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc_sw128(sa);
+        const uint64_t db = make_smem_desc_sw128(sa + 16384u);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(&bars.empty[s]);          // stage reusable once these MMAs have read it
-          if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+          if (kb == KB - 1) umma_commit(&bars.tmem_full[ab]);   // accumulator complete
         }
-        umma_commit(&bars.tmem_full[ab]);       // accumulator complete
+        __syncwarp();
+        if (++s == kGemmStages) { s = 0; ph ^= 1u; }
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     const int lg = warp & 3;                     // TMEM lane group this warp may access

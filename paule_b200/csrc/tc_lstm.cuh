@@ -4,6 +4,16 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#ifdef PAULE_TC_TRACE
+#define TRACE_DECL uint64_t tr_last = globaltimer_ns(); uint64_t tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TRACE(i) { const uint64_t _n = globaltimer_ns(); tr_acc[i] += _n - tr_last; tr_last = _n; }
+#define TRACE_DUMP(base) { uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + kXchgTraceOff) + (base); for (int _i = 0; _i < 8; ++_i) _o[_i] = tr_acc[_i]; }
+#else
+#define TRACE_DECL
+#define TRACE(i) {}
+#define TRACE_DUMP(base) {}
+#endif
+
 namespace paule {
 namespace tc {
 
@@ -35,7 +45,8 @@ constexpr int kXchgImageBytes = kNumKB * kRows * 128;  // 98304
 // 16 words are the N dimension, and the recurrent state travels between CTAs as 8-byte {bf16x2, step tag} elements
 // that carry their own validity (no counters, no release/acquire chain, no TMA on the exchange).
 constexpr int kWq = 16;                              // words per CTA ("word quarter" of a 64-word group)
-constexpr int kMaxQ = 6;                             // word quarters per launch: 23 x 6 = 138 / 24 x 6 = 144 CTAs <= 148 SMs
+constexpr int kMaxQ = 6;                             // word quarters per forward launch: 23 x 6 = 138 CTAs <= 148 SMs
+constexpr int kMaxQBwd = 5;                          // backward: clusters of 4 -> at most 132 co-resident CTAs; 24 x 5 = 120
 constexpr int kV2M = 128;                            // UMMA M: gate rows (forward) / hidden units (backward) per CTA
 constexpr int kV2SliceBytes = kNumKB * kV2M * 128;   // 196608: resident A operand [128, 768] bf16 = 384 TMEM columns
 constexpr int kV2WCols = kKPad / 2;                  // 384 32-bit TMEM columns (two bf16 per column)
@@ -54,6 +65,14 @@ constexpr size_t kPackedFwd2Off = kPackedV1Bytes;
 constexpr size_t kPackedBwd2Off = kPackedFwd2Off + (size_t)kFwd2Groups * kV2SliceBytes;
 constexpr size_t kPackedBytes = kPackedBwd2Off + (size_t)kBwd2Groups * 4 * kV2SliceBytes;
 
+
+// words per launch when B words are split into the fewest passes of at most max_q quarters, balanced over the passes
+inline int64_t pass_words(int64_t B, int max_q) {
+  const int64_t cap = (int64_t)max_q * kWq;
+  const int64_t n_pass = (B + cap - 1) / cap;
+  const int64_t per = (B + n_pass - 1) / n_pass;
+  return (per + kWq - 1) / kWq * kWq;
+}
 
 #ifdef __CUDACC__
 // Weight image of one CTA as tcgen05.st wants it: [48 column octets][128 rows][8 x u32]; u32 column c of row m holds the

@@ -9,8 +9,8 @@
 //   gate g's da_{t+1} of its 16 words out of the exchange (24 KB of payload), runs 48 tcgen05.mma (M=128, N=16, K=16;
 //   12 issuers, one TMEM accumulator) and owns the finalisation of hidden units 128 ugb + 32 g .. +31: TMEM lane group
 //   lg of every CTA holds the partial sums of the units that sibling lg finalises, so each epilogue warp pushes its
-//   lanes straight into sibling lg's shared memory (st.shared::cluster) and arrives on its mbarrier (release.cluster);
-//   no cluster-wide barrier in the loop.
+//   lanes straight into sibling lg's shared memory with st.async, whose bytes complete on the DESTINATION's mbarrier
+//   (tx-count): no release fence on the sender, no cluster-wide barrier in the loop.
 //   Reference operator replaced: autograd through aten::lstm (discrepancy.backward(), paule/paule.py:1052).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -19,12 +19,15 @@
 namespace paule {
 namespace tc {
 
+constexpr int kRedStride = 20;                      // floats per unit row: 16 words + pad (16-byte aligned, spreads banks)
+constexpr uint32_t kRedBytes = 4 * 32 * kWq * 4;    // payload per step and CTA
+
 struct Bwd2Smem {
   uint8_t b[kV2BBytes];         // B operand: gate g's da_{t+1} of this CTA's 16 words (24 KB)
-  float red[4][kWq][32];        // partial sums from the 4 gate CTAs for this CTA's 32 units (8 KB)
+  float red[4][32][kRedStride]; // partial sums from the 4 gate CTAs for this CTA's 32 units: [source][unit][word] (10 KB)
   uint64_t mma_done;
   uint64_t acc_free;
-  uint64_t red_full;            // 8 arrivals per step: two warps of each of the four CTAs of the cluster
+  uint64_t red_full;            // per step: 8 KB of st.async payload from the four CTAs of the cluster (tx-count)
   uint32_t tmem_base;
 };
 
@@ -36,11 +39,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// remote (or local) 16-byte store whose completion is signalled on the DESTINATION CTA's mbarrier (complete_tx 16 bytes):
+// the sender needs no fence and no separate arrive, the receiver sees the data once its barrier phase completes
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   cluster_addr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar)
+               : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -94,7 +99,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   if (tid == 0) {
     mbar_init(&S.mma_done, kNumKB);
     mbar_init(&S.acc_free, kB2EpiWarps);
-    mbar_init(&S.red_full, 8);
+    mbar_init(&S.red_full, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < kV2BBytes / 16; i += kB2Threads) reinterpret_cast<uint4*>(S.b)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -121,26 +126,42 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
     const uint32_t probe_off = (uint32_t)(((lane & 7) * 2 * 64 + ((lane >> 3) & 1) * 32) * 2);
     const int rows = min(kWq, Bv - qs * kWq);   // valid words of this quarter: only their rows travel
     const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 7) * 2 < rows);
+    TRACE_DECL
     for (int it = 1; it < T; ++it) {
       const uint8_t* src = ll + (size_t)(((it - 1) & 1) * 4 + g) * kLLBlockBytes + (size_t)kb * (kWq * 128);
+#ifdef PAULE_TC_TRACE
+      uint64_t ftr[2] = {0, 0};
+      if (!xchg_fetch_kblock(src, S.b + (size_t)kb * kWq * 128, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr)) break;
+      tr_acc[0] += ftr[0] - tr_last;   // until the probes pass
+      tr_last = ftr[0];
+      TRACE(1)
+#else
       if (!xchg_fetch_kblock(src, S.b + (size_t)kb * kWq * 128, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err)) break;
+#endif
       fence_proxy_async_shared();
       __syncwarp();
       mbar_wait(&S.acc_free, (uint32_t)((it - 1) & 1), err);
       tcgen05_fence_after();
+      TRACE(2)
       if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + kV2AccCol, ta + 8 * k, db + 2 * k, idesc, 1u);
         umma_commit(&S.mma_done);
       }
       __syncwarp();
+      TRACE(3)
+#ifdef PAULE_TC_TRACE
+      mbar_wait(&S.mma_done, (uint32_t)((it - 1) & 1), err);
+      TRACE(4)
+#endif
     }
+    if (blockIdx.x == 0 && kb == 3 && lane == 0) TRACE_DUMP(0)
   } else {
     // ===================== cell adjoint =====================
     // TMEM read role: lane group lg = the 32 units sibling lg finalises, column half ch = 8 words
     const int lg = warp & 3, ch = warp >> 2;
     const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(kV2AccCol + ch * 8);
-    const uint32_t red_dst = mapa_u32(smem_u32(&S.red[g][ch * 8][lane]), (uint32_t)lg);
+    const uint32_t red_dst = mapa_u32(smem_u32(&S.red[g][lane][ch * 8]), (uint32_t)lg);
     const uint32_t bar_dst = mapa_u32(smem_u32(&S.red_full), (uint32_t)lg);
     // cell role: unit pair a (units j, j+1) of word w
     const int a = lane & 15, w = (lane >> 4) + 2 * warp;
@@ -159,6 +180,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.acc_free);
 
+    TRACE_DECL
     for (int it = 0; it < T; ++it) {
       const int t = T - 1 - it;
       // (1) everything that does not depend on da_{t+1}: stash, cell states, external gradient
@@ -185,7 +207,10 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
       }
       if (it > 0) {
         float p[8];
+        if (tid == 0) mbar_arrive_expect_tx(&S.red_full, kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
+        TRACE(0)
         mbar_wait(&S.mma_done, (uint32_t)((it - 1) & 1), err);
+        TRACE(1)
         tcgen05_fence_after();
         tmem_ld_x8(taddr, p);
         if (it + 1 < T) {   // re-arm the accumulator: every MMA of the next step adds into it
@@ -193,19 +218,19 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           tmem_st_wait();
         }
         tcgen05_fence_before();
+        TRACE(2)
         // push this warp's partial sums (unit = lane of sibling lg's 32, words 8ch..8ch+7) and signal the sibling
-#pragma unroll
-        for (int i = 0; i < 8; ++i) st_cluster_f32(red_dst + (uint32_t)(i * 32 * 4), p[i]);
+        st_async_v4(red_dst, p[0], p[1], p[2], p[3], bar_dst);
+        st_async_v4(red_dst + 16, p[4], p[5], p[6], p[7], bar_dst);
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&S.acc_free);
-          mbar_arrive_remote_release(bar_dst);
-        }
+        if (lane == 0) mbar_arrive(&S.acc_free);
+        TRACE(3)
         mbar_wait_cluster(&S.red_full, (uint32_t)((it - 1) & 1), err);
+        TRACE(4)
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          const float2 v = *reinterpret_cast<const float2*>(&S.red[s][w][2 * a]);
-          dh.x += v.x; dh.y += v.y;
+          dh.x += S.red[s][2 * a][w];
+          dh.y += S.red[s][2 * a + 1][w];
         }
       }
       // (2) cell adjoint (oracle: manual_lstm_backward_input)
@@ -233,6 +258,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
         xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
       }
+      TRACE(5)
       if (valid) {   // off the critical path: bf16 images (A operand of the dX GEMM) and fp32 da_t over the stash
         if (img_seq != nullptr) {
           uint8_t* d = img_dst + (size_t)t * 4 * kXchgImageBytes;
@@ -246,7 +272,9 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
         *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
       }
+      TRACE(6)
     }
+    if (blockIdx.x == 0 && tid == 0) TRACE_DUMP(8)
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -265,9 +293,9 @@ int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float*
   // cooperative + cluster launch accepted by this driver?  (Nsight Compute rejects the combination with LaunchFailed;
   // PAULE_NO_COOP_CLUSTER=1 launches with the cluster attribute only -- at most 144 CTAs always fit the 148 SMs.)
   static int coop_ok = getenv("PAULE_NO_COOP_CLUSTER") ? 0 : 1;
-  const int64_t pass_words = (int64_t)kMaxQ * kWq;
-  for (int64_t r0 = 0; r0 < B; r0 += pass_words) {
-    const int Bv = (int)((B - r0 < pass_words) ? (B - r0) : pass_words);
+  const int64_t pw = pass_words(B, kMaxQBwd);
+  for (int64_t r0 = 0; r0 < B; r0 += pw) {
+    const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
     const int nq = (Bv + kWq - 1) / kWq;
     PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));
     PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)nq * 2 * 4 * kLLBlockBytes, s));

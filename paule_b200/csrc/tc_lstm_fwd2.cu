@@ -22,16 +22,6 @@
 #include "tc_common.cuh"
 #include "tc_lstm.cuh"
 
-#ifdef PAULE_TC_TRACE
-#define TRACE_DECL uint64_t tr_last = globaltimer_ns(); uint64_t tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define TRACE(i) { const uint64_t _n = globaltimer_ns(); tr_acc[i] += _n - tr_last; tr_last = _n; }
-#define TRACE_DUMP(base) { uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + kXchgTraceOff) + (base); for (int _i = 0; _i < 8; ++_i) _o[_i] = tr_acc[_i]; }
-#else
-#define TRACE_DECL
-#define TRACE(i) {}
-#define TRACE_DUMP(base) {}
-#endif
-
 namespace paule {
 namespace tc {
 
@@ -299,10 +289,10 @@ int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xc
     PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int64_t pass_words = (int64_t)kMaxQ * kWq;
-  // words are independent: batches larger than one launch's 96 words run as consecutive passes
-  for (int64_t r0 = 0; r0 < B; r0 += pass_words) {
-    const int Bv = (int)((B - r0 < pass_words) ? (B - r0) : pass_words);
+  const int64_t pw = pass_words(B, kMaxQ);
+  // words are independent: batches larger than one launch's 96 words run as consecutive, balanced passes
+  for (int64_t r0 = 0; r0 < B; r0 += pw) {
+    const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
     const int nq = (Bv + kWq - 1) / kWq;
     // error flag; exchange blocks of this pass start with the phase bit set (0x4040 per value): never a valid first step
     PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));

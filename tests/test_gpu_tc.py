@@ -73,7 +73,9 @@ def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
 
 def test_tc_is_repeatable(setup):
     """Same inputs -> the same outputs across launches up to fp32 summation order: the 12 MMA issuers of a step add their
-    k-blocks into one shared TMEM accumulator in arrival order, so the last bits may differ (like a split-K GEMM)."""
+    k-blocks into one shared TMEM accumulator in arrival order, so the last bits may differ (like a split-K GEMM).  A
+    last-bit difference occasionally flips the bf16 rounding of one h value (2^-9 relative), which the recurrence then
+    carries: the first steps must agree to fp32 round-off, the whole sequence to a few bf16 flips."""
     from paule_b200 import _lib, ops
     dev, lib, w = setup
     H, B, T = 720, 64, 40
@@ -86,7 +88,11 @@ def test_tc_is_repeatable(setup):
                                              xchg.data_ptr(), None, T, B, 1,ops._stream()))
         torch.cuda.synchronize()
         outs.append(h1)
-    assert (outs[0] - outs[1]).abs().max().item() < 1e-5 and (outs[0] - outs[2]).abs().max().item() < 1e-5
+    for other in outs[1:]:
+        d = (outs[0] - other).abs()
+        assert d[:2].max().item() < 2e-6, "steps 0 and 1 see only fp32 summation-order noise"
+        assert d.max().item() < 5e-4, "later steps: a few bf16 rounding flips of h, never more"
+        assert (d > 5e-5).float().mean().item() < 1e-2
 
 
 @pytest.mark.parametrize("B,T", [(64, 10), (37, 7), (100, 5)])
