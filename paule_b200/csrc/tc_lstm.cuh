@@ -57,7 +57,7 @@ constexpr int kFwd2Groups = (kH + 31) / 32;          // 23 CTAs per word quarter
 constexpr int kBwd2Groups = (kH + 127) / 128;        // 6 clusters of 4 (one CTA per gate) per word quarter, 128 units each
 // exchange block per (quarter, parity[, gate]): dense bf16 [12 kb][16 words][64 units], phase bit in bit 14 of every value
 constexpr int kLLBlockBytes = kNumKB * kWq * 128;     // 24576
-constexpr size_t kLLBytes = (size_t)kMaxQ * 2 * 4 * kLLBlockBytes;   // backward: 4 gate images per (quarter, parity)
+constexpr size_t kLLBytes = (size_t)kMaxQ * 4 * 2 * 4 * kLLBlockBytes;   // up to 6 groups x 4 quarters; backward: 4 gate images per parity
 
 // offsets of the v2 weight images inside the packed buffer of one layer
 constexpr size_t kPackedV1Bytes = (size_t)kFwdCtas * kFwdSliceBytes + (size_t)kBwdCtas * kBwdSliceBytes;
@@ -66,12 +66,24 @@ constexpr size_t kPackedBwd2Off = kPackedFwd2Off + (size_t)kFwd2Groups * kV2Slic
 constexpr size_t kPackedBytes = kPackedBwd2Off + (size_t)kBwd2Groups * 4 * kV2SliceBytes;
 
 
-// words per launch when B words are split into the fewest passes of at most max_q quarters, balanced over the passes
-inline int64_t pass_words(int64_t B, int max_q) {
-  const int64_t cap = (int64_t)max_q * kWq;
+// quarters per CTA for a batch of B words when a launch holds at most max_groups groups: the smallest of 1..4 that
+// fits the batch into one launch (latency first, and the most CTAs), 4 beyond that.  PAULE_RNN_NQ overrides (testing).
+inline int choose_nq(int64_t B, int max_groups) {
+  static const int forced = getenv("PAULE_RNN_NQ") ? atoi(getenv("PAULE_RNN_NQ")) : 0;
+  if (forced >= 1 && forced <= 4) return forced;
+  const int64_t cap = (int64_t)max_groups * kWq * 4;          // most words one launch can hold
+  const int64_t n_pass = (B + cap - 1) / cap;
+  const int64_t per = (B + n_pass - 1) / n_pass;              // words per (balanced) pass
+  for (int nq = 1; nq < 4; ++nq)
+    if (per <= (int64_t)max_groups * kWq * nq) return nq;
+  return 4;
+}
+// words per launch when B words are split into the fewest passes of at most max_groups groups of 16 nq words, balanced
+inline int64_t pass_words(int64_t B, int max_groups, int nq) {
+  const int64_t gw = (int64_t)kWq * nq, cap = (int64_t)max_groups * gw;
   const int64_t n_pass = (B + cap - 1) / cap;
   const int64_t per = (B + n_pass - 1) / n_pass;
-  return (per + kWq - 1) / kWq * kWq;
+  return (per + gw - 1) / gw * gw;
 }
 
 #ifdef __CUDACC__
@@ -88,21 +100,22 @@ __device__ __forceinline__ void load_weights_to_tmem(const uint8_t* __restrict__
   tmem_st_wait();
 }
 
-// Pulls k-block kb of a [16 words x 768] bf16 operand (2 KB: [16 rows][128 B]) out of an exchange block into the swizzled
+// Pulls k-block kb of a [16 NQ words x 768] bf16 operand ([16 NQ rows][128 B]) out of an exchange block into the swizzled
 // UMMA layout at `dst`, waiting until every value carries phase bit `phase`.  Called by one full warp.  Lanes 0..15
 // first poll ONE value of each of the 16 writer warps of the k-block (`probe_off`: byte offset of this lane's probe; a
 // warp's values leave the SM with one store instruction, so they become visible together), then the block is read once
-// with 16-byte loads; stragglers are re-read.  Returns false when the watchdog fired.
+// with 16-byte loads (all in flight together); stragglers are re-read.  Only the first `rows` rows (valid words) are
+// published and read.  Returns false when the watchdog fired.
+template <int NQ>
 __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int kb,
                                                   uint32_t phase, int lane, uint32_t probe_off, bool prober,
                                                   int rows, volatile int* err, uint64_t* trace = nullptr) {
-  // k-block 11 holds units 704..767: only 704..735 have a writer (chunks 0..3), the rest stays zero in shared memory;
-  // only the first `rows` rows (valid words of this quarter) are published and read
+  // k-block 11 holds units 704..767: only 704..735 have a writer (chunks 0..3), the rest stays zero in shared memory
   const int c = lane & 7;
   const bool active = (kb < kNumKB - 1) || (c < 4);
   uint32_t pending = 0u;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pending |= (4 * i < rows) ? (1u << i) : 0u;
+  for (int i = 0; i < 4 * NQ; ++i) pending |= (4 * i < rows) ? (1u << i) : 0u;
   {
     const uint8_t* pp = src + probe_off;
     uint64_t t0 = 0;
@@ -121,18 +134,18 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
   if (trace) { trace[0] = globaltimer_ns(); }
   for (unsigned int spin = 0; pending != 0u; ++spin) {
     if (trace) trace[1] += 1;
-    uint4 v[4];
+    uint4 v[4 * NQ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4 * NQ; ++i)
       if (((pending >> i) & 1u) && active && 4 * i + (lane >> 3) < rows) v[i] = xchg_load4(src + (size_t)(i * 32 + lane) * 16);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4 * NQ; ++i) {
       if ((pending >> i) & 1u) {
-        const bool ok = !active || 4 * i + (lane >> 3) >= rows || (((v[i].x & kPhaseMask) == phase) && ((v[i].y & kPhaseMask) == phase) &&
-                                    ((v[i].z & kPhaseMask) == phase) && ((v[i].w & kPhaseMask) == phase));
+        const int row = 4 * i + (lane >> 3);
+        const bool ok = !active || row >= rows || (((v[i].x & kPhaseMask) == phase) && ((v[i].y & kPhaseMask) == phase) &&
+                                                   ((v[i].z & kPhaseMask) == phase) && ((v[i].w & kPhaseMask) == phase));
         if (__all_sync(0xffffffffu, ok)) {
           pending &= ~(1u << i);
-          const int row = 4 * i + (lane >> 3);
           if (active && row < rows) {
             *reinterpret_cast<uint4*>(dst + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4)) =
                 make_uint4(v[i].x & ~kPhaseMask, v[i].y & ~kPhaseMask, v[i].z & ~kPhaseMask, v[i].w & ~kPhaseMask);
@@ -148,6 +161,9 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
   }
   return true;
 }
+
+// words per CTA group (16 NQ) for a batch of B words: small batches keep one quarter per CTA (lowest latency), large
+// ones put 2 or 4 quarters on a CTA (the grid is limited to 6 / 5 groups, so this is what scales the throughput)
 #endif  // __CUDACC__
 
 // host entry points of the v2 kernels (dispatched from paule_tc_lstm_seq_fwd / _bwd; PAULE_RNN_V1=1 keeps the v1 kernels)

@@ -20,14 +20,15 @@ namespace paule {
 namespace tc {
 
 constexpr int kRedStride = 20;                      // floats per unit row: 16 words + pad (16-byte aligned, spreads banks)
-constexpr uint32_t kRedBytes = 4 * 32 * kWq * 4;    // payload per step and CTA
+constexpr uint32_t kRedBytes = 4 * 32 * kWq * 4;    // payload per step, quarter and CTA
 
+template <int NQ>
 struct Bwd2Smem {
-  uint8_t b[kV2BBytes];         // B operand: gate g's da_{t+1} of this CTA's 16 words (24 KB)
-  float red[4][32][kRedStride]; // partial sums from the 4 gate CTAs for this CTA's 32 units: [source][unit][word] (10 KB)
-  uint64_t mma_done;
-  uint64_t acc_free;
-  uint64_t red_full;            // per step: 8 KB of st.async payload from the four CTAs of the cluster (tx-count)
+  uint8_t b[NQ][kV2BBytes];          // B operand per quarter: gate g's da_{t+1} of its 16 words
+  float red[NQ][4][32][kRedStride];  // partial sums from the 4 gate CTAs for this CTA's 32 units: [quarter][source][unit][word]
+  uint64_t mma_done[NQ];
+  uint64_t acc_free[NQ];
+  uint64_t red_full[NQ];             // per step and quarter: 8 KB of st.async payload from the four CTAs of the cluster
   uint32_t tmem_base;
 };
 
@@ -83,26 +84,31 @@ __device__ __forceinline__ void cluster_sync_all2() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int NQ>
 __global__ void __launch_bounds__(kB2Threads, 1)
 tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed,
                     const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
                     uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0) {
   extern __shared__ uint8_t smem_raw[];
-  Bwd2Smem& S = *reinterpret_cast<Bwd2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Smem = Bwd2Smem<NQ>;
+  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kGW = kWq * NQ;                        // words per CTA group (NQ independent quarters, see tc_lstm_fwd2.cu)
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int g = (int)cluster_ctarank_u32();                 // gate handled by this CTA's K slice
   const int cl = blockIdx.x >> 2;
-  const int ugb = cl % kBwd2Groups, qs = cl / kBwd2Groups;  // unit group (128 hidden units), word quarter
+  const int ugb = cl % kBwd2Groups, grp = cl / kBwd2Groups; // unit group (128 hidden units), word group
   volatile int* err = reinterpret_cast<volatile int*>(xchg + kXchgErrOff);
-  uint8_t* ll = xchg + kXchgHeader + (size_t)qs * 2 * 4 * kLLBlockBytes;   // [parity][gate] blocks of this quarter
+  uint8_t* ll = xchg + kXchgHeader + (size_t)grp * NQ * 2 * 4 * kLLBlockBytes;   // [quarter][parity][gate] blocks of this group
 
   if (tid == 0) {
-    mbar_init(&S.mma_done, kNumKB);
-    mbar_init(&S.acc_free, kB2EpiWarps);
-    mbar_init(&S.red_full, 1);
+    for (int q = 0; q < NQ; ++q) {
+      mbar_init(&S.mma_done[q], kNumKB);
+      mbar_init(&S.acc_free[q], kB2EpiWarps);
+      mbar_init(&S.red_full[q], 1);
+    }
     fence_mbar_init();
   }
-  for (int i = tid; i < kV2BBytes / 16; i += kB2Threads) reinterpret_cast<uint4*>(S.b)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < NQ * kV2BBytes / 16; i += kB2Threads) reinterpret_cast<uint4*>(&S.b[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_shared();
   if (warp == kB2EpiWarps) tmem_alloc<512>(&S.tmem_base);
   tcgen05_fence_before();
@@ -114,165 +120,191 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  cluster_sync_all2();   // every sibling's mbarriers are initialised before any remote arrive / DSMEM store
+  cluster_sync_all2();   // every sibling's mbarriers are initialised before any st.async targets them
 
   if (warp >= kB2EpiWarps) {
     // ===================== loader + MMA issuer of k-block kb =====================
     const int kb = warp - kB2EpiWarps;
     const uint32_t idesc = make_idesc_bf16(kV2M, kWq);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);
-    const uint64_t db = make_smem_desc_sw128(smem_u32(S.b + (size_t)kb * kWq * 128));
     // probes: lane p < 16 watches cell warp p&7 (rows 2(p&7), 2(p&7)+1) of writer CTA p>>3 of the k-block's two
     const uint32_t probe_off = (uint32_t)(((lane & 7) * 2 * 64 + ((lane >> 3) & 1) * 32) * 2);
-    const int rows = min(kWq, Bv - qs * kWq);   // valid words of this quarter: only their rows travel
-    const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 7) * 2 < rows);
     TRACE_DECL
     for (int it = 1; it < T; ++it) {
-      const uint8_t* src = ll + (size_t)(((it - 1) & 1) * 4 + g) * kLLBlockBytes + (size_t)kb * (kWq * 128);
-#ifdef PAULE_TC_TRACE
-      uint64_t ftr[2] = {0, 0};
-      if (!xchg_fetch_kblock(src, S.b + (size_t)kb * kWq * 128, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr)) break;
-      tr_acc[0] += ftr[0] - tr_last;   // until the probes pass
-      tr_last = ftr[0];
-      TRACE(1)
-#else
-      if (!xchg_fetch_kblock(src, S.b + (size_t)kb * kWq * 128, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err)) break;
-#endif
-      fence_proxy_async_shared();
-      __syncwarp();
-      mbar_wait(&S.acc_free, (uint32_t)((it - 1) & 1), err);
-      tcgen05_fence_after();
-      TRACE(2)
-      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + kV2AccCol, ta + 8 * k, db + 2 * k, idesc, 1u);
-        umma_commit(&S.mma_done);
-      }
-      __syncwarp();
-      TRACE(3)
+      for (int q = 0; q < NQ; ++q) {
+        const int rows = min(kWq, Bv - (grp * NQ + q) * kWq);   // valid words of this quarter: only their rows travel
+        if (rows <= 0) continue;
+        const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 7) * 2 < rows);
+        uint8_t* bdst = &S.b[q][(size_t)kb * kWq * 128];
+        const uint64_t db = make_smem_desc_sw128(smem_u32(bdst));
+        const uint8_t* src = ll + (size_t)((q * 2 + ((it - 1) & 1)) * 4 + g) * kLLBlockBytes + (size_t)kb * (kWq * 128);
 #ifdef PAULE_TC_TRACE
-      mbar_wait(&S.mma_done, (uint32_t)((it - 1) & 1), err);
-      TRACE(4)
+        uint64_t ftr[2] = {0, 0};
+        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr)) break;
+        tr_acc[0] += ftr[0] - tr_last;   // until the probes pass
+        tr_last = ftr[0];
+        TRACE(1)
+#else
+        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err)) break;
 #endif
+        fence_proxy_async_shared();
+        __syncwarp();
+        mbar_wait(&S.acc_free[q], (uint32_t)((it - 1) & 1), err);
+        tcgen05_fence_after();
+        TRACE(2)
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + (uint32_t)(kV2AccCol + q * kWq), ta + 8 * k, db + 2 * k, idesc, 1u);
+          umma_commit(&S.mma_done[q]);
+        }
+        __syncwarp();
+        TRACE(3)
+#ifdef PAULE_TC_TRACE
+        mbar_wait(&S.mma_done[q], (uint32_t)((it - 1) & 1), err);
+        TRACE(4)
+#endif
+      }
     }
     if (blockIdx.x == 0 && kb == 3 && lane == 0) TRACE_DUMP(0)
   } else {
     // ===================== cell adjoint =====================
-    // TMEM read role: lane group lg = the 32 units sibling lg finalises, column half ch = 8 words
+    // TMEM read role: lane group lg = the 32 units sibling lg finalises, column half ch = 8 words of a quarter
     const int lg = warp & 3, ch = warp >> 2;
     const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(kV2AccCol + ch * 8);
-    const uint32_t red_dst = mapa_u32(smem_u32(&S.red[g][lane][ch * 8]), (uint32_t)lg);
-    const uint32_t bar_dst = mapa_u32(smem_u32(&S.red_full), (uint32_t)lg);
-    // cell role: unit pair a (units j, j+1) of word w
+    const uint32_t red_dst = mapa_u32(smem_u32(&S.red[0][g][lane][ch * 8]), (uint32_t)lg);
+    const uint32_t bar_dst = mapa_u32(smem_u32(&S.red_full[0]), (uint32_t)lg);
+    // cell role: unit pair a (units j, j+1) of word w of every quarter
     const int a = lane & 15, w = (lane >> 4) + 2 * warp;
     const int j = ugb * kV2M + g * 32 + 2 * a;
-    const int wp = qs * kWq + w;
-    const bool valid = (wp < Bv) && (j < kH);
-    const int wg = w0 + wp;
+    const bool jvalid = j < kH;
     const size_t ll_off = ((size_t)((j >> 6) * kWq + w) * 64 + (size_t)(j & 63)) * 2;
-    const bool publish = (j < kH + 16) && (wp < Bv);   // k-block 11: pairs 0..15 (units 704..735) are read, zeros beyond H
-    uint8_t* img_dst = img_seq ? img_seq + (size_t)(wg / kRows) * (size_t)T * 4 * kXchgImageBytes + umma_offset(kRows, wg % kRows, j < kKPad ? j : 0)
-                               : nullptr;
-    float dc[2] = {0.f, 0.f};
-    tmem_zero_x8(taddr);
+    const bool jpublish = j < kH + 16;   // k-block 11: units 704..735 are read, zeros beyond H
+    float dc[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) dc[q][0] = dc[q][1] = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
     tmem_st_wait();
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.acc_free);
+    if (lane == 0)
+      for (int q = 0; q < NQ; ++q) mbar_arrive(&S.acc_free[q]);
 
     TRACE_DECL
     for (int it = 0; it < T; ++it) {
       const int t = T - 1 - it;
-      // (1) everything that does not depend on da_{t+1}: stash, cell states, external gradient
+      // (1) everything that does not depend on da_{t+1}: stash, cell states, external gradient of one quarter
       float2 s_i, s_f, s_g, s_o, ct, cp, dh;
-      s_i = s_f = s_g = s_o = ct = cp = dh = make_float2(0.f, 0.f);
-      float* grow = gates + ((size_t)t * Bs + (valid ? wp : 0)) * (4 * kH);
-      if (valid) {
-        s_i = *reinterpret_cast<const float2*>(grow + 0 * kH + j);
-        s_f = *reinterpret_cast<const float2*>(grow + 1 * kH + j);
-        s_g = *reinterpret_cast<const float2*>(grow + 2 * kH + j);
-        s_o = *reinterpret_cast<const float2*>(grow + 3 * kH + j);
-        ct = *reinterpret_cast<const float2*>(c_seq + ((size_t)t * Bs + wp) * kH + j);
-        if (t > 0) cp = *reinterpret_cast<const float2*>(c_seq + ((size_t)(t - 1) * Bs + wp) * kH + j);
-        if (dh_mode == 1) {
-          dh = *reinterpret_cast<const float2*>(dh_seq + ((size_t)t * Bs + wp) * kH + j);
-        } else if (dh_mode == 2 && (t >> 1) < (T >> 1)) {
-          const float2 v = *reinterpret_cast<const float2*>(dh_seq + ((size_t)(t >> 1) * Bs + wp) * kH + j);
-          dh = make_float2(0.5f * v.x, 0.5f * v.y);
+      auto load_q = [&](int q) {
+        s_i = s_f = s_g = s_o = ct = cp = dh = make_float2(0.f, 0.f);
+        const int wp = grp * kGW + q * kWq + w;
+        if (jvalid && wp < Bv) {
+          const float* grow = gates + ((size_t)t * Bs + wp) * (4 * kH);
+          s_i = *reinterpret_cast<const float2*>(grow + 0 * kH + j);
+          s_f = *reinterpret_cast<const float2*>(grow + 1 * kH + j);
+          s_g = *reinterpret_cast<const float2*>(grow + 2 * kH + j);
+          s_o = *reinterpret_cast<const float2*>(grow + 3 * kH + j);
+          ct = *reinterpret_cast<const float2*>(c_seq + ((size_t)t * Bs + wp) * kH + j);
+          if (t > 0) cp = *reinterpret_cast<const float2*>(c_seq + ((size_t)(t - 1) * Bs + wp) * kH + j);
+          if (dh_mode == 1) {
+            dh = *reinterpret_cast<const float2*>(dh_seq + ((size_t)t * Bs + wp) * kH + j);
+          } else if (dh_mode == 2 && (t >> 1) < (T >> 1)) {
+            const float2 v = *reinterpret_cast<const float2*>(dh_seq + ((size_t)(t >> 1) * Bs + wp) * kH + j);
+            dh = make_float2(0.5f * v.x, 0.5f * v.y);
+          }
+          if (dh_last != nullptr && t == T - 1) {
+            const float2 v = *reinterpret_cast<const float2*>(dh_last + (size_t)wp * kH + j);
+            dh.x += v.x; dh.y += v.y;
+          }
         }
-        if (dh_last != nullptr && t == T - 1) {
-          const float2 v = *reinterpret_cast<const float2*>(dh_last + (size_t)wp * kH + j);
-          dh.x += v.x; dh.y += v.y;
-        }
-      }
-      if (it > 0) {
+      };
+      // stage 1 of quarter q: partial sums out of TMEM and over to the sibling that finalises them (st.async: the bytes
+      // complete on the sibling's mbarrier)
+      auto push_q = [&](int q) {
         float p[8];
-        if (tid == 0) mbar_arrive_expect_tx(&S.red_full, kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
+        if (tid == 0) mbar_arrive_expect_tx(&S.red_full[q], kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
         TRACE(0)
-        mbar_wait(&S.mma_done, (uint32_t)((it - 1) & 1), err);
+        mbar_wait(&S.mma_done[q], (uint32_t)((it - 1) & 1), err);
         TRACE(1)
         tcgen05_fence_after();
-        tmem_ld_x8(taddr, p);
+        tmem_ld_x8(taddr + (uint32_t)(q * kWq), p);
         if (it + 1 < T) {   // re-arm the accumulator: every MMA of the next step adds into it
-          tmem_zero_x8(taddr);
+          tmem_zero_x8(taddr + (uint32_t)(q * kWq));
           tmem_st_wait();
         }
         tcgen05_fence_before();
         TRACE(2)
-        // push this warp's partial sums (unit = lane of sibling lg's 32, words 8ch..8ch+7) and signal the sibling
-        st_async_v4(red_dst, p[0], p[1], p[2], p[3], bar_dst);
-        st_async_v4(red_dst + 16, p[4], p[5], p[6], p[7], bar_dst);
+        st_async_v4(red_dst + (uint32_t)(q * 4 * 32 * kRedStride * 4), p[0], p[1], p[2], p[3], bar_dst + (uint32_t)(q * 8));
+        st_async_v4(red_dst + (uint32_t)(q * 4 * 32 * kRedStride * 4) + 16, p[4], p[5], p[6], p[7], bar_dst + (uint32_t)(q * 8));
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.acc_free);
+        if (lane == 0) mbar_arrive(&S.acc_free[q]);
         TRACE(3)
-        mbar_wait_cluster(&S.red_full, (uint32_t)((it - 1) & 1), err);
-        TRACE(4)
+      };
+      // stage 2 of quarter q: sum the four partials, cell adjoint, publish da_t
+      auto finalize_q = [&](int q) {
+        if (it > 0) {
+          mbar_wait_cluster(&S.red_full[q], (uint32_t)((it - 1) & 1), err);
+          TRACE(4)
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          dh.x += S.red[s][2 * a][w];
-          dh.y += S.red[s][2 * a + 1][w];
+          for (int s = 0; s < 4; ++s) {
+            dh.x += S.red[q][s][2 * a][w];
+            dh.y += S.red[q][s][2 * a + 1][w];
+          }
+        }
+        // cell adjoint (oracle: manual_lstm_backward_input)
+        float2 d_i, d_f, d_g, d_o;
+        {
+          const float tc0 = fast_tanh(fminf(fmaxf(ct.x, -15.f), 15.f)), tc1 = fast_tanh(fminf(fmaxf(ct.y, -15.f), 15.f));
+          const float do0 = dh.x * tc0, do1 = dh.y * tc1;
+          const float dc0 = dc[q][0] + dh.x * s_o.x * (1.f - tc0 * tc0), dc1 = dc[q][1] + dh.y * s_o.y * (1.f - tc1 * tc1);
+          d_i = make_float2(dc0 * s_g.x * s_i.x * (1.f - s_i.x), dc1 * s_g.y * s_i.y * (1.f - s_i.y));
+          d_f = make_float2(dc0 * cp.x * s_f.x * (1.f - s_f.x), dc1 * cp.y * s_f.y * (1.f - s_f.y));
+          d_g = make_float2(dc0 * s_i.x * (1.f - s_g.x * s_g.x), dc1 * s_i.y * (1.f - s_g.y * s_g.y));
+          d_o = make_float2(do0 * s_o.x * (1.f - s_o.x), do1 * s_o.y * (1.f - s_o.y));
+          dc[q][0] = dc0 * s_f.x;
+          dc[q][1] = dc1 * s_f.y;
+        }
+        const int wp = grp * kGW + q * kWq + w;
+        const bool wvalid = wp < Bv;
+        if (t > 0 && jpublish && wvalid) {   // da_t into the four gate blocks of the exchange: critical path of the next step
+          uint8_t* dst = ll + (size_t)((q * 2 + (it & 1)) * 4) * kLLBlockBytes + ll_off;
+          const uint32_t ph = phase_bits(it);
+          xchg_store(dst + 0 * (size_t)kLLBlockBytes, xchg_clamped(d_i) | ph);
+          xchg_store(dst + 1 * (size_t)kLLBlockBytes, xchg_clamped(d_f) | ph);
+          xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
+          xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
+        }
+        TRACE(5)
+        if (jvalid && wvalid) {   // off the critical path: bf16 images (A operand of the dX GEMM) and fp32 da_t over the stash
+          if (img_seq != nullptr) {
+            const int wg = w0 + wp;
+            const __nv_bfloat162 b_i = __floats2bfloat162_rn(d_i.x, d_i.y), b_f = __floats2bfloat162_rn(d_f.x, d_f.y);
+            const __nv_bfloat162 b_g = __floats2bfloat162_rn(d_g.x, d_g.y), b_o = __floats2bfloat162_rn(d_o.x, d_o.y);
+            uint8_t* d = img_seq + ((size_t)(wg / kRows) * (size_t)T + t) * 4 * kXchgImageBytes + umma_offset(kRows, wg % kRows, j);
+            *reinterpret_cast<uint32_t*>(d + 0 * (size_t)kXchgImageBytes) = *reinterpret_cast<const uint32_t*>(&b_i);
+            *reinterpret_cast<uint32_t*>(d + 1 * (size_t)kXchgImageBytes) = *reinterpret_cast<const uint32_t*>(&b_f);
+            *reinterpret_cast<uint32_t*>(d + 2 * (size_t)kXchgImageBytes) = *reinterpret_cast<const uint32_t*>(&b_g);
+            *reinterpret_cast<uint32_t*>(d + 3 * (size_t)kXchgImageBytes) = *reinterpret_cast<const uint32_t*>(&b_o);
+          }
+          float* grow = gates + ((size_t)t * Bs + wp) * (4 * kH);
+          *reinterpret_cast<float2*>(grow + 0 * kH + j) = d_i;
+          *reinterpret_cast<float2*>(grow + 1 * kH + j) = d_f;
+          *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
+          *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
+        }
+        TRACE(6)
+      };
+      // software pipeline over the quarters: quarter q's push overlaps quarter q-1's wait for its partial sums
+      load_q(0);
+#pragma unroll
+      for (int st = 0; st <= NQ; ++st) {
+        if (st < NQ && it > 0 && (grp * NQ + st) * kWq < Bv) push_q(st);
+        if (st >= 1 && (grp * NQ + st - 1) * kWq < Bv) {
+          finalize_q(st - 1);
+          if (st < NQ) load_q(st);
         }
       }
-      // (2) cell adjoint (oracle: manual_lstm_backward_input)
-      float2 d_i, d_f, d_g, d_o;
-      {
-        const float tc0 = fast_tanh(fminf(fmaxf(ct.x, -15.f), 15.f)), tc1 = fast_tanh(fminf(fmaxf(ct.y, -15.f), 15.f));
-        const float do0 = dh.x * tc0, do1 = dh.y * tc1;
-        const float dc0 = dc[0] + dh.x * s_o.x * (1.f - tc0 * tc0), dc1 = dc[1] + dh.y * s_o.y * (1.f - tc1 * tc1);
-        d_i = make_float2(dc0 * s_g.x * s_i.x * (1.f - s_i.x), dc1 * s_g.y * s_i.y * (1.f - s_i.y));
-        d_f = make_float2(dc0 * cp.x * s_f.x * (1.f - s_f.x), dc1 * cp.y * s_f.y * (1.f - s_f.y));
-        d_g = make_float2(dc0 * s_i.x * (1.f - s_g.x * s_g.x), dc1 * s_i.y * (1.f - s_g.y * s_g.y));
-        d_o = make_float2(do0 * s_o.x * (1.f - s_o.x), do1 * s_o.y * (1.f - s_o.y));
-        dc[0] = dc0 * s_f.x;
-        dc[1] = dc1 * s_f.y;
-      }
-      const __nv_bfloat162 b_i = __floats2bfloat162_rn(d_i.x, d_i.y), b_f = __floats2bfloat162_rn(d_f.x, d_f.y);
-      const __nv_bfloat162 b_g = __floats2bfloat162_rn(d_g.x, d_g.y), b_o = __floats2bfloat162_rn(d_o.x, d_o.y);
-      const uint32_t p_i = *reinterpret_cast<const uint32_t*>(&b_i), p_f = *reinterpret_cast<const uint32_t*>(&b_f);
-      const uint32_t p_g = *reinterpret_cast<const uint32_t*>(&b_g), p_o = *reinterpret_cast<const uint32_t*>(&b_o);
-      if (t > 0 && publish) {   // da_t into the four gate blocks of the exchange: critical path of the next step
-        uint8_t* dst = ll + (size_t)((it & 1) * 4) * kLLBlockBytes + ll_off;
-        const uint32_t ph = phase_bits(it);
-        xchg_store(dst + 0 * (size_t)kLLBlockBytes, xchg_clamped(d_i) | ph);
-        xchg_store(dst + 1 * (size_t)kLLBlockBytes, xchg_clamped(d_f) | ph);
-        xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
-        xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
-      }
-      TRACE(5)
-      if (valid) {   // off the critical path: bf16 images (A operand of the dX GEMM) and fp32 da_t over the stash
-        if (img_seq != nullptr) {
-          uint8_t* d = img_dst + (size_t)t * 4 * kXchgImageBytes;
-          *reinterpret_cast<uint32_t*>(d + 0 * (size_t)kXchgImageBytes) = p_i;
-          *reinterpret_cast<uint32_t*>(d + 1 * (size_t)kXchgImageBytes) = p_f;
-          *reinterpret_cast<uint32_t*>(d + 2 * (size_t)kXchgImageBytes) = p_g;
-          *reinterpret_cast<uint32_t*>(d + 3 * (size_t)kXchgImageBytes) = p_o;
-        }
-        *reinterpret_cast<float2*>(grow + 0 * kH + j) = d_i;
-        *reinterpret_cast<float2*>(grow + 1 * kH + j) = d_f;
-        *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
-        *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
-      }
-      TRACE(6)
     }
     if (blockIdx.x == 0 && tid == 0) TRACE_DUMP(8)
   }
@@ -282,29 +314,30 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   cluster_sync_all2();   // no CTA exits while a sibling may still address its shared memory
 }
 
-int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                  void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+template <int NQ>
+int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s) {
   static bool attr_set = false;
-  const int smem = (int)sizeof(Bwd2Smem) + 1024;
+  const int smem = (int)sizeof(Bwd2Smem<NQ>) + 1024;
   if (!attr_set) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   // cooperative + cluster launch accepted by this driver?  (Nsight Compute rejects the combination with LaunchFailed;
-  // PAULE_NO_COOP_CLUSTER=1 launches with the cluster attribute only -- at most 144 CTAs always fit the 148 SMs.)
+  // PAULE_NO_COOP_CLUSTER=1 launches with the cluster attribute only -- at most 120 CTAs always fit the 148 SMs.)
   static int coop_ok = getenv("PAULE_NO_COOP_CLUSTER") ? 0 : 1;
-  const int64_t pw = pass_words(B, kMaxQBwd);
+  const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQBwd, NQ);
   for (int64_t r0 = 0; r0 < B; r0 += pw) {
     const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
-    const int nq = (Bv + kWq - 1) / kWq;
+    const int ng = (int)((Bv + gw - 1) / gw);
     PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));
-    PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)nq * 2 * 4 * kLLBlockBytes, s));
+    PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)ng * 2 * 4 * NQ * kLLBlockBytes, s));
     float* gp = gates + r0 * 4 * kH;
     const float* cp = c + r0 * kH;
     const float* dsp = dh_seq ? dh_seq + r0 * kH : nullptr;
     const float* dlp = dh_last ? dh_last + r0 * kH : nullptr;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(kBwd2Groups * 4 * nq);
+    cfg.gridDim = dim3(kBwd2Groups * 4 * ng);
     cfg.blockDim = dim3(kB2Threads);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = s;
@@ -320,17 +353,27 @@ int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float*
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
     uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
                                        (int)r0);
     if (e != cudaSuccess && coop_ok) {
       cudaGetLastError();
       coop_ok = 0;
       cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0);
+      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0);
     }
     PAULE_CUDA(e);
   }
   return PAULE_OK;
+}
+
+int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+  switch (choose_nq(B, kMaxQBwd)) {
+    case 1: return launch_bwd2<1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
+    case 2: return launch_bwd2<2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
+    case 3: return launch_bwd2<3>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
+    default: return launch_bwd2<4>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
+  }
 }
 
 }  // namespace tc

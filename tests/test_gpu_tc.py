@@ -27,7 +27,7 @@ def _status(xchg):
     return int(xchg[2048:2052].view(torch.int32).item())    # kXchgErrOff: watchdog flag of the persistent kernels
 
 
-@pytest.mark.parametrize("B,T", [(64, 24), (1, 9), (37, 16), (100, 12), (130, 7)])
+@pytest.mark.parametrize("B,T", [(64, 24), (1, 9), (37, 16), (100, 12), (130, 7), (300, 6), (450, 5)])
 def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
     from paule_b200 import _lib, ops
     dev, lib, w = setup
