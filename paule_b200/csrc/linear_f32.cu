@@ -96,6 +96,119 @@ linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, cons
   }
 }
 
+// Skinny-K projection (K <= 64, contiguous rows): y[M,N] = x[M,K] W[N,K]^T + b.  The whole K extent of a 128 x 128 output
+// tile sits in shared memory (transposed, so that a thread's 8 rows / 8 columns are two 16-byte reads each), every
+// thread owns an 8 x 8 register tile: 64 FFMA per 4 LDS.128, rows written as 32-byte segments.  Used for the K = 30 / 60
+// input projections (147 MB of output per launch at B=64, T=200) and the K = 60 post_linear^T.
+constexpr int kSkM = 128, kSkN = 128, kSkPad = 4;
+__global__ void __launch_bounds__(256)
+linear_skinny_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                         float* __restrict__ C, int64_t M, int64_t N, int K, int accumulate) {
+  extern __shared__ __align__(16) float sk_smem[];
+  float* As = sk_smem;                                   // [K][128 + 4]
+  float* Ws = sk_smem + (size_t)K * (kSkM + kSkPad);     // [K][128 + 4]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * kSkM, n0 = (int64_t)blockIdx.x * kSkN;
+  const int64_t a_rows = (M - m0 < kSkM) ? (M - m0) : kSkM, w_rows = (N - n0 < kSkN) ? (N - n0) : kSkN;
+  const float* a_src = A + m0 * K;
+  const float* w_src = W + n0 * K;
+  for (int e = tid; e < kSkM * K; e += 256) {
+    const int r = e / K, kk = e - r * K;
+    As[kk * (kSkM + kSkPad) + r] = (r < a_rows) ? __ldg(a_src + e) : 0.f;
+  }
+  for (int e = tid; e < kSkN * K; e += 256) {
+    const int r = e / K, kk = e - r * K;
+    Ws[kk * (kSkN + kSkPad) + r] = (r < w_rows) ? __ldg(w_src + e) : 0.f;
+  }
+  __syncthreads();
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int kk = 0; kk < K; ++kk) {
+    const float4 a0 = *reinterpret_cast<const float4*>(As + kk * (kSkM + kSkPad) + ty * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(As + kk * (kSkM + kSkPad) + ty * 8 + 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(Ws + kk * (kSkN + kSkPad) + tx * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(Ws + kk * (kSkN + kSkPad) + tx * 8 + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+  }
+  const int64_t gn = n0 + tx * 8;
+  const bool vec = ((N & 3) == 0) && (gn + 8 <= N);
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = (bias != nullptr && gn + j < N) ? __ldg(bias + gn + j) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gr = m0 + ty * 8 + i;
+    if (gr >= M) continue;
+    float* crow = C + gr * N + gn;
+    if (vec) {
+      float4 o0 = make_float4(acc[i][0] + bv[0], acc[i][1] + bv[1], acc[i][2] + bv[2], acc[i][3] + bv[3]);
+      float4 o1 = make_float4(acc[i][4] + bv[4], acc[i][5] + bv[5], acc[i][6] + bv[6], acc[i][7] + bv[7]);
+      if (accumulate) {
+        const float4 p0 = *reinterpret_cast<const float4*>(crow), p1 = *reinterpret_cast<const float4*>(crow + 4);
+        o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+        o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+      }
+      *reinterpret_cast<float4*>(crow) = o0;
+      *reinterpret_cast<float4*>(crow + 4) = o1;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (gn + j >= N) continue;
+        float v = acc[i][j] + bv[j];
+        if (accumulate) v += crow[j];
+        crow[j] = v;
+      }
+    }
+  }
+}
+
+// Few-row projection (M <= 64 rows, e.g. the heads: one row per word): a CTA owns 8 output columns, keeps their weight
+// rows in shared memory and gives every warp a share of the rows; a row's dot products are split over the lanes along K
+// (coalesced reads of x) and reduced with shuffles.  The generic tile kernel needs 45 dependent load/sync rounds here.
+__global__ void __launch_bounds__(256)
+linear_fewrows_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                          float* __restrict__ C, int M, int64_t N, int K, int accumulate) {
+  extern __shared__ __align__(16) float fr_smem[];   // [8][K]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n0 = (int64_t)blockIdx.x * 8;
+  for (int e = tid; e < 8 * K; e += 256) {
+    const int j = e / K, kk = e - j * K;
+    fr_smem[e] = (n0 + j < N) ? __ldg(W + (n0 + j) * K + kk) : 0.f;
+  }
+  __syncthreads();
+  for (int m = warp; m < M; m += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* arow = A + (size_t)m * K;
+    for (int kk = lane; kk < K; kk += 32) {
+      const float a = __ldg(arow + kk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, fr_smem[j * K + kk], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (lane < 8 && n0 + lane < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v = (lane == j) ? acc[j] : v;
+      v += bias ? __ldg(bias + n0 + lane) : 0.f;
+      float* dst = C + (size_t)m * N + n0 + lane;
+      if (accumulate) v += *dst;
+      *dst = v;
+    }
+  }
+}
+
 __global__ void transpose_btc_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n_outer,
                                      int64_t n_inner, int64_t C) {
   // out[i, o, :] = in[o, i, :]; one thread per element, coalesced on the store side (C contiguous on both).
@@ -119,7 +232,29 @@ extern "C" int paule_linear_f32(const float* A, const float* W, const float* bia
   PAULE_REQUIRE(M >= 0 && N > 0 && K > 0 && a_inner > 0 && c_inner > 0);
   if (M == 0) return PAULE_OK;
   RowMap am{a_inner, a_outer_stride, a_inner_stride}, cm{c_inner, c_outer_stride, c_inner_stride};
-  if (M <= 64 && N > 32) {
+  // contiguous rows on both sides (row r of x at r*K, row r of y at r*N) and no pooled pair: the specialised kernels apply
+  const bool plain = a_pair_stride == 0 && (a_inner == 1 ? a_outer_stride == K : (a_inner_stride == K && a_outer_stride == a_inner * K)) &&
+                     (c_inner == 1 ? c_outer_stride == N : (c_inner_stride == N && c_outer_stride == c_inner * N));
+  if (plain && M <= 64 && N >= 64 && K <= 2048) {
+    const size_t smem = (size_t)8 * K * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      PAULE_CUDA(cudaFuncSetAttribute(linear_fewrows_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4));
+      attr_set = true;
+    }
+    linear_fewrows_f32_kernel<<<(unsigned)ceil_div(N, 8), 256, smem, as_stream(stream)>>>(A, W, bias, C, (int)M, N, (int)K,
+                                                                                          accumulate);
+  } else if (plain && K <= 64 && M >= 256 && N >= 64) {
+    const size_t smem = (size_t)K * (kSkM + kSkPad + kSkN + kSkPad) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      PAULE_CUDA(cudaFuncSetAttribute(linear_skinny_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      64 * (kSkM + kSkPad + kSkN + kSkPad) * 4));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(N, kSkN), (unsigned)ceil_div(M, kSkM));
+    linear_skinny_f32_kernel<<<grid, 256, smem, as_stream(stream)>>>(A, W, bias, C, M, N, (int)K, accumulate);
+  } else if (M <= 64 && N > 32) {
     // few rows (heads: M = words): narrow column tiles so that the grid still covers many SMs
     constexpr int BM = 64, BN = 16, BK = 16, TM = 4, TN = 1;
     dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
