@@ -228,6 +228,29 @@ def run_ours(args):
     # ---- the dominant kernel alone (live CUDA-event timing of the recurrent step kernels)
     roof = dominant_kernel_roofline(planner, math, dev)
 
+    # ---- the other half of BASELINE.json's metric: ms per inner step at batch 1 (rank 0), and the throughput regime
+    # (one rank's shard of configs[3]: 256 words, 1 s utterances) as supplementary figures
+    extra = {}
+    if rank == 0:
+        def timed(Bx, Tx, steps):
+            cpx, tmx = O.synthetic_inputs(Bx, Tx, seed=77)
+            pl = P.BatchPlanner(pred, emb, cpx.to(dev), tmx.to(dev), None, max_log_steps=steps + 4, math=math)
+            pl.step(3)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pl.step(steps)
+            b.record()
+            torch.cuda.synchronize()
+            pl.close()
+            return a.elapsed_time(b) / steps
+        ms1 = timed(1, T, 10)
+        extra["batch1"] = {"ms_per_inner_step": ms1, "steps_words_per_s": 1e3 / ms1, "T": T}
+        if not args.no_cpu_baseline:
+            msL = timed(256, 400, 3)
+            extra["configs[3]_shard"] = {"words": 256, "T": 400, "ms_per_inner_step": msL, "steps_words_per_s": 256e3 / msL,
+                                         "tflops_algorithmic": flops_per_word_step(400) * 256e3 / msL / 1e12}
+
     t_ms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -262,6 +285,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "tflops_algorithmic": flops_per_word_step(T) * world * B * K / (ms_max * 1e-3) / 1e12,
             "loss_first_last": [loss_curve[0], loss_curve[-1]],
+            "other": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -275,7 +299,7 @@ def launches_per_step(T, math):
     if math == 0:
         rec = 2 * (T + Tm + Tm)                       # one launch per time step, forward + backward
     else:
-        rec = 2 * 3                                   # one persistent launch per layer and direction (per 64-word group)
+        rec = 2 * 3                                   # one persistent launch per layer and direction (batches <= 80 words)
     return 1 + gemms + rec + 2 + 1                    # tick, GEMMs, recurrences, loss (2), Adam  (= 20 for the tcgen05 path)
 
 
@@ -329,9 +353,16 @@ def dominant_kernel_roofline(planner, math, dev):
     flops_seq = 2.0 * B * 4 * H * H * T                 # T cell steps of a [B,H]x[H,4H] GEMM
     achieved = flops_seq / (out[name] * 1e-3) / 1e12
     launches = T if math == 0 else 1
-    return {"bound": "tensor", "kernel": ("lstm_step_%s_f32" % name) if math == 0 else ("tc_lstm_seq_%s" % name),
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if math != 0 and os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(name)
+        if tj:
+            traffic = tj["dram_bytes_per_word_step"] * B * T   # per launch, like `achieved`
+    kname = {"fwd": "tc_lstm_fwd2_kernel<1>", "bwd": "tc_lstm_bwd2_kernel<1>"}[name]
+    return {"bound": "tensor", "kernel": ("lstm_step_%s_f32" % name) if math == 0 else kname,
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-            "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long sequence)",
+            "traffic": traffic, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long sequence)",
             "us_per_cell_step": {k: v * 1e3 / T for k, v in out.items()},
             "launches_timed": launches, "flops_per_launch": flops_seq / launches}
 

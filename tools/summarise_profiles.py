@@ -1,5 +1,5 @@
 """Summarise gpurun_out/launches.csv and *.ncu-rep into small text files under profiles/ (run in the build container)."""
-import csv, io, os, subprocess, sys, collections, re
+import csv, io, json, os, subprocess, sys, collections, re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 out_dir = os.path.join(ROOT, "profiles"); os.makedirs(out_dir, exist_ok=True)
@@ -68,3 +68,24 @@ for rep in ("prof_fwd", "prof_bwd", "prof_gemm", "prof_elem"):
                 if any(m in h for m in METRICS):
                     f.write(f"{h:80s} {v:>20s} {u}\n")
     print("wrote", rep)
+
+# ---- DRAM traffic of the recurrent kernels per (word, cell step), for bench.py's roofline.traffic
+def _metric(path, name):
+    for line in open(path):
+        if line.startswith(name + " "):
+            parts = line.split()
+            v, unit = float(parts[1]), parts[2]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-6, "ms": 1e-3, "ns": 1e-9}.get(unit, 1)
+    return None
+traffic = {}
+for kind in ("fwd", "bwd"):
+    path = os.path.join(out_dir, f"{tag}_ncu_{kind}.txt")
+    if os.path.exists(path):
+        rd, wr, dur = _metric(path, "dram__bytes_read.sum"), _metric(path, "dram__bytes_write.sum"), _metric(path, "gpu__time_duration.sum")
+        if rd is not None and wr is not None and dur:
+            # the captured launch is one layer of the bench workload (B = 64): 200 steps if it ran > 400 us, else 100
+            steps = 200 if dur > 400e-6 else 100
+            traffic[kind] = {"dram_bytes_per_word_step": (rd + wr) / (64 * steps), "captured_steps": steps, "captured_us": dur * 1e6,
+                             "source": f"profiles/{tag}_ncu_{kind}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+json.dump(traffic, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
+print("traffic", traffic)
