@@ -251,6 +251,11 @@ typedef struct paule_plan {
   /* workspace: >= paule_plan_workspace_bytes() */
   void* workspace;
   size_t workspace_bytes;
+  /* ragged batches (the reference plans one word per call, so a word never sees another word's frames):
+     device int32 [B], cp frames of every word, 13 <= word_frames[b] <= T; word b has word_frames[b]/2 mel frames
+     (paule/models.py:353 AvgPool1d(2,2)), its semvec is taken at that last frame (models.py:442), every loss term is a
+     mean over the word's own frames, and frames beyond it are padding that receives a zero gradient.  NULL: all T. */
+  const int32_t* word_frames;
 } paule_plan;
 
 PAULE_API size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);

@@ -35,6 +35,7 @@ class Plan(C.Structure):
         ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("clamp", f32),
         ("loss_log", vp), ("pred_mel", vp), ("pred_sv", vp), ("grad_out", vp),
         ("workspace", vp), ("workspace_bytes", sz),
+        ("word_frames", vp),
     ]
 
 

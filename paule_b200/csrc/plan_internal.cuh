@@ -11,8 +11,13 @@ namespace paule {
 // (step_count may be NULL: slot 0).
 int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const float* tsv, const float* cp,
                      float* terms, const int32_t* step_count, int slots, float* dmel, float* dsv, float* dcp_smooth,
-                     float* scratch, int64_t T, int64_t Tm, int64_t B, int64_t C, int64_t Cm, int64_t S,
-                     int objective, paule_stream_t stream);
+                     float* scratch, int64_t T, int64_t Tm, const int32_t* word_T, int64_t B, int64_t C, int64_t Cm,
+                     int64_t S, int objective, paule_stream_t stream);
+
+// ragged batches (word_T[b] cp frames per word): out[b,:] = seq[word_T[b]/2 - 1, b, :], and its adjoint into a zero-filled
+// [Tm,B,H] sequence
+int gather_last(const float* seq, const int32_t* word_T, float* out, int64_t B, int64_t H, paule_stream_t stream);
+int scatter_last(const float* rows, const int32_t* word_T, float* seq, int64_t Tm, int64_t B, int64_t H, paule_stream_t stream);
 
 // paule_adam_clamp_f32 that can also emit the summed gradient (log_gradients, paule.py:1062-1063).
 int adam_clamp_logged(float* cp, const float* g_a, const float* g_b, float* m, float* v, const int32_t* step_count,

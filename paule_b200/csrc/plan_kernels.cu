@@ -32,7 +32,7 @@ __device__ __forceinline__ float d5(float v0, float v1, float v3, float v4) {
 //   x -> vel (valid: T-4) -> acc (T-8) -> jerk (T-12);  r3 = s_j*jerk; r2 = D^T r3; r1 = D^T r2 + s_v*vel; g = D^T r1 + ll part
 __global__ void __launch_bounds__(256)
 smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth, float* __restrict__ partial,
-                    int64_t T, int64_t B, int64_t C, int n_tiles) {
+                    int64_t Tmax, const int32_t* __restrict__ word_T, int64_t B, int64_t C, int n_tiles) {
   constexpr int W = kTileT + 2 * kHalo;  // 88 frames
   __shared__ float sx[W * kMaxC];
   __shared__ float sa[W * kMaxC];
@@ -42,6 +42,8 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   const int64_t t0 = (int64_t)blockIdx.x * kTileT;
   const int tid = threadIdx.x;
   const int n = W * (int)C;
+  // ragged batches: word b has T frames; frames [T, Tmax) are padding and get a zero gradient
+  const int64_t T = word_T ? (int64_t)word_T[b] : Tmax;
   const float sv = 2.0f * kVelWeight / (float)((T - 4) * C);
   const float sj = 2.0f * kJerkWeight / (float)((T - 12) * C);
   const float sl = 2.0f * kLocalLinearWeight / (float)((T - 2) * C);
@@ -148,7 +150,8 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   for (int e = tid; e < kTileT * (int)C; e += 256) {
     const int f = kHalo + e / (int)C, c = e % (int)C;
     const int64_t t = t0 + e / (int)C;
-    if (t >= T) continue;
+    if (t >= Tmax) continue;
+    if (t >= T) { dcp_smooth[(t * B + b) * C + c] = 0.f; continue; }
     const int idx = f * (int)C + c;
     float g = adj(sa, idx, f);
     // local-linear adjoint: ll[i] = x[i+1] - (x[i] + x[i+2])/2, i in [0,T-2); g_ll[t] = sl*(ll[t-1] - ll[t]/2 - ll[t-2]/2)
@@ -191,11 +194,13 @@ __global__ void __launch_bounds__(256)
 word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, const float* __restrict__ sv,
                  const float* __restrict__ tsv, const float* __restrict__ partial, int n_tiles,
                  float* __restrict__ terms, const int32_t* __restrict__ step_count, int slots,
-                 float* __restrict__ dmel, float* __restrict__ dsv, int64_t T, int64_t Tm,
-                 int64_t B, int64_t C, int64_t Cm, int64_t S, int objective) {
+                 float* __restrict__ dmel, float* __restrict__ dsv, int64_t Tmax, int64_t Tm_max,
+                 const int32_t* __restrict__ word_T, int64_t B, int64_t C, int64_t Cm, int64_t S, int objective) {
   __shared__ float sh[8];
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
+  const int64_t T = word_T ? (int64_t)word_T[b] : Tmax;        // this word's cp frames
+  const int64_t Tm = word_T ? (int64_t)(word_T[b] / 2) : Tm_max;  // ... and mel frames
   const bool use_mel = objective != PAULE_OBJ_SEMVEC, use_sem = objective != PAULE_OBJ_ACOUSTIC;
   float sm = 0.f;
   const int64_t nm = Tm * Cm;
@@ -237,10 +242,10 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
   }
   // d(w*sqrt(mean(e^2)))/de = w*e/(N*rmse); eps = 0 -> NaN at zero error, as in the reference (paule.py:68)
   const float gm = use_mel ? kMelWeight / ((float)nm * rmse_m) : 0.f;
-  for (int64_t e = tid; e < nm; e += 256) {
+  for (int64_t e = tid; e < Tm_max * Cm; e += 256) {   // padded mel frames get a zero gradient
     const int64_t t = e / Cm, c = e % Cm;
     const int64_t off = (t * B + b) * Cm + c;
-    dmel[off] = use_mel ? gm * (mel[off] - tmel[off]) : 0.f;
+    dmel[off] = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
   }
   if (dsv != nullptr) {
     const float gs = (use_sem && sv != nullptr) ? kSemWeight / ((float)S * rmse_s) : 0.f;
@@ -250,6 +255,21 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
 }
 
 __global__ void step_tick_kernel(int32_t* step_count) { *step_count += 1; }
+
+// ragged batches: row b of `out` [B,H] = seq[word_T[b]/2 - 1, b, :]  (EmbeddingModel takes h at lens[b]-1, models.py:442)
+__global__ void gather_last_kernel(const float* __restrict__ seq, const int32_t* __restrict__ word_T, float* __restrict__ out,
+                                   int64_t B, int64_t H) {
+  const int64_t b = blockIdx.x;
+  const int64_t t = (int64_t)(word_T[b] / 2) - 1;
+  for (int64_t j = threadIdx.x; j < H; j += blockDim.x) out[b * H + j] = seq[(t * B + b) * H + j];
+}
+// ... and its adjoint: seq[word_T[b]/2 - 1, b, :] = rows[b, :] in a zero-filled [Tm,B,H] buffer
+__global__ void scatter_last_kernel(const float* __restrict__ rows, const int32_t* __restrict__ word_T, float* __restrict__ seq,
+                                    int64_t B, int64_t H) {
+  const int64_t b = blockIdx.x;
+  const int64_t t = (int64_t)(word_T[b] / 2) - 1;
+  for (int64_t j = threadIdx.x; j < H; j += blockDim.x) seq[(t * B + b) * H + j] = rows[b * H + j];
+}
 
 // torch/optim/adam.py::_single_tensor_adam (foreach/fused variants are arithmetic-equivalent):
 //   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); x.addcdiv_(m, sqrt(v)/sqrt(bc2) + eps, -lr/bc1)
@@ -333,22 +353,35 @@ extern "C" size_t paule_plan_loss_scratch_floats(int64_t T, int64_t B) {
 
 namespace paule {
 
+int gather_last(const float* seq, const int32_t* word_T, float* out, int64_t B, int64_t H, paule_stream_t stream) {
+  gather_last_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(seq, word_T, out, B, H);
+  PAULE_LAUNCH_CHECK("gather_last_kernel");
+  return PAULE_OK;
+}
+
+int scatter_last(const float* rows, const int32_t* word_T, float* seq, int64_t Tm, int64_t B, int64_t H, paule_stream_t stream) {
+  PAULE_CUDA(cudaMemsetAsync(seq, 0, (size_t)(Tm * B * H) * sizeof(float), as_stream(stream)));
+  scatter_last_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(rows, word_T, seq, B, H);
+  PAULE_LAUNCH_CHECK("scatter_last_kernel");
+  return PAULE_OK;
+}
+
 int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const float* tsv, const float* cp,
                      float* terms, const int32_t* step_count, int slots, float* dmel, float* dsv, float* dcp_smooth,
-                     float* scratch, int64_t T, int64_t Tm, int64_t B, int64_t C, int64_t Cm, int64_t S,
-                     int objective, paule_stream_t stream) {
+                     float* scratch, int64_t T, int64_t Tm, const int32_t* word_T, int64_t B, int64_t C, int64_t Cm,
+                     int64_t S, int objective, paule_stream_t stream) {
   PAULE_REQUIRE(mel && tmel && cp && terms && dmel && dcp_smooth && scratch && slots >= 1);
   PAULE_REQUIRE((sv == nullptr) == (tsv == nullptr));
   PAULE_REQUIRE(T >= 13 && Tm >= 1 && B >= 1 && C >= 1 && C <= kMaxC && Cm >= 1 && S >= 1);
   PAULE_REQUIRE(objective >= 0 && objective <= 2);
   if (objective != PAULE_OBJ_ACOUSTIC) PAULE_REQUIRE(sv && tsv && dsv);
   const int n_tiles = (int)ceil_div(T, (int64_t)kTileT);
-  smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, B, C,
-                                                                                 n_tiles);
+  smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B,
+                                                                                 C, n_tiles);
   PAULE_LAUNCH_CHECK("smooth_terms_kernel");
   word_loss_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(mel, tmel, sv, tsv, scratch, n_tiles, terms,
-                                                               step_count, slots, dmel, dsv, T, Tm, B, C, Cm, S,
-                                                               objective);
+                                                               step_count, slots, dmel, dsv, T, Tm, word_T, B, C, Cm,
+                                                               S, objective);
   PAULE_LAUNCH_CHECK("word_loss_kernel");
   return PAULE_OK;
 }
@@ -379,8 +412,8 @@ extern "C" int paule_plan_loss_f32(const float* mel, const float* tmel, const fl
                                    const float* cp, float* terms, float* dmel, float* dsv, float* dcp_smooth,
                                    float* scratch, int64_t T, int64_t Tm, int64_t B, int64_t C, int64_t Cm,
                                    int64_t S, int objective, paule_stream_t stream) {
-  return plan_loss_logged(mel, tmel, sv, tsv, cp, terms, nullptr, 1, dmel, dsv, dcp_smooth, scratch, T, Tm, B, C, Cm,
-                          S, objective, stream);
+  return plan_loss_logged(mel, tmel, sv, tsv, cp, terms, nullptr, 1, dmel, dsv, dcp_smooth, scratch, T, Tm, nullptr, B, C,
+                          Cm, S, objective, stream);
 }
 
 extern "C" int paule_step_tick(int32_t* step_count, paule_stream_t stream) {

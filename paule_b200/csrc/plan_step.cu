@@ -128,8 +128,12 @@ int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, pa
     PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
   }
   PAULE_TRY(recur_forward(p, p->emb1, Tm, w.gates_1, w.h_1, w.c_1, w, nullptr, s));
-  PAULE_TRY(paule_linear_f32(w.h_1 + (Tm - 1) * B * H, p->head_w, p->head_b, p->pred_sv, B, S, H, 1, H, 0, 0, 1, S, 0,
-                             0, s));
+  const float* h_last = w.h_1 + (Tm - 1) * B * H;
+  if (p->word_frames) {   // ragged: every word's own last mel frame (models.py:442); dh1_last is free until the backward
+    PAULE_TRY(gather_last(w.h_1, p->word_frames, w.dh1_last, B, H, s));
+    h_last = w.dh1_last;
+  }
+  PAULE_TRY(paule_linear_f32(h_last, p->head_w, p->head_b, p->pred_sv, B, S, H, 1, H, 0, 0, 1, S, 0, 0, s));
   return PAULE_OK;
 }
 
@@ -160,11 +164,19 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
   PAULE_TRY(forward_models(p, w, need_sv, s));                                    // paule.py:913, :924
   PAULE_TRY(plan_loss_logged(p->pred_mel, p->target_mel, need_sv ? p->pred_sv : nullptr,
                              need_sv ? p->target_sv : nullptr, p->cp, p->loss_log, p->step_count, p->log_slot_count,
-                             w.dmel, w.dsv, w.dcp_smooth, w.partial, T, Tm, B, C, Cm, S, p->objective, s));  // :986
+                             w.dmel, w.dsv, w.dcp_smooth, w.partial, T, Tm, p->word_frames, B, C, Cm, S, p->objective,
+                             s));  // :986
   if (use_sem) {                                                                   // discrepancy.backward(), :1052
     // head: dh1[Tm-1] = dsv W_head
     PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));
-    PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, s));
+    if (p->word_frames) {
+      // ragged: the semvec gradient enters layer 1 at every word's own last frame -- a full external-gradient sequence that
+      // is zero elsewhere (dhp is free until post_linear^T), so the recurrent kernels stay unaware of word lengths
+      PAULE_TRY(scatter_last(w.dh1_last, p->word_frames, w.dhp, Tm, B, H, s));
+      PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, w.dhp, 1, nullptr, Tm, w.dh0, 0, w, s));
+    } else {
+      PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, s));
+    }
     PAULE_TRY(layer_backward(p, p->emb0, w.gates_0, w.c_0, w.dh0, 1, nullptr, Tm, w.dmel, 1, w, s));  // += d(mel loss)/dmel
   }
   // post_linear^T; the un-pooling (x0.5 to both frames of a pair) is folded into the BPTT's dh load

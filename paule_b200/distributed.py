@@ -6,7 +6,7 @@ Backend: ``torch.distributed`` -- NCCL over NVLink on the GPU box, gloo in the C
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -73,3 +73,82 @@ def plan_sharded(make_planner, initial_cp: torch.Tensor, target_mel: torch.Tenso
     cps = gather_words(planner.planned_cp(), n_words, gather_dst, group)
     loss = gather_words(planner.losses()["total"].transpose(0, 1).contiguous(), n_words, gather_dst, group)
     return cps, (None if loss is None else loss.transpose(0, 1))
+
+
+# ---- ragged jobs: length-bucketed sharding ----------------------------------------------
+def length_buckets(lengths: Sequence[int], world_size: int) -> List[List[int]]:
+    """Assign words of different lengths to ranks.  A rank plans its words in lock-step, padded to ITS longest word, so
+    its cost is (longest word) x (number of words): words are sorted by length (longest first, ties by index) and cut
+    into ``world_size`` contiguous runs whose largest cost is minimal -- ranks with long words get fewer of them, and no
+    word is padded beyond the longest word of its own rank.  Returns the word indices of every rank (possibly empty)."""
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    L = [int(lengths[i]) for i in order]
+
+    def cuts(limit):   # greedy: longest run from `start` whose cost L[start] * n stays within limit
+        out, start = [], 0
+        while start < len(L):
+            n = max(1, limit // L[start])
+            out.append((start, min(len(L), start + n)))
+            start += n
+        return out
+
+    if not L:
+        return [[] for _ in range(world_size)]
+    lo, hi = L[0], L[0] * len(L)
+    while lo < hi:   # smallest cost limit that needs at most world_size runs
+        mid = (lo + hi) // 2
+        if len(cuts(mid)) <= world_size:
+            hi = mid
+        else:
+            lo = mid + 1
+    runs = cuts(lo)
+    return [[order[i] for i in range(a, b)] for a, b in runs] + [[] for _ in range(world_size - len(runs))]
+
+
+def plan_sharded_ragged(make_planner, cps: Sequence[torch.Tensor], mels: Sequence[torch.Tensor], n_steps: int,
+                        group: Optional[dist.ProcessGroup] = None):
+    """Ragged job over the ranks of ``group``: ``cps[b]`` is [T_b, C], ``mels[b]`` [T_b // 2, Cm].  Every rank plans its
+    length bucket padded to the bucket's longest word (``make_planner(cp_pad, mel_pad, lengths)``) and one all_gather
+    returns, on every rank, the planned cps as a list in the ORIGINAL word order plus the loss log [steps, B]."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lengths = [int(c.shape[0]) for c in cps]
+    buckets = length_buckets(lengths, ws)
+    mine = buckets[rank]
+    T_glob, C = max(lengths), cps[0].shape[1]
+    dev = cps[0].device
+    if mine:
+        T_loc = max(lengths[i] for i in mine)
+        cp_pad = cps[0].new_zeros((len(mine), T_loc, C))
+        mel_pad = mels[0].new_zeros((len(mine), T_loc // 2, mels[0].shape[1]))
+        for k, i in enumerate(mine):
+            cp_pad[k, :lengths[i]] = cps[i]
+            mel_pad[k, :lengths[i] // 2] = mels[i]
+        planner = make_planner(cp_pad, mel_pad, [lengths[i] for i in mine])
+        planner.step(n_steps)
+        out_cp, out_loss = planner.planned_cp(), planner.losses()["total"].transpose(0, 1).contiguous()
+    else:
+        T_loc = 0
+        out_cp, out_loss = cps[0].new_zeros((0, 0, C)), cps[0].new_zeros((0, n_steps))
+    # one collective: every rank's block padded to [largest bucket, T_glob * C + n_steps]
+    mx = max(len(b) for b in buckets)
+    block = torch.zeros((mx, T_glob * C + n_steps), dtype=out_cp.dtype, device=dev)
+    if mine:
+        block[:len(mine), :T_loc * C] = out_cp.reshape(len(mine), -1).to(dev)
+        block[:len(mine), T_glob * C:] = out_loss.to(dev)
+    if ws > 1:
+        bufs = [torch.empty_like(block) for _ in range(ws)]
+        dist.all_gather(bufs, block, group=group)
+    else:
+        bufs = [block]
+    planned: List[Optional[torch.Tensor]] = [None] * len(lengths)
+    loss = torch.zeros((n_steps, len(lengths)), dtype=out_cp.dtype, device=dev)
+    for r, idx in enumerate(buckets):
+        for k, i in enumerate(idx):
+            # rank r laid word i out with row stride T_r * C (its own padding), then zero-filled up to T_glob * C
+            T_r = max(lengths[j] for j in idx)
+            planned[i] = bufs[r][k, :T_r * C].reshape(T_r, C)[:lengths[i]].clone()
+            loss[:, i] = bufs[r][k, T_glob * C:]
+    return planned, loss

@@ -145,6 +145,35 @@ class Paule():
         if log_ii > n_inner:
             raise ValueError('results can only be logged between first and last planning step')
 
+        # ---- ragged batches (new): a list of per-word mel arrays [Tm_b, 60] of different lengths.  The words
+        # are padded to the longest one and planned in lock-step, each exactly as if it were alone.
+        lengths = None
+        if (isinstance(target_acoustic, (list, tuple)) and len(target_acoustic) > 0
+                and all(isinstance(m, (np.ndarray, torch.Tensor)) and np.ndim(m) == 2 for m in target_acoustic)
+                and len({int(np.shape(m)[0]) for m in target_acoustic}) > 1):
+            mels = [torch.as_tensor(np.ascontiguousarray(m) if isinstance(m, np.ndarray) else m).float() for m in target_acoustic]
+            lengths = [2 * int(m.shape[0]) for m in mels]
+            if past_cp is not None:
+                raise NotImplementedError("past_cp with ragged batches")
+            if initialize_from == "semvec":
+                raise NotImplementedError("initialize_from='semvec' with ragged batches")
+            if initial_cp is None:   # the inverse model is not causal: initialise every word on its own (paule.py:551-557)
+                with torch.no_grad():
+                    inits = [self.inv_model(m.unsqueeze(0).to(self.device)).clamp(min=-1, max=1)[0] for m in mels]
+                initialize_from = None
+            else:
+                if initialize_from is not None:
+                    raise ValueError('one of initial_cp and initialize_from has to be None')
+                inits = [torch.as_tensor(np.ascontiguousarray(c) if isinstance(c, np.ndarray) else c).float() for c in initial_cp]
+                if len(inits) != len(mels) or any(c.shape[0] != L for c, L in zip(inits, lengths)):
+                    raise ValueError("initial_cp needs one [2 * mel frames, 30] array per word")
+            Tm_max = max(m.shape[0] for m in mels)
+            target_acoustic = torch.zeros((len(mels), Tm_max, mels[0].shape[1]))
+            initial_cp = torch.zeros((len(mels), 2 * Tm_max, inits[0].shape[1]))
+            for b, (m, c) in enumerate(zip(mels, inits)):
+                target_acoustic[b, :m.shape[0]] = m
+                initial_cp[b, :c.shape[0]] = c.to(initial_cp.device)
+
         # ---- target parsing (paule.py:486-529).  Audio targets need librosa + VocalTractLab-side tooling
         batched = False
         target_mel = None
@@ -164,7 +193,7 @@ class Paule():
             if target_mel.dim() == 2:
                 target_mel = target_mel.unsqueeze(0)
             elif target_mel.dim() == 3:
-                batched = target_mel.shape[0] != 1 or (initial_cp is not None and np.ndim(initial_cp) == 3)
+                batched = target_mel.shape[0] != 1 or (initial_cp is not None and np.ndim(initial_cp) == 3) or lengths is not None
             else:
                 raise ValueError("target_acoustic has to be torch.Tensor at this point")
             target_seq_length = target_mel.shape[1]
@@ -240,11 +269,14 @@ class Paule():
                                lr=learning_rate_planning, objective=objective, smiling=self.smiling, past_cp=past_t,
                                log_semantics=log_semantics, log_gradients=log_gradients,
                                max_log_steps=max(n_steps, 1), math=self.math,
-                               use_cuda_graph=True)
+                               use_cuda_graph=True, lengths=lengths)
         self.last_planner = planner
 
         def out(t):
             a = t.detach().cpu().numpy()
+            if lengths is not None and a.ndim == 3:   # ragged: per-word arrays without the padding frames
+                per = 1 if a.shape[1] == cp0.shape[1] else 2
+                return [a[b, :L // per] for b, L in enumerate(lengths)]
             return a if batched else a[0]
 
         # initial predictions (paule.py:822-824)
@@ -279,7 +311,8 @@ class Paule():
 
         sem_logged = objective in ('acoustic_semvec', 'semvec') or log_semantics
         return PlanningResults(
-            out(planned_cp), initial_cp_np if batched else initial_cp_np[0], None, None, None, out(initial_pred_mel),
+            out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None, None, None,
+            out(initial_pred_mel),
             None, None, out(target_mel), None, None, None, out(pred_mel), None, out(initial_pred_semvec), None,
             out(pred_semvec), list(), per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
             per_step("semvec") if sem_logged else list(), list(), cp_steps, pred_semvec_steps, list(), grad_steps,

@@ -24,13 +24,18 @@ class BatchPlanner:
     Parameters mirror what ``Paule.plan_resynth`` sets up before its loop (paule/paule.py:585-597,797):
     ``initial_cp`` [B,T,30], ``target_mel`` [B,T//2,60], ``target_semvec`` [B,300] or None (then it is the
     embedder's output on the target mel, :533-535), Adam(lr) with torch defaults, clamp 1.05.
+
+    ``lengths`` (optional, B ints): cp frames of every word of a RAGGED batch.  ``initial_cp`` and
+    ``target_mel`` are then padded to the longest word; word b is planned exactly as if it were alone (the reference plans
+    one word per call): its mel / semvec / smoothness terms are means over its own ``lengths[b]`` (``lengths[b] // 2`` mel)
+    frames, its semvec is read at its own last mel frame, and the padding frames receive a zero gradient.
     """
 
     def __init__(self, pred_model: ForwardModel, embedder: EmbeddingModel, initial_cp: torch.Tensor,
                  target_mel: torch.Tensor, target_semvec: Optional[torch.Tensor] = None, *, lr: float = 0.01,
                  objective: str = "acoustic_semvec", smiling: bool = False, past_cp: Optional[torch.Tensor] = None,
                  log_semantics: bool = True, log_gradients: bool = False, max_log_steps: int = 1024,
-                 math: int = ops.MATH_FP32, use_cuda_graph: bool = True):
+                 math: int = ops.MATH_FP32, use_cuda_graph: bool = True, lengths=None):
         _lib.require_device()
         if objective not in ops.OBJECTIVES:
             raise ValueError("objective has to be one of 'acoustic_semvec', 'acoustic' or 'semvec'")
@@ -55,6 +60,18 @@ class BatchPlanner:
         Cm, S = target_mel.shape[2], embedder.linear_mapping.out_features
         self.B, self.T, self.Tm, self.H, self.C, self.Cm, self.S = B, T, Tm, H, C, Cm, S
         self.objective, self.math = objective, math
+        self.lengths, self.word_frames = None, None
+        if lengths is not None:
+            ln = [int(v) for v in lengths]
+            if len(ln) != B:
+                raise ValueError(f"lengths has {len(ln)} entries for {B} words")
+            if min(ln) < 13 or max(ln) > T:
+                raise ValueError("every word needs 13 <= lengths[b] <= initial_cp.shape[1] cp frames")
+            if past_cp is not None:
+                raise NotImplementedError("past_cp with ragged batches")
+            if any(v != T for v in ln):
+                self.lengths = ln
+                self.word_frames = torch.tensor(ln, device=dev, dtype=torch.int32)
         tc = math != ops.MATH_FP32
         # ---- weights (replicated per GPU; repacked by refresh_weights() after continue-learning)
         self._pred, self._emb = pred_model, embedder
@@ -145,6 +162,7 @@ class BatchPlanner:
         s.loss_log, s.pred_mel, s.pred_sv = self.loss_log.data_ptr(), self.pred_mel.data_ptr(), self.pred_sv.data_ptr()
         s.grad_out = None if self.grad_out is None else self.grad_out.data_ptr()
         s.workspace, s.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        s.word_frames = None if self.word_frames is None else self.word_frames.data_ptr()
         self._struct = s
 
     def struct_ref(self):
@@ -157,7 +175,12 @@ class BatchPlanner:
             h = mel_tm
             for L in (self.w_e0, self.w_e1):
                 h, _, _ = ops.lstm_layer_fwd(h, False, L.w_ih, L.w_hh, L.bias)
-            return ops.linear_tm(h[-1:].contiguous(), self.head_w, self.head_b, False, False)[0]
+            if self.word_frames is None:
+                last = h[-1:]
+            else:   # every word's own last mel frame (paule/models.py:442)
+                idx = (self.word_frames // 2 - 1).long()
+                last = h[idx, torch.arange(self.B, device=h.device)].unsqueeze(0)
+            return ops.linear_tm(last.contiguous(), self.head_w, self.head_b, False, False)[0]
 
     def forward(self):
         """no_grad predictions for the current cps -> (pred_mel [B,Tm,Cm], pred_semvec [B,S])."""

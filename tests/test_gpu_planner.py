@@ -276,3 +276,75 @@ def test_full_size_properties_cfg5_long_utterance_shard(dev, models):
     pred, emb, _ = models
     cp0, tmel = O.synthetic_inputs(64, 1200, seed=47)
     _full_size_check(dev, pred, emb, cp0, tmel, 3, 1, probe=33)
+
+
+# ---- ragged batches: words of different lengths padded to the longest one --------------------------
+RAGGED = [40, 64, 51, 80, 46, 80, 13]   # cp frames per word (one odd, one at the 13-frame minimum of the jerk stencil)
+
+
+def _ragged_inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    T = max(RAGGED)
+    cps = [torch.rand((L, 30), generator=g) - 0.5 for L in RAGGED]
+    mels = [torch.rand((L // 2, 60), generator=g) for L in RAGGED]
+    cp0, tmel = torch.zeros(len(RAGGED), T, 30), torch.zeros(len(RAGGED), T // 2, 60)
+    for b, (c, m) in enumerate(zip(cps, mels)):
+        cp0[b, :c.shape[0]] = c
+        tmel[b, :m.shape[0]] = m
+    # padding frames are NOT zeros: whatever is there must not leak into a word
+    cp0[0, RAGGED[0]:] = 0.37
+    tmel[0, RAGGED[0] // 2:] = 5.0
+    return cps, mels, cp0, tmel
+
+
+@pytest.mark.parametrize("math", math_params())
+def test_ragged_batch_equals_words_planned_alone(dev, models, math):
+    """Every word of a ragged batch == the same word planned alone (its own length, no padding), and the padding frames of
+    the cps never move; word 2 (odd length) is also held against the CPU oracle at the BASELINE tolerance."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    cps, mels, cp0, tmel = _ragged_inputs(11)
+    n = 6
+    pl = BatchPlanner(pred, emb, cp0.to(dev), tmel.to(dev), None, max_log_steps=n, math=math, lengths=RAGGED)
+    pl.step(n)
+    cp_b, L_b = _np(pl.planned_cp()), {k: _np(v) for k, v in pl.losses().items()}
+    mel_b, sv_b = pl.forward()
+    assert np.isfinite(cp_b).all() and np.isfinite(L_b["total"]).all()
+    np.testing.assert_array_equal(cp_b[0, RAGGED[0]:], np.float32(0.37))        # padding untouched
+    cp_tol, loss_tol = (5e-6, 1e-5) if math == 0 else (3e-5, 2e-4)
+    for b, L in enumerate(RAGGED):
+        solo = BatchPlanner(pred, emb, cps[b][None].to(dev), mels[b][None].to(dev), None, max_log_steps=n, math=math)
+        solo.step(n)
+        np.testing.assert_allclose(cp_b[b, :L], _np(solo.planned_cp())[0], atol=cp_tol, err_msg=f"word {b} (T={L})")
+        for k in ("total", "mel", "semvec", "velocity", "jerk", "local_linear"):
+            np.testing.assert_allclose(L_b[k][:, b], _np(solo.losses()[k])[:, 0], rtol=loss_tol, atol=1e-6, err_msg=f"{k} word {b}")
+        m1, s1 = solo.forward()
+        np.testing.assert_allclose(_np(mel_b)[b, :L // 2], _np(m1)[0], atol=1e-5 if math == 0 else 2e-3)
+        np.testing.assert_allclose(_np(sv_b)[b], _np(s1)[0], atol=1e-5 if math == 0 else 2e-3)
+        solo.close()
+    pr, em, _ = O.build_reference_models(0, 720, torch.float32, with_inverse=False)
+    r = O.plan_inner_loop(pr, em, cps[2][None], mels[2][None], n)
+    np.testing.assert_allclose(L_b["total"][:, 2], r["loss"].double().numpy()[:, 0], rtol=1e-3)
+    np.testing.assert_allclose(cp_b[2, :RAGGED[2]], r["planned_cp"].double().numpy()[0], atol=1e-3)
+
+
+def test_paule_plan_resynth_ragged_list(dev, models):
+    """Paule.plan_resynth with a list of per-word mel arrays: per-word results without padding, each equal to the word
+    planned through the single-word API; the inverse-model initialisation runs per word (it is not causal)."""
+    import paule_b200 as P
+    pred, emb, inv = models
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev)
+    g = torch.Generator().manual_seed(3)
+    mels = [torch.rand((n, 60), generator=g).numpy() for n in (20, 32, 25)]
+    res = pm.plan_resynth(target_acoustic=mels, initialize_from="acoustic", objective="acoustic_semvec", n_outer=1, n_inner=4,
+                          continue_learning=False, verbose=False)
+    assert [c.shape for c in res.planned_cp] == [(40, 30), (64, 30), (50, 30)]
+    assert [m.shape for m in res.pred_mel] == [(20, 60), (32, 60), (25, 60)]
+    for b, m in enumerate(mels):
+        solo = pm.plan_resynth(target_acoustic=m, initialize_from="acoustic", objective="acoustic_semvec", n_outer=1, n_inner=4,
+                               continue_learning=False, verbose=False)
+        np.testing.assert_allclose(res.initial_cp[b], solo.initial_cp, atol=1e-6)
+        np.testing.assert_allclose(np.stack(res.planned_loss_steps)[:, b], np.array(solo.planned_loss_steps), rtol=1e-4)
+        np.testing.assert_allclose(res.planned_cp[b], solo.planned_cp, atol=1e-5)
+    with pytest.raises(ValueError):
+        P.BatchPlanner(pred, emb, torch.zeros(2, 40, 30, device=dev), torch.zeros(2, 20, 60, device=dev), None, lengths=[40, 12])

@@ -135,3 +135,80 @@ def test_sharded_plan_equals_single_rank_gloo_world2(n_words):
         np.testing.assert_array_equal(loss, ref.losses()["total"].numpy())
         if rank == 0:
             np.testing.assert_array_equal(cps0, ref.planned_cp().numpy())
+
+
+# ---- ragged jobs: length-bucketed sharding --------------------------------------------------------------------------
+def test_length_buckets_balance_cost_and_cover_every_word():
+    from paule_b200.distributed import length_buckets
+    rng = np.random.RandomState(0)
+    for ws in (1, 2, 3, 8):
+        for n in (0, 1, 5, 64, 257):
+            lengths = (2 * rng.randint(7, 600, size=n)).tolist()
+            b = length_buckets(lengths, ws)
+            assert len(b) == ws and sorted(i for r in b for i in r) == list(range(n))
+            if n == 0:
+                continue
+            cost = [max(lengths[i] for i in r) * len(r) if r else 0 for r in b]
+            # every rank holds a contiguous run of the length-sorted words ...
+            flat = [lengths[i] for r in b for i in r]
+            assert flat == sorted(lengths, reverse=True)
+            # ... and no rank costs more than the even share plus one longest word
+            assert max(cost) <= sum(l for l in lengths) / ws + 2 * max(lengths) * max(1, n // (4 * ws)) or ws == 1
+    assert length_buckets([100, 20, 20, 20, 20, 20], 2) == [[0], [1, 2, 3, 4, 5]]
+
+
+class _FakeRaggedPlanner(_FakePlanner):
+    def __init__(self, cp, mel, lengths):
+        super().__init__(cp, mel, None)
+        self.lengths = lengths
+        m = torch.zeros(cp.shape[:2])
+        for b, L in enumerate(lengths):
+            m[b, :L] = 1
+        self.mask = m
+
+    def step(self, n):
+        for _ in range(n):
+            per = (self.cp.pow(2).mean(2) * self.mask).sum(1) / self.mask.sum(1)
+            self.log.append(per)
+            self.cp = 0.9 * self.cp
+
+
+def _ragged_job(n_words):
+    g = torch.Generator().manual_seed(1)
+    lengths = [2 * int(v) for v in torch.randint(7, 40, (n_words,), generator=g)]
+    cps = [torch.rand(L, 30, generator=g) for L in lengths]
+    mels = [torch.rand(L // 2, 60, generator=g) for L in lengths]
+    return lengths, cps, mels
+
+
+def _ragged_worker(rank, ws, port, n_words, out_q):
+    sys.path.insert(0, REPO)
+    from paule_b200 import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    _, cps, mels = _ragged_job(n_words)
+    planned, loss = D.plan_sharded_ragged(_FakeRaggedPlanner, cps, mels, 3)
+    out_q.put((rank, [p.numpy() for p in planned], loss.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_sharded_plan_equals_words_planned_alone_gloo_world2():
+    n_words = 9
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ragged_worker, args=(r, 2, port, n_words, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lengths, cps, mels = _ragged_job(n_words)
+    for rank, planned, loss in res:
+        for b in range(n_words):
+            solo = _FakeRaggedPlanner(cps[b][None], mels[b][None], [lengths[b]])
+            solo.step(3)
+            np.testing.assert_array_equal(planned[b], solo.planned_cp()[0].numpy())
+            np.testing.assert_allclose(loss[:, b], torch.stack(solo.log)[:, 0].numpy(), rtol=1e-6)
