@@ -14,6 +14,8 @@
 //
 // All launches go to one stream; there is no host synchronisation, no allocation and no host-visible state,
 // so the whole step can be captured in a CUDA graph and replayed.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "plan_internal.cuh"
 
@@ -27,6 +29,7 @@ struct Workspace {
   float *gates_1, *h_1, *c_1;
   float *dmel, *dsv, *dh1_last, *dh0, *dhp, *dcp_lstm, *dcp_smooth, *dc, *partial;
   void *xchg, *h_img, *hf_img, *da_img;   // tensor-core path only; the image buffers must have been zero-filled once
+  void *x_img_f, *x_img_0;                // operand blocks of the fused input projections (cps, mel)
   size_t floats;
 };
 
@@ -55,6 +58,8 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
     w.h_img = take_bytes(paule_tc_img_seq_bytes(Tm, B, 1));    // h_0 of every mel frame: A operand of Xp1 = h_0 W_ih1^T
     w.hf_img = take_bytes(paule_tc_img_seq_bytes(T, B, 1));    // forward model's h_t: A operand of the pooled post_linear
     w.da_img = take_bytes(paule_tc_img_seq_bytes(T, B, 4));    // dA of the layer being back-propagated (reused by all three)
+    w.x_img_f = take_bytes(paule_tc_x_image_bytes(T, B));      // cps as hi/lo bf16 operand blocks
+    w.x_img_0 = take_bytes(paule_tc_x_image_bytes(Tm, B));     // predicted mel as bf16 operand blocks
   }
   w.floats = off;
   return w;
@@ -103,12 +108,26 @@ int layer_backward(const paule_plan* p, const paule_lstm_layer& L, float* gates,
   return paule_linear_f32(gates, L.w_ih_t, nullptr, dx, steps * B, I, 4 * H, 1, 4 * H, 0, 0, 1, I, 0, accumulate, s);
 }
 
+// Input projection + recurrence of a layer fed by a narrow input (the cps: 30, the mel: 60 channels).  Tensor-core path:
+// the projection runs INSIDE the recurrent kernel (paule_tc_lstm_seq_fwd_x), the [steps,B,2880] pre-activations never
+// touch HBM; PAULE_NO_FUSED_X=1 keeps the separate FFMA projection (A/B timing, bisecting).
+int project_and_recur(const paule_plan* p, const paule_lstm_layer& L, const float* x, int64_t steps, float* gates, float* h,
+                      float* c, const Workspace& w, void* x_img, void* h_img, paule_stream_t s) {
+  const int64_t B = p->B, H = p->H, I = L.input_size;
+  static const bool no_fuse = getenv("PAULE_NO_FUSED_X") != nullptr;
+  if (tc(p) && I <= 64 && !no_fuse) {
+    PAULE_TRY(paule_tc_x_image(x, x_img, steps, B, I, s));
+    return paule_tc_lstm_seq_fwd_x(gates, L.packed, L.bias, x_img, h, c, w.xchg, h_img, steps, B, p->math, s);
+  }
+  PAULE_TRY(paule_linear_f32(x, L.w_ih, L.bias, gates, steps * B, 4 * H, I, 1, I, 0, 0, 1, 4 * H, 0, 0, s));
+  return recur_forward(p, L, steps, gates, h, c, w, h_img, s);
+}
+
 int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s) {
   const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, C = p->C, Cm = p->Cm, S = p->S;
-  // ForwardModel (models.py:348-356): K = 30 input projection, recurrence
-  PAULE_TRY(paule_linear_f32(p->cp, p->fwd.w_ih, p->fwd.bias, w.gates_f, T * B, 4 * H, C, 1, C, 0, 0, 1, 4 * H, 0, 0, s));
+  // ForwardModel (models.py:348-356): K = 30 input projection + recurrence
   const bool tc_post = tc(p) && p->post_packed != nullptr && (T % 2 == 0);
-  PAULE_TRY(recur_forward(p, p->fwd, T, w.gates_f, w.h_f, w.c_f, w, tc_post ? w.hf_img : nullptr, s));
+  PAULE_TRY(project_and_recur(p, p->fwd, p->cp, T, w.gates_f, w.h_f, w.c_f, w, w.x_img_f, tc_post ? w.hf_img : nullptr, s));
   // post_linear + AvgPool1d(2,2) (the pool commutes with the Linear)
   if (tc_post) {
     // on tcgen05: frames 2k and 2k+1 are consecutive images = two K segments of row (k, b); weights [0.5 W | 0.5 W]
@@ -119,9 +138,7 @@ int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, pa
   }
   if (!need_semvec) return PAULE_OK;
   // EmbeddingModel (models.py:440-448), lens = Tm for every word (paule.py:922-924)
-  PAULE_TRY(paule_linear_f32(p->pred_mel, p->emb0.w_ih, p->emb0.bias, w.gates_0, Tm * B, 4 * H, Cm, 1, Cm, 0, 0, 1, 4 * H,
-                             0, 0, s));
-  PAULE_TRY(recur_forward(p, p->emb0, Tm, w.gates_0, w.h_0, w.c_0, w, w.h_img, s));
+  PAULE_TRY(project_and_recur(p, p->emb0, p->pred_mel, Tm, w.gates_0, w.h_0, w.c_0, w, w.x_img_0, w.h_img, s));
   if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
     PAULE_TRY(paule_tc_gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, s));
   } else {

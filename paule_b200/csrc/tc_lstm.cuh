@@ -63,7 +63,15 @@ constexpr size_t kLLBytes = (size_t)kMaxQ * 4 * 2 * 4 * kLLBlockBytes;   // up t
 constexpr size_t kPackedV1Bytes = (size_t)kFwdCtas * kFwdSliceBytes + (size_t)kBwdCtas * kBwdSliceBytes;
 constexpr size_t kPackedFwd2Off = kPackedV1Bytes;
 constexpr size_t kPackedBwd2Off = kPackedFwd2Off + (size_t)kFwd2Groups * kV2SliceBytes;
-constexpr size_t kPackedBytes = kPackedBwd2Off + (size_t)kBwd2Groups * 4 * kV2SliceBytes;
+// fused input projection (K = input_size <= 64 padded to 64): per forward CTA a [128 gate rows, 64] bf16 slice = 32 more
+// TMEM columns behind the W_hh slice, stored in the same tcgen05.st order [4 column octets][128 rows][8 x u32]
+constexpr int kXK = 64;                              // K of the fused input projection (one k-block)
+constexpr int kXCols = kXK / 2;                      // 32 TMEM columns
+constexpr int kXWCol = kV2WCol + kV2WCols;           // 448: first column of the input-projection weights
+constexpr int kXSliceBytes = kV2M * kXK * 2;         // 16384
+constexpr int kXBlockBytes = kWq * 128;              // 2048: x_t of one word quarter as a B operand [16 rows][128 B]
+constexpr size_t kPackedXOff = kPackedBwd2Off + (size_t)kBwd2Groups * 4 * kV2SliceBytes;
+constexpr size_t kPackedBytes = kPackedXOff + (size_t)kFwd2Groups * kXSliceBytes;
 
 
 // quarters per CTA for a batch of B words when a launch holds at most max_groups groups: the smallest of 1..4 that
@@ -89,11 +97,12 @@ inline int64_t pass_words(int64_t B, int max_groups, int nq) {
 #ifdef __CUDACC__
 // Weight image of one CTA as tcgen05.st wants it: [48 column octets][128 rows][8 x u32]; u32 column c of row m holds the
 // bf16 pair (k = 2c, 2c+1).  Warp w (lanes 32w..32w+31) copies its rows with one 32-byte load + one x8 store per octet.
-__device__ __forceinline__ void load_weights_to_tmem(const uint8_t* __restrict__ slice, uint32_t tmem, int warp, int lane) {
+__device__ __forceinline__ void load_weights_to_tmem(const uint8_t* __restrict__ slice, uint32_t tmem, int warp, int lane,
+                                                     int first_col = kV2WCol, int n_cols = kV2WCols) {
   const uint4* src = reinterpret_cast<const uint4*>(slice) + (size_t)(warp * 32 + lane) * 2;
-  const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)kV2WCol;
+  const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)first_col;
 #pragma unroll 4
-  for (int c8 = 0; c8 < kV2WCols / 8; ++c8) {
+  for (int c8 = 0; c8 < n_cols / 8; ++c8) {
     const uint4 a = __ldg(src + (size_t)c8 * kV2M * 2), b = __ldg(src + (size_t)c8 * kV2M * 2 + 1);
     tmem_st_x8(dst + (uint32_t)(c8 * 8), a, b);
   }
@@ -167,9 +176,13 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
 #endif  // __CUDACC__
 
 // host entry points of the v2 kernels (dispatched from paule_tc_lstm_seq_fwd / _bwd; PAULE_RNN_V1=1 keeps the v1 kernels)
-int pack_v2(const float* w_hh, uint8_t* packed, cudaStream_t s);
+int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cudaStream_t s);
+int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s);
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
                   cudaStream_t s);
+// fused input projection: gates is output only (the activated-gate stash), pre-activations = W_hh h + W_ih x_t + bias
+int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
+                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s);
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                   void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s);
 inline bool use_v1_fwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_FWD_V1") != nullptr; return v; }

@@ -251,7 +251,6 @@ extern "C" size_t paule_tc_packed_lstm_bytes(int64_t H, int64_t I) {
 
 extern "C" int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* packed, int64_t H, int64_t I,
                                   paule_stream_t stream) {
-  (void)w_ih; (void)I;
   PAULE_REQUIRE(w_hh && packed);
   if (H != kH) return PAULE_ERR_UNSUPPORTED;
   uint8_t* img = reinterpret_cast<uint8_t*>(packed);
@@ -259,7 +258,7 @@ extern "C" int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* pa
   pack_fwd_kernel<<<kFwdCtas, 256, 0, as_stream(stream)>>>(w_hh, img);
   pack_bwd_kernel<<<kBwdCtas, 256, 0, as_stream(stream)>>>(w_hh, img + (size_t)kFwdCtas * kFwdSliceBytes);
   PAULE_LAUNCH_CHECK("pack kernels");
-  return pack_v2(w_hh, img, as_stream(stream));
+  return pack_v2(w_ih, w_hh, I, img, as_stream(stream));
 }
 
 extern "C" size_t paule_tc_rnn_xchg_bytes(int64_t B) {
@@ -267,6 +266,28 @@ extern "C" size_t paule_tc_rnn_xchg_bytes(int64_t B) {
   // header (barrier counters, error flag) + forward: 2 h images; backward: 2 x 4 gate images (sized for the larger user)
   const size_t v1 = (size_t)8 * kXchgImageBytes;
   return (size_t)kXchgHeader + (v1 > kLLBytes ? v1 : kLLBytes);
+}
+
+extern "C" size_t paule_tc_x_image_bytes(int64_t T, int64_t B) {
+  if (T <= 0 || B <= 0) return 0;
+  return (size_t)T * (size_t)((B + kWq - 1) / kWq) * kXBlockBytes;
+}
+
+extern "C" int paule_tc_x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, paule_stream_t stream) {
+  PAULE_REQUIRE(x && img && T >= 0 && B > 0 && I >= 1 && I <= kXK);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(img) % 16 == 0);
+  return x_image(x, img, T, B, I, as_stream(stream));
+}
+
+extern "C" int paule_tc_lstm_seq_fwd_x(float* gates, const void* packed, const float* bias, const void* x_img, float* h,
+                                       float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B, int math,
+                                       paule_stream_t stream) {
+  PAULE_REQUIRE(gates && packed && bias && x_img && h && c && xchg && T >= 0 && B > 0);
+  PAULE_REQUIRE(math == PAULE_MATH_BF16);
+  if (T == 0) return PAULE_OK;
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(xchg) % 16 == 0 && reinterpret_cast<uintptr_t>(x_img) % 16 == 0);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(h_img_seq) % 16 == 0);
+  return lstm_seq_fwd2x(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, as_stream(stream));
 }
 
 extern "C" size_t paule_tc_img_seq_bytes(int64_t T, int64_t B, int64_t images_per_step) {

@@ -55,12 +55,58 @@ __global__ void pack_bwd2_kernel(const float* __restrict__ w_hh, uint8_t* __rest
   }
 }
 
+// Input-projection weights of unit group ug (16 KB), same row order and tcgen05.st layout as pack_fwd2_kernel, K = 64.
+// input_size <= 32 (the cps): columns [0,32) and [32,64) both hold W_ih -- the operand carries x as a hi/lo bf16 pair, so
+// the planned variable itself is not rounded.  32 < input_size <= 64 (the mel): columns [0, input_size) hold W_ih.
+__global__ void pack_x_kernel(const float* __restrict__ w_ih, int I, uint8_t* __restrict__ img) {
+  const int ug = blockIdx.x;
+  const bool split = I <= 32;
+  uint32_t* out = reinterpret_cast<uint32_t*>(img + (size_t)ug * kXSliceBytes);
+  for (int e = threadIdx.x; e < kV2M * kXCols; e += blockDim.x) {
+    const int c8 = e / (kV2M * 8), m = (e / 8) % kV2M, i = e % 8;
+    const int k = 2 * (c8 * 8 + i);
+    const int u = ug * 32 + (m >> 2), gate = m & 3;
+    float v[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int kk = split ? ((k + x) & 31) : (k + x);
+      v[x] = (u < kH && kk < I) ? w_ih[(size_t)(gate * kH + u) * I + kk] : 0.f;
+    }
+    out[e] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[1])) << 16);
+  }
+}
+
+// x [T,B,I] fp32 -> operand images [T][ceil(B/16)][16 rows][128 B] (bf16, SWIZZLE_128B): one 2 KB block per (step, word
+// quarter), fetched by the recurrent kernel with one TMA bulk copy.  Split mode: column k < 32 = bf16(x_k), column 32 + k =
+// bf16(x_k - float(bf16(x_k))).  Rows of words >= B and unused columns stay zero (the buffer is zero-filled once).
+__global__ void x_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int64_t T, int64_t B, int I) {
+  const bool split = I <= 32;
+  const int64_t Q = (B + kWq - 1) / kWq;
+  const int64_t total = T * B * I;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % I);
+    const int64_t tb = e / I, b = tb % B, t = tb / B;
+    const int row = (int)(b % kWq);
+    uint8_t* blk = img + ((size_t)t * Q + (size_t)(b / kWq)) * kXBlockBytes + (size_t)row * 128;
+    const float v = x[e];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(blk + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2) = hi;
+    if (split) {
+      const int k2 = 32 + k;
+      *reinterpret_cast<__nv_bfloat16*>(blk + (((k2 >> 3) ^ (row & 7)) << 4) + (k2 & 7) * 2) =
+          __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+
 template <int NQ>
 struct Fwd2Smem {
   uint8_t b[NQ][kV2BBytes];   // B operand per quarter: h_{t-1} of its 16 words, [12 kb][16 rows][128 B]
   uint64_t mma_done[NQ];      // accumulator of quarter q complete: one commit per loader warp
   uint64_t acc_free[NQ];      // accumulator of quarter q read and re-zeroed: one arrival per epilogue warp
+  uint64_t xfull[2];          // fused input projection: x_t blocks of all quarters landed (TMA tx-count)
   uint32_t tmem_base;
+  alignas(1024) uint8_t xb[2][NQ][kXBlockBytes];   // x_t / x_{t+1} operand blocks (double-buffered)
 };
 
 constexpr int kF2EpiWarps = 8;
@@ -70,11 +116,18 @@ constexpr int kF2Threads = 32 * (kF2EpiWarps + kNumKB);   // 640
 // weights: each has its own accumulator, barriers, operand buffer and exchange blocks, and the loader / epilogue warps
 // visit them round-robin, so one quarter's cell runs while another quarter's h_t is in flight between the SMs.  NQ = 1
 // is the latency-optimal layout for batches that fit one launch (<= 96 words); NQ = 2 / 4 fill the waiting time.
-template <int NQ>
+//
+// FUSED: the layer's input projection runs inside the recurrence.  W_ih (K <= 64) sits in 32 more TMEM columns, x_t of the
+// CTA's quarters arrives as 2 KB operand blocks by TMA one step ahead, and loader warp 11 -- whose k-block holds only 16
+// real hidden units, i.e. one useful MMA -- issues the four x MMAs into the same accumulator; the epilogue adds the bias
+// from registers.  `gates` is then output only (the activated-gate stash): the [T,B,2880] pre-activation tensor is never
+// written to or read from HBM, and the x MMAs do not wait for the exchange.
+template <int NQ, bool FUSED>
 __global__ void __launch_bounds__(kF2Threads, 1)
 tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed, float* __restrict__ h_out,
                     float* __restrict__ c_out, uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv,
-                    int Bs, int w0) {
+                    int Bs, int w0, const uint8_t* __restrict__ packed_x, const uint8_t* __restrict__ x_img,
+                    const float* __restrict__ bias, int Qtot) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = Fwd2Smem<NQ>;
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,6 +139,8 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
 
   if (tid == 0) {
     for (int q = 0; q < NQ; ++q) { mbar_init(&S.mma_done[q], kNumKB); mbar_init(&S.acc_free[q], kF2EpiWarps); }
+    mbar_init(&S.xfull[0], 1);
+    mbar_init(&S.xfull[1], 1);
     fence_mbar_init();
   }
   for (int i = tid; i < NQ * kV2BBytes / 16; i += kF2Threads) reinterpret_cast<uint4*>(&S.b[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -96,7 +151,10 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
   tcgen05_fence_after();
   const uint32_t tmem = S.tmem_base;
   // resident weights: this CTA's [128 gate rows, 768] slice of W_hh goes into tensor memory once (384 columns)
-  if (warp < 4) load_weights_to_tmem(packed + (size_t)ug * kV2SliceBytes, tmem, warp, lane);
+  if (warp < 4) {
+    load_weights_to_tmem(packed + (size_t)ug * kV2SliceBytes, tmem, warp, lane);
+    if (FUSED) load_weights_to_tmem(packed_x + (size_t)ug * kXSliceBytes, tmem, warp, lane, kXWCol, kXCols);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -109,45 +167,78 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     // probes: lane p < 16 watches writer warp (CTA p>>3 of the k-block's two, lane group (p>>1)&3, column half p&1):
     // its lane 0 publishes row 8 (p&1), units 32 (p>>3) + 8 ((p>>1)&3) of the k-block
     const uint32_t probe_off = (uint32_t)(((lane & 1) * 8 * 64 + ((lane >> 3) & 1) * 32 + ((lane >> 1) & 3) * 8) * 2);
+    const bool xwarp = FUSED && kb == kNumKB - 1;   // this warp also feeds the fused input projection
+    const int nk = (kb == kNumKB - 1) ? 1 : 4;       // k-block 11 holds 16 real units: one K = 16 step, the rest is padding
+    const int q_first = w0 / kWq + grp * NQ;         // first global word quarter of this CTA (x image addressing)
+    int nvq = 0;                                     // quarters of this CTA that hold words
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) nvq += ((grp * NQ + q) * kWq < Bv) ? 1 : 0;
+    auto fetch_x = [&](int t) {   // x_t blocks of every valid quarter: one bulk copy each onto xfull[t & 1]
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&S.xfull[t & 1], (uint32_t)(nvq * kXBlockBytes));
+        for (int q = 0; q < nvq; ++q)
+          bulk_g2s(S.xb[t & 1][q], x_img + ((size_t)t * Qtot + (size_t)(q_first + q)) * kXBlockBytes, kXBlockBytes, &S.xfull[t & 1]);
+      }
+      __syncwarp();
+    };
+    if (xwarp) fetch_x(0);
     TRACE_DECL
-    for (int t = 1; t < T; ++t) {
+    for (int t = FUSED ? 0 : 1; t < T; ++t) {
+      const uint32_t par = (uint32_t)((FUSED ? t : t - 1) & 1);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int rows = min(kWq, Bv - (grp * NQ + q) * kWq);   // valid words of this quarter: only their rows travel
         if (rows <= 0) continue;
-        const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 1) * 8 < rows);
         uint8_t* bdst = &S.b[q][(size_t)kb * kWq * 128];
         const uint64_t db = make_smem_desc_sw128(smem_u32(bdst));
-        const uint8_t* src = ll + (size_t)(q * 2 + ((t - 1) & 1)) * kLLBlockBytes + (size_t)kb * (kWq * 128);
+        if (t > 0) {
+          const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 1) * 8 < rows);
+          const uint8_t* src = ll + (size_t)(q * 2 + ((t - 1) & 1)) * kLLBlockBytes + (size_t)kb * (kWq * 128);
 #ifdef PAULE_TC_TRACE
-        while ((xchg_load(src) & kPhaseMask) != phase_bits(t - 1)) {}   // split the fetch: until the first value is visible
-        TRACE(0)
-        uint64_t ftr[2] = {0, 0};
-        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr)) break;
-        tr_acc[6] += ftr[0] - tr_last;   // probe phase
-        tr_acc[7] += ftr[1] * 1000;      // bulk passes (x1000 so that the printout shows passes per step)
+          while ((xchg_load(src) & kPhaseMask) != phase_bits(t - 1)) {}   // split the fetch: until the first value is visible
+          TRACE(0)
+          uint64_t ftr[2] = {0, 0};
+          if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr)) break;
+          tr_acc[6] += ftr[0] - tr_last;   // probe phase
+          tr_acc[7] += ftr[1] * 1000;      // bulk passes (x1000 so that the printout shows passes per step)
 #else
-        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err)) break;
+          if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err)) break;
 #endif
-        TRACE(1)
-        fence_proxy_async_shared();   // generic-proxy shared-memory writes -> async-proxy (tensor core) reads
-        __syncwarp();
+          TRACE(1)
+          fence_proxy_async_shared();   // generic-proxy shared-memory writes -> async-proxy (tensor core) reads
+          __syncwarp();
+        }
         TRACE(2)
-        mbar_wait(&S.acc_free[q], (uint32_t)((t - 1) & 1), err);   // long complete by now: the tile was zeroed a step ago
+        mbar_wait(&S.acc_free[q], par, err);   // long complete by now: the tile was zeroed a step ago
+        if (xwarp) mbar_wait(&S.xfull[t & 1], (uint32_t)((t >> 1) & 1), err);   // x_t landed (issued a step ago)
         tcgen05_fence_after();
         TRACE(3)
         if (elect_one_sync()) {
+          const uint32_t d = tmem + (uint32_t)(kV2AccCol + q * kWq);
+          if (t > 0) {
+            if (nk == 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + (uint32_t)(kV2AccCol + q * kWq), ta + 8 * k, db + 2 * k, idesc, 1u);
+              for (int k = 0; k < 4; ++k) umma_bf16_ts(d, ta + 8 * k, db + 2 * k, idesc, 1u);
+            } else {
+              umma_bf16_ts(d, ta, db, idesc, 1u);
+            }
+          }
+          if (xwarp) {
+            const uint64_t dx = make_smem_desc_sw128(smem_u32(S.xb[t & 1][q]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(d, tmem + (uint32_t)(kXWCol + 8 * k), dx + 2 * k, idesc, 1u);
+          }
           umma_commit(&S.mma_done[q]);
         }
         __syncwarp();
         TRACE(4)
 #ifdef PAULE_TC_TRACE
-        mbar_wait(&S.mma_done[q], (uint32_t)((t - 1) & 1), err);
+        mbar_wait(&S.mma_done[q], par, err);
         TRACE(5)
 #endif
       }
+      // x_{t+1}: its buffer was last read by the x MMAs of step t-1, which completed before any h_{t-1} could be fetched
+      if (xwarp && t + 1 < T) fetch_x(t + 1);
     }
     if (blockIdx.x == 0 && kb == 3 && lane == 0) TRACE_DUMP(0)
   } else {
@@ -166,6 +257,9 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     float c_prev[NQ][2];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) c_prev[q][0] = c_prev[q][1] = 0.f;
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};   // FUSED: b_ih + b_hh of this thread's unit, one per gate
+    if (FUSED && uvalid)
+      for (int g = 0; g < 4; ++g) bias4[g] = __ldg(bias + g * kH + u);
 
 #pragma unroll
     for (int q = 0; q < NQ; ++q) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
@@ -181,6 +275,11 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
       // q + 1's while quarter q is computed
       float xp[4][2];
       auto load_xp = [&](int q) {
+        if (FUSED) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) xp[g][0] = xp[g][1] = bias4[g];
+          return;
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int wp = grp * kGW + q * kWq + wl0 + k;
@@ -195,9 +294,9 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
       for (int q = 0; q < NQ; ++q) {
         if ((grp * NQ + q) * kWq >= Bv) continue;   // empty quarter (uniform over the CTA)
         float pre[4][2];
-        if (t > 0) {
+        if (FUSED || t > 0) {
           float acc[8];
-          mbar_wait(&S.mma_done[q], (uint32_t)((t - 1) & 1), err);
+          mbar_wait(&S.mma_done[q], (uint32_t)((FUSED ? t : t - 1) & 1), err);
           TRACE(0)
           tcgen05_fence_after();
           tmem_ld_x8(taddr + (uint32_t)(q * kWq), acc);
@@ -299,20 +398,25 @@ using namespace paule::tc;
 namespace paule {
 namespace tc {
 
-int pack_v2(const float* w_hh, uint8_t* packed, cudaStream_t s) {
+int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cudaStream_t s) {
   pack_fwd2_kernel<<<kFwd2Groups, 256, 0, s>>>(w_hh, packed + kPackedFwd2Off);
   pack_bwd2_kernel<<<kBwd2Groups * 4, 256, 0, s>>>(w_hh, packed + kPackedBwd2Off);
+  if (w_ih != nullptr && I >= 1 && I <= kXK) {   // fused input projection (layers fed by the cps or the mel)
+    pack_x_kernel<<<kFwd2Groups, 256, 0, s>>>(w_ih, (int)I, packed + kPackedXOff);
+  } else {
+    PAULE_CUDA(cudaMemsetAsync(packed + kPackedXOff, 0, (size_t)kFwd2Groups * kXSliceBytes, s));
+  }
   PAULE_LAUNCH_CHECK("pack v2 kernels");
   return PAULE_OK;
 }
 
-template <int NQ>
-int launch_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
-                cudaStream_t s) {
+template <int NQ, bool FUSED>
+int launch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
+                void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
   static bool attr_set = false;
   const int smem = (int)sizeof(Fwd2Smem<NQ>) + 1024;
   if (!attr_set) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NQ, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQ, NQ);
@@ -323,16 +427,18 @@ int launch_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg
     // error flag; exchange blocks of this pass start with the phase bit set (0x4040 per value): never a valid first step
     PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));
     PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)ng * 2 * NQ * kLLBlockBytes, s));
-    int Ti = (int)T, Bsi = (int)B, w0 = (int)r0, Bvi = Bv;
+    int Ti = (int)T, Bsi = (int)B, w0 = (int)r0, Bvi = Bv, Qtot = (int)((B + kWq - 1) / kWq);
     float* gp = gates + r0 * 4 * kH;
     float* hp = h + r0 * kH;
     float* cp = c + r0 * kH;
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
     uint8_t* is = reinterpret_cast<uint8_t*>(h_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedFwd2Off;
-    void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bvi, &Bsi, &w0};
-    PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NQ>, dim3(kFwd2Groups * ng), dim3(kF2Threads), args,
-                                           (size_t)smem, s));
+    const uint8_t* pkx = reinterpret_cast<const uint8_t*>(packed) + kPackedXOff;
+    const uint8_t* xi = reinterpret_cast<const uint8_t*>(x_img);
+    void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bvi, &Bsi, &w0, &pkx, &xi, &bias, &Qtot};
+    PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NQ, FUSED>, dim3(kFwd2Groups * ng), dim3(kF2Threads),
+                                           args, (size_t)smem, s));
   }
   return PAULE_OK;
 }
@@ -340,11 +446,31 @@ int launch_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
                   cudaStream_t s) {
   switch (choose_nq(B, kMaxQ)) {
-    case 1: return launch_fwd2<1>(gates, packed, h, c, xchg, h_img_seq, T, B, s);
-    case 2: return launch_fwd2<2>(gates, packed, h, c, xchg, h_img_seq, T, B, s);
-    case 3: return launch_fwd2<3>(gates, packed, h, c, xchg, h_img_seq, T, B, s);
-    default: return launch_fwd2<4>(gates, packed, h, c, xchg, h_img_seq, T, B, s);
+    case 1: return launch_fwd2<1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    case 2: return launch_fwd2<2, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    case 3: return launch_fwd2<3, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    default: return launch_fwd2<4, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
   }
+}
+
+int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
+                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+  switch (choose_nq(B, kMaxQ)) {
+    case 1: return launch_fwd2<1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    case 2: return launch_fwd2<2, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    case 3: return launch_fwd2<3, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    default: return launch_fwd2<4, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  }
+}
+
+int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s) {
+  const int64_t total = T * B * I;
+  if (total == 0) return PAULE_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  x_image_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<uint8_t*>(img), T, B, (int)I);
+  PAULE_LAUNCH_CHECK("x_image_kernel");
+  return PAULE_OK;
 }
 
 }  // namespace tc
