@@ -143,6 +143,32 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
   if (trace) { trace[0] = globaltimer_ns(); }
   for (unsigned int spin = 0; pending != 0u; ++spin) {
     if (trace) trace[1] += 1;
+#if PAULE_XCHG_LOAD == 2
+    // asynchronous 16-byte copies straight to the swizzled position, then validate + clear the phase bits in place
+#pragma unroll
+    for (int i = 0; i < 4 * NQ; ++i) {
+      const int row = 4 * i + (lane >> 3);
+      if (((pending >> i) & 1u) && active && row < rows)
+        cp_async_cg16(dst + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), src + (size_t)(i * 32 + lane) * 16);
+    }
+    cp_async_wait_all();
+#pragma unroll
+    for (int i = 0; i < 4 * NQ; ++i) {
+      if ((pending >> i) & 1u) {
+        const int row = 4 * i + (lane >> 3);
+        const bool mine = active && row < rows;
+        uint4* sp = reinterpret_cast<uint4*>(dst + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+        uint4 v = make_uint4(phase, phase, phase, phase);
+        if (mine) v = *sp;
+        const bool ok = ((v.x & kPhaseMask) == phase) && ((v.y & kPhaseMask) == phase) && ((v.z & kPhaseMask) == phase) &&
+                        ((v.w & kPhaseMask) == phase);
+        if (__all_sync(0xffffffffu, ok)) {
+          pending &= ~(1u << i);
+          if (mine) *sp = make_uint4(v.x & ~kPhaseMask, v.y & ~kPhaseMask, v.z & ~kPhaseMask, v.w & ~kPhaseMask);
+        }
+      }
+    }
+#else
     uint4 v[4 * NQ];
 #pragma unroll
     for (int i = 0; i < 4 * NQ; ++i)
@@ -162,6 +188,7 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
         }
       }
     }
+#endif
     if ((spin & 255u) == 255u) {
       if (t0 == 0) t0 = globaltimer_ns();
       if (*err != 0) return false;

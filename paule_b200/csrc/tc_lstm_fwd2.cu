@@ -99,51 +99,54 @@ __global__ void x_image_kernel(const float* __restrict__ x, uint8_t* __restrict_
   }
 }
 
-template <int NQ>
+template <int NS, int QS>
 struct Fwd2Smem {
-  uint8_t b[NQ][kV2BBytes];   // B operand per quarter: h_{t-1} of its 16 words, [12 kb][16 rows][128 B]
-  uint64_t mma_done[NQ];      // accumulator of quarter q complete: one commit per loader warp
-  uint64_t acc_free[NQ];      // accumulator of quarter q read and re-zeroed: one arrival per epilogue warp
-  uint64_t xfull[2];          // fused input projection: x_t blocks of all quarters landed (TMA tx-count)
+  uint8_t b[NS][QS * kV2BBytes];   // B operand per slot: h_{t-1} of its 16 QS words, [12 kb][16 QS rows][128 B]
+  uint64_t mma_done[NS];           // accumulator of slot s complete: one commit per loader warp
+  uint64_t acc_free[NS];           // accumulator of slot s read and re-zeroed: one arrival per epilogue warp
+  uint64_t xfull[2];               // fused input projection: x_t blocks of all quarters landed (TMA tx-count)
   uint32_t tmem_base;
-  alignas(1024) uint8_t xb[2][NQ][kXBlockBytes];   // x_t / x_{t+1} operand blocks (double-buffered)
+  alignas(1024) uint8_t xb[2][NS * QS][kXBlockBytes];   // x_t / x_{t+1} operand blocks (double-buffered)
 };
 
 constexpr int kF2EpiWarps = 8;
 constexpr int kF2Threads = 32 * (kF2EpiWarps + kNumKB);   // 640
 
-// NQ = word quarters (16 words each) per CTA.  The quarters of a CTA are INDEPENDENT recurrences that share the resident
-// weights: each has its own accumulator, barriers, operand buffer and exchange blocks, and the loader / epilogue warps
-// visit them round-robin, so one quarter's cell runs while another quarter's h_t is in flight between the SMs.  NQ = 1
-// is the latency-optimal layout for batches that fit one launch (<= 96 words); NQ = 2 / 4 fill the waiting time.
+// A CTA carries NS x QS word quarters (16 words each) behind its resident weights.  The NS SLOTS are INDEPENDENT
+// recurrences (own accumulator, barriers, operand buffer, exchange blocks) visited round-robin by the loader and epilogue
+// warps, so one slot's cell runs while another slot's h_t is in flight between the SMs; the QS quarters of a slot advance in
+// lock-step as one MMA of N = 16 QS, so one probe + fetch latency covers all of them.  (1,1) is the latency-optimal layout
+// for batches that fit one launch (<= 96 words); (2,1), (3,1), (2,2) put 32 / 48 / 64 words on a CTA.
 //
 // FUSED: the layer's input projection runs inside the recurrence.  W_ih (K <= 64) sits in 32 more TMEM columns, x_t of the
 // CTA's quarters arrives as 2 KB operand blocks by TMA one step ahead, and loader warp 11 -- whose k-block holds only 16
 // real hidden units, i.e. one useful MMA -- issues the four x MMAs into the same accumulator; the epilogue adds the bias
 // from registers.  `gates` is then output only (the activated-gate stash): the [T,B,2880] pre-activation tensor is never
 // written to or read from HBM, and the x MMAs do not wait for the exchange.
-template <int NQ, bool FUSED>
+template <int NS, int QS, bool FUSED>
 __global__ void __launch_bounds__(kF2Threads, 1)
 tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed, float* __restrict__ h_out,
                     float* __restrict__ c_out, uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv,
                     int Bs, int w0, const uint8_t* __restrict__ packed_x, const uint8_t* __restrict__ x_img,
                     const float* __restrict__ bias, int Qtot) {
   extern __shared__ uint8_t smem_raw[];
-  using Smem = Fwd2Smem<NQ>;
+  using Smem = Fwd2Smem<NS, QS>;
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kGW = kWq * NQ;                        // words per CTA group
+  constexpr int kSW = kWq * QS;                        // words per slot (the MMA N)
+  constexpr int kGW = kSW * NS;                        // words per CTA group
+  constexpr int kBlk = QS * kLLBlockBytes;             // exchange block of one (slot, parity): [12 kb][16 QS rows][128 B]
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int ug = blockIdx.x % kFwd2Groups, grp = blockIdx.x / kFwd2Groups;
   volatile int* err = reinterpret_cast<volatile int*>(xchg + kXchgErrOff);
-  uint8_t* ll = xchg + kXchgHeader + (size_t)grp * NQ * 2 * kLLBlockBytes;   // [quarter][parity] blocks of this group
+  uint8_t* ll = xchg + kXchgHeader + (size_t)grp * NS * 2 * kBlk;   // [slot][parity] blocks of this group
 
   if (tid == 0) {
-    for (int q = 0; q < NQ; ++q) { mbar_init(&S.mma_done[q], kNumKB); mbar_init(&S.acc_free[q], kF2EpiWarps); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&S.mma_done[s], kNumKB); mbar_init(&S.acc_free[s], kF2EpiWarps); }
     mbar_init(&S.xfull[0], 1);
     mbar_init(&S.xfull[1], 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < NQ * kV2BBytes / 16; i += kF2Threads) reinterpret_cast<uint4*>(&S.b[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < NS * QS * kV2BBytes / 16; i += kF2Threads) reinterpret_cast<uint4*>(&S.b[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_shared();
   if (warp == kF2EpiWarps) tmem_alloc<512>(&S.tmem_base);
   tcgen05_fence_before();
@@ -162,17 +165,14 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
   if (warp >= kF2EpiWarps) {
     // ===================== loader + MMA issuer of k-block kb =====================
     const int kb = warp - kF2EpiWarps;
-    const uint32_t idesc = make_idesc_bf16(kV2M, kWq);
+    const uint32_t idesc = make_idesc_bf16(kV2M, kSW);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);   // A operand: 32 columns per k-block, 8 per K = 16
-    // probes: lane p < 16 watches writer warp (CTA p>>3 of the k-block's two, lane group (p>>1)&3, column half p&1):
-    // its lane 0 publishes row 8 (p&1), units 32 (p>>3) + 8 ((p>>1)&3) of the k-block
-    const uint32_t probe_off = (uint32_t)(((lane & 1) * 8 * 64 + ((lane >> 3) & 1) * 32 + ((lane >> 1) & 3) * 8) * 2);
     const bool xwarp = FUSED && kb == kNumKB - 1;   // this warp also feeds the fused input projection
     const int nk = (kb == kNumKB - 1) ? 1 : 4;       // k-block 11 holds 16 real units: one K = 16 step, the rest is padding
-    const int q_first = w0 / kWq + grp * NQ;         // first global word quarter of this CTA (x image addressing)
-    int nvq = 0;                                     // quarters of this CTA that hold words
+    const int q_first = w0 / kWq + grp * NS * QS;    // first global word quarter of this CTA (x image addressing)
+    int nvq = 0;                                     // quarters of this CTA that hold words (a prefix)
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) nvq += ((grp * NQ + q) * kWq < Bv) ? 1 : 0;
+    for (int q = 0; q < NS * QS; ++q) nvq += (grp * kGW + q * kWq < Bv) ? 1 : 0;
     auto fetch_x = [&](int t) {   // x_t blocks of every valid quarter: one bulk copy each onto xfull[t & 1]
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&S.xfull[t & 1], (uint32_t)(nvq * kXBlockBytes));
@@ -186,35 +186,41 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     for (int t = FUSED ? 0 : 1; t < T; ++t) {
       const uint32_t par = (uint32_t)((FUSED ? t : t - 1) & 1);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int rows = min(kWq, Bv - (grp * NQ + q) * kWq);   // valid words of this quarter: only their rows travel
+      for (int s = 0; s < NS; ++s) {
+        const int rows = min(kSW, Bv - (grp * kGW + s * kSW));   // valid words of this slot: only their rows travel
         if (rows <= 0) continue;
-        uint8_t* bdst = &S.b[q][(size_t)kb * kWq * 128];
+        uint8_t* bdst = &S.b[s][(size_t)kb * kSW * 128];
         const uint64_t db = make_smem_desc_sw128(smem_u32(bdst));
         if (t > 0) {
-          const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 1) * 8 < rows);
-          const uint8_t* src = ll + (size_t)(q * 2 + ((t - 1) & 1)) * kLLBlockBytes + (size_t)kb * (kWq * 128);
+          // probes: lane p < 16 watches writer warp (CTA p>>3 of the k-block's two, lane group (p>>1)&3, column half p&1): its
+          // lane 0 publishes row 8 (p&1) of every quarter, units 32 (p>>3) + 8 ((p>>1)&3) of the k-block; quarters are
+          // published in order, so the probe sits in the last quarter of the slot that has this row
+          const int prow = (lane & 1) * 8;
+          const int pq = prow < rows ? min(QS - 1, (rows - 1 - prow) / kWq) : 0;
+          const uint32_t probe_off = (uint32_t)(((pq * kWq + prow) * 64 + ((lane >> 3) & 1) * 32 + ((lane >> 1) & 3) * 8) * 2);
+          const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && (prow < rows);
+          const uint8_t* src = ll + (size_t)(s * 2 + ((t - 1) & 1)) * kBlk + (size_t)kb * (kSW * 128);
 #ifdef PAULE_TC_TRACE
           while ((xchg_load(src) & kPhaseMask) != phase_bits(t - 1)) {}   // split the fetch: until the first value is visible
           TRACE(0)
           uint64_t ftr[2] = {0, 0};
-          if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr)) break;
+          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr)) break;
           tr_acc[6] += ftr[0] - tr_last;   // probe phase
           tr_acc[7] += ftr[1] * 1000;      // bulk passes (x1000 so that the printout shows passes per step)
 #else
-          if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err)) break;
+          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err)) break;
 #endif
           TRACE(1)
           fence_proxy_async_shared();   // generic-proxy shared-memory writes -> async-proxy (tensor core) reads
           __syncwarp();
         }
         TRACE(2)
-        mbar_wait(&S.acc_free[q], par, err);   // long complete by now: the tile was zeroed a step ago
+        mbar_wait(&S.acc_free[s], par, err);   // long complete by now: the tile was zeroed a step ago
         if (xwarp) mbar_wait(&S.xfull[t & 1], (uint32_t)((t >> 1) & 1), err);   // x_t landed (issued a step ago)
         tcgen05_fence_after();
         TRACE(3)
         if (elect_one_sync()) {
-          const uint32_t d = tmem + (uint32_t)(kV2AccCol + q * kWq);
+          const uint32_t d = tmem + (uint32_t)(kV2AccCol + s * kSW);
           if (t > 0) {
             if (nk == 4) {
 #pragma unroll
@@ -224,16 +230,16 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             }
           }
           if (xwarp) {
-            const uint64_t dx = make_smem_desc_sw128(smem_u32(S.xb[t & 1][q]));
+            const uint64_t dx = make_smem_desc_sw128(smem_u32(S.xb[t & 1][s * QS]));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16_ts(d, tmem + (uint32_t)(kXWCol + 8 * k), dx + 2 * k, idesc, 1u);
           }
-          umma_commit(&S.mma_done[q]);
+          umma_commit(&S.mma_done[s]);
         }
         __syncwarp();
         TRACE(4)
 #ifdef PAULE_TC_TRACE
-        mbar_wait(&S.mma_done[q], par, err);
+        mbar_wait(&S.mma_done[s], par, err);
         TRACE(5)
 #endif
       }
@@ -252,22 +258,22 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     // value pair this thread publishes: even units take word 0 of the pair, odd units word 1
     const int e = ul & 1;
     const int prow = wl0 + e;
-    const size_t ll_off = ((size_t)((ug >> 1) * kWq + prow) * 64 + (size_t)((ug & 1) * 32 + lg * 8 + (ul & ~1))) * 2;
+    const size_t ll_unit = (size_t)((ug & 1) * 32 + lg * 8 + (ul & ~1)) * 2;   // byte offset of the unit pair inside a row
     const bool b1 = (gq & 2) != 0, b0 = (gq & 1) != 0;
-    float c_prev[NQ][2];
+    float c_prev[NS * QS][2];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) c_prev[q][0] = c_prev[q][1] = 0.f;
+    for (int q = 0; q < NS * QS; ++q) c_prev[q][0] = c_prev[q][1] = 0.f;
     float bias4[4] = {0.f, 0.f, 0.f, 0.f};   // FUSED: b_ih + b_hh of this thread's unit, one per gate
     if (FUSED && uvalid)
       for (int g = 0; g < 4; ++g) bias4[g] = __ldg(bias + g * kH + u);
 
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
+    for (int q = 0; q < NS * QS; ++q) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
     tmem_st_wait();
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int q = 0; q < NQ; ++q) mbar_arrive(&S.acc_free[q]);
+      for (int s = 0; s < NS; ++s) mbar_arrive(&S.acc_free[s]);
 
     TRACE_DECL
     for (int t = 0; t < T; ++t) {
@@ -291,95 +297,103 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
       };
       load_xp(0);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        if ((grp * NQ + q) * kWq >= Bv) continue;   // empty quarter (uniform over the CTA)
-        float pre[4][2];
-        if (FUSED || t > 0) {
-          float acc[8];
-          mbar_wait(&S.mma_done[q], (uint32_t)((FUSED ? t : t - 1) & 1), err);
+      for (int s = 0; s < NS; ++s) {
+        if (grp * kGW + s * kSW >= Bv) continue;   // empty slot (uniform over the CTA)
+        const bool has_acc = FUSED || t > 0;
+        if (has_acc) {
+          mbar_wait(&S.mma_done[s], (uint32_t)((FUSED ? t : t - 1) & 1), err);
           TRACE(0)
           tcgen05_fence_after();
-          tmem_ld_x8(taddr + (uint32_t)(q * kWq), acc);
-          TRACE(1)
-          if (t + 1 < T) {   // re-arm the accumulator: every MMA of the next step adds into it
-            tmem_zero_x8(taddr + (uint32_t)(q * kWq));
-            tmem_st_wait();
-          }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&S.acc_free[q]);
-          TRACE(2)
-          // quad transpose (branch-free butterfly): lane gq holds gate gq for word pairs 0..3; afterwards it holds word
-          // pair gq of all four gates.  Round 1 (xor 2) swaps the pair halves, round 2 (xor 1) the pairs inside a half.
-          float k0[2], k1[2], r0[2], r1[2];   // kept / received pair-half after round 1: pair indices 2*b1 + {0, 1}
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            k0[x] = b1 ? acc[4 + x] : acc[0 + x];
-            k1[x] = b1 ? acc[6 + x] : acc[2 + x];
-            r0[x] = __shfl_xor_sync(0xffffffffu, b1 ? acc[0 + x] : acc[4 + x], 2);
-            r1[x] = __shfl_xor_sync(0xffffffffu, b1 ? acc[2 + x] : acc[6 + x], 2);
-          }
-          float s[4][2];   // s[h] = pair gq of gate (gq ^ h)
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            s[0][x] = b0 ? k1[x] : k0[x];
-            s[2][x] = b0 ? r1[x] : r0[x];
-            s[1][x] = __shfl_xor_sync(0xffffffffu, b0 ? k0[x] : k1[x], 1);
-            s[3][x] = __shfl_xor_sync(0xffffffffu, b0 ? r0[x] : r1[x], 1);
-          }
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {   // gate g sits in slot g ^ gq
-            pre[0][x] = b1 ? (b0 ? s[3][x] : s[2][x]) : (b0 ? s[1][x] : s[0][x]);
-            pre[1][x] = b1 ? (b0 ? s[2][x] : s[3][x]) : (b0 ? s[0][x] : s[1][x]);
-            pre[2][x] = b1 ? (b0 ? s[1][x] : s[0][x]) : (b0 ? s[3][x] : s[2][x]);
-            pre[3][x] = b1 ? (b0 ? s[0][x] : s[1][x]) : (b0 ? s[2][x] : s[3][x]);
-          }
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) pre[g][0] = pre[g][1] = 0.f;
-        }
-        float hv[2], gi[2], gf[2], gg[2], go[2], cn[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          gi[k] = fast_sigmoid(fminf(fmaxf(pre[0][k] + xp[0][k], -30.f), 30.f));
-          gf[k] = fast_sigmoid(fminf(fmaxf(pre[1][k] + xp[1][k], -30.f), 30.f));
-          gg[k] = fast_tanh(fminf(fmaxf(pre[2][k] + xp[2][k], -15.f), 15.f));
-          go[k] = fast_sigmoid(fminf(fmaxf(pre[3][k] + xp[3][k], -30.f), 30.f));
-          cn[k] = gf[k] * c_prev[q][k] + gi[k] * gg[k];
-          hv[k] = go[k] * fast_tanh(fminf(fmaxf(cn[k], -15.f), 15.f));
-          c_prev[q][k] = cn[k];
-        }
-        if (q + 1 < NQ) load_xp(q + 1);   // next quarter's input projection while this one's results go out
-        // pair neighbouring units (lane ^ 4) so that one thread owns {h[u], h[u+1]} of one word
-        const float other = __shfl_xor_sync(0xffffffffu, e ? hv[0] : hv[1], 4);
-        const __nv_bfloat162 pr = e ? __floats2bfloat162_rn(other, hv[1]) : __floats2bfloat162_rn(hv[0], other);
-        const uint32_t payload = *reinterpret_cast<const uint32_t*>(&pr);
-        const int wq = grp * kGW + q * kWq;           // first word of this quarter inside the launch
-        const bool pvalid = wq + prow < Bv;
-        if (t + 1 < T && pvalid)                      // critical path: the next step's operand
-          xchg_store(ll + (size_t)(q * 2 + (t & 1)) * kLLBlockBytes + ll_off, payload | phase_bits(t));
-        TRACE(3)
-        // everything below is off the critical path: the next step is already fed
-        if (img_seq != nullptr && uvalid && pvalid) {
-          const int wg = w0 + wq + prow;              // global word (image addressing)
-          *reinterpret_cast<uint32_t*>(img_seq + ((size_t)(wg / kRows) * (size_t)T + t) * kXchgImageBytes +
-                                       umma_offset(kRows, wg % kRows, u & ~1)) = payload;
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int wp = wq + wl0 + k;
-          if (uvalid && wp < Bv) {
-            float* grow = gates + ((size_t)t * Bs + wp) * (4 * kH) + u;
-            grow[0 * kH] = gi[k];
-            grow[1 * kH] = gf[k];
-            grow[2 * kH] = gg[k];
-            grow[3 * kH] = go[k];
-            const size_t o = ((size_t)t * Bs + wp) * kH + u;
-            c_out[o] = cn[k];
-            h_out[o] = hv[k];
+        for (int j = 0; j < QS; ++j) {
+          const int q = s * QS + j;                     // quarter inside the CTA
+          const int wq = grp * kGW + q * kWq;           // first word of this quarter inside the launch
+          float pre[4][2];
+          if (has_acc) {
+            float acc[8];
+            tmem_ld_x8(taddr + (uint32_t)(q * kWq), acc);
+            TRACE(1)
+            if (t + 1 < T) tmem_zero_x8(taddr + (uint32_t)(q * kWq));   // re-arm: every MMA of the next step adds into it
+            if (j == QS - 1) {
+              tmem_st_wait();
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S.acc_free[s]);
+            }
+            TRACE(2)
+            // quad transpose (branch-free butterfly): lane gq holds gate gq for word pairs 0..3; afterwards it holds word
+            // pair gq of all four gates.  Round 1 (xor 2) swaps the pair halves, round 2 (xor 1) the pairs inside a half.
+            float k0[2], k1[2], r0[2], r1[2];   // kept / received pair-half after round 1: pair indices 2*b1 + {0, 1}
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              k0[x] = b1 ? acc[4 + x] : acc[0 + x];
+              k1[x] = b1 ? acc[6 + x] : acc[2 + x];
+              r0[x] = __shfl_xor_sync(0xffffffffu, b1 ? acc[0 + x] : acc[4 + x], 2);
+              r1[x] = __shfl_xor_sync(0xffffffffu, b1 ? acc[2 + x] : acc[6 + x], 2);
+            }
+            float sl[4][2];   // sl[h] = pair gq of gate (gq ^ h)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              sl[0][x] = b0 ? k1[x] : k0[x];
+              sl[2][x] = b0 ? r1[x] : r0[x];
+              sl[1][x] = __shfl_xor_sync(0xffffffffu, b0 ? k0[x] : k1[x], 1);
+              sl[3][x] = __shfl_xor_sync(0xffffffffu, b0 ? r0[x] : r1[x], 1);
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {   // gate g sits in slot g ^ gq
+              pre[0][x] = b1 ? (b0 ? sl[3][x] : sl[2][x]) : (b0 ? sl[1][x] : sl[0][x]);
+              pre[1][x] = b1 ? (b0 ? sl[2][x] : sl[3][x]) : (b0 ? sl[0][x] : sl[1][x]);
+              pre[2][x] = b1 ? (b0 ? sl[1][x] : sl[0][x]) : (b0 ? sl[3][x] : sl[2][x]);
+              pre[3][x] = b1 ? (b0 ? sl[0][x] : sl[1][x]) : (b0 ? sl[2][x] : sl[3][x]);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pre[g][0] = pre[g][1] = 0.f;
           }
+          float hv[2], gi[2], gf[2], gg[2], go[2], cn[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            gi[k] = fast_sigmoid(fminf(fmaxf(pre[0][k] + xp[0][k], -30.f), 30.f));
+            gf[k] = fast_sigmoid(fminf(fmaxf(pre[1][k] + xp[1][k], -30.f), 30.f));
+            gg[k] = fast_tanh(fminf(fmaxf(pre[2][k] + xp[2][k], -15.f), 15.f));
+            go[k] = fast_sigmoid(fminf(fmaxf(pre[3][k] + xp[3][k], -30.f), 30.f));
+            cn[k] = gf[k] * c_prev[q][k] + gi[k] * gg[k];
+            hv[k] = go[k] * fast_tanh(fminf(fmaxf(cn[k], -15.f), 15.f));
+            c_prev[q][k] = cn[k];
+          }
+          if (q + 1 < NS * QS) load_xp(q + 1);   // next quarter's input projection while this one's results go out
+          // pair neighbouring units (lane ^ 4) so that one thread owns {h[u], h[u+1]} of one word
+          const float other = __shfl_xor_sync(0xffffffffu, e ? hv[0] : hv[1], 4);
+          const __nv_bfloat162 pr = e ? __floats2bfloat162_rn(other, hv[1]) : __floats2bfloat162_rn(hv[0], other);
+          const uint32_t payload = *reinterpret_cast<const uint32_t*>(&pr);
+          const bool pvalid = wq + prow < Bv;
+          if (t + 1 < T && pvalid)                      // critical path: the next step's operand
+            xchg_store(ll + (size_t)(s * 2 + (t & 1)) * kBlk + ((size_t)((ug >> 1) * kSW + j * kWq + prow) * 64) * 2 + ll_unit,
+                       payload | phase_bits(t));
+          TRACE(3)
+          // everything below is off the critical path: the next step is already fed
+          if (img_seq != nullptr && uvalid && pvalid) {
+            const int wg = w0 + wq + prow;              // global word (image addressing)
+            *reinterpret_cast<uint32_t*>(img_seq + ((size_t)(wg / kRows) * (size_t)T + t) * kXchgImageBytes +
+                                         umma_offset(kRows, wg % kRows, u & ~1)) = payload;
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int wp = wq + wl0 + k;
+            if (uvalid && wp < Bv) {
+              float* grow = gates + ((size_t)t * Bs + wp) * (4 * kH) + u;
+              grow[0 * kH] = gi[k];
+              grow[1 * kH] = gf[k];
+              grow[2 * kH] = gg[k];
+              grow[3 * kH] = go[k];
+              const size_t o = ((size_t)t * Bs + wp) * kH + u;
+              c_out[o] = cn[k];
+              h_out[o] = hv[k];
+            }
+          }
+          TRACE(4)
         }
-        TRACE(4)
       }
     }
     if (blockIdx.x == 0 && tid == 0) TRACE_DUMP(8)
@@ -410,13 +424,14 @@ int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cu
   return PAULE_OK;
 }
 
-template <int NQ, bool FUSED>
+template <int NS, int QS, bool FUSED>
 int launch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                 void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
   static bool attr_set = false;
-  const int smem = (int)sizeof(Fwd2Smem<NQ>) + 1024;
+  constexpr int NQ = NS * QS;
+  const int smem = (int)sizeof(Fwd2Smem<NS, QS>) + 1024;
   if (!attr_set) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NQ, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NS, QS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQ, NQ);
@@ -437,7 +452,7 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
     const uint8_t* pkx = reinterpret_cast<const uint8_t*>(packed) + kPackedXOff;
     const uint8_t* xi = reinterpret_cast<const uint8_t*>(x_img);
     void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bvi, &Bsi, &w0, &pkx, &xi, &bias, &Qtot};
-    PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NQ, FUSED>, dim3(kFwd2Groups * ng), dim3(kF2Threads),
+    PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NS, QS, FUSED>, dim3(kFwd2Groups * ng), dim3(kF2Threads),
                                            args, (size_t)smem, s));
   }
   return PAULE_OK;
@@ -446,20 +461,20 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
                   cudaStream_t s) {
   switch (choose_nq(B, kMaxQ)) {
-    case 1: return launch_fwd2<1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-    case 2: return launch_fwd2<2, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-    case 3: return launch_fwd2<3, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-    default: return launch_fwd2<4, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    case 1: return launch_fwd2<1, 1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    case 2: return launch_fwd2<2, 1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    case 3: return launch_fwd2<3, 1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+    default: return launch_fwd2<2, 2, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
   }
 }
 
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                    void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
   switch (choose_nq(B, kMaxQ)) {
-    case 1: return launch_fwd2<1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    case 2: return launch_fwd2<2, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    case 3: return launch_fwd2<3, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    default: return launch_fwd2<4, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    case 1: return launch_fwd2<1, 1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    case 2: return launch_fwd2<2, 1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    case 3: return launch_fwd2<3, 1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    default: return launch_fwd2<2, 2, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
   }
 }
 
