@@ -30,9 +30,12 @@ __device__ __forceinline__ float d5(float v0, float v1, float v3, float v4) {
 // Smoothness terms of one (word, time tile): vel/jerk/local-linear partial sums and their gradient.
 // Buffers in shared memory hold frames [t0-12, t0+kTileT+12) of the word, all C channels.
 //   x -> vel (valid: T-4) -> acc (T-8) -> jerk (T-12);  r3 = s_j*jerk; r2 = D^T r3; r1 = D^T r2 + s_v*vel; g = D^T r1 + ll part
+// CT: compile-time channel count (30 in PAULE: the e / C, e % C index splits become multiply-shift), 0 = runtime C.
+template <int CT>
 __global__ void __launch_bounds__(256)
 smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth, float* __restrict__ partial,
-                    int64_t Tmax, const int32_t* __restrict__ word_T, int64_t B, int64_t C, int n_tiles) {
+                    int64_t Tmax, const int32_t* __restrict__ word_T, int64_t B, int64_t C_rt, int n_tiles) {
+  const int C = CT ? CT : C_rt;
   constexpr int W = kTileT + 2 * kHalo;  // 88 frames
   __shared__ float sx[W * kMaxC];
   __shared__ float sa[W * kMaxC];
@@ -41,7 +44,7 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   const int64_t b = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * kTileT;
   const int tid = threadIdx.x;
-  const int n = W * (int)C;
+  const int n = W * C;
   // ragged batches: word b has T frames; frames [T, Tmax) are padding and get a zero gradient
   const int64_t T = word_T ? (int64_t)word_T[b] : Tmax;
   const float sv = 2.0f * kVelWeight / (float)((T - 4) * C);
@@ -50,41 +53,41 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
 
   // frame index f in [0,W) <-> global t = t0 - kHalo + f
   for (int e = tid; e < n; e += 256) {
-    const int f = e / (int)C, c = e % (int)C;
+    const int f = e / C, c = e % C;
     const int64_t t = t0 - kHalo + f;
     sx[e] = (t >= 0 && t < T) ? __ldg(cp + (t * B + b) * C + c) : 0.f;
   }
   __syncthreads();
   // vel[i] uses x[i..i+4], i in [0, T-4): stored at frame of global index i  -> sa
   for (int e = tid; e < n; e += 256) {
-    const int f = e / (int)C, c = e % (int)C;
+    const int f = e / C, c = e % C;
     const int64_t i = t0 - kHalo + f;
     float v = 0.f;
     if (i >= 0 && i < T - 4 && f + 4 < W)
-      v = d5(sx[e], sx[e + (int)C], sx[e + 3 * (int)C], sx[e + 4 * (int)C]);
+      v = d5(sx[e], sx[e + C], sx[e + 3 * C], sx[e + 4 * C]);
     sa[e] = v;
   }
   __syncthreads();
   // local partial sums of vel^2 and ll^2 over the frames this CTA owns
   float pv = 0.f, pj = 0.f, pl = 0.f;
-  for (int e = tid; e < kTileT * (int)C; e += 256) {
-    const int f = kHalo + e / (int)C, c = e % (int)C;
-    const int64_t i = t0 + e / (int)C;
-    const int idx = f * (int)C + c;
+  for (int e = tid; e < kTileT * C; e += 256) {
+    const int f = kHalo + e / C, c = e % C;
+    const int64_t i = t0 + e / C;
+    const int idx = f * C + c;
     if (i < T - 4) pv += sa[idx] * sa[idx];
     if (i >= 1 && i < T - 1) {
       // ll[i-1] = (2 x[i] - x[i-1] - x[i+1]) / 2   (util.py:614)
-      const float l = __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[idx]), sx[idx - (int)C]), sx[idx + (int)C]), 2.0f);
+      const float l = __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[idx]), sx[idx - C]), sx[idx + C]), 2.0f);
       pl += l * l;
     }
   }
   // acc[i] = d5(vel)[i], i in [0, T-8) -> sb
   for (int e = tid; e < n; e += 256) {
-    const int f = e / (int)C;
+    const int f = e / C;
     const int64_t i = t0 - kHalo + f;
     float v = 0.f;
     if (i >= 0 && i < T - 8 && f + 4 < W)
-      v = d5(sa[e], sa[e + (int)C], sa[e + 3 * (int)C], sa[e + 4 * (int)C]);
+      v = d5(sa[e], sa[e + C], sa[e + 3 * C], sa[e + 4 * C]);
     sb[e] = v;
   }
   __syncthreads();
@@ -93,11 +96,11 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   {
     int q = 0;
     for (int e = tid; e < n; e += 256, ++q) {
-      const int f = e / (int)C;
+      const int f = e / C;
       const int64_t i = t0 - kHalo + f;
       float v = 0.f;
       if (i >= 0 && i < T - 12 && f + 4 < W) {
-        v = d5(sb[e], sb[e + (int)C], sb[e + 3 * (int)C], sb[e + 4 * (int)C]);
+        v = d5(sb[e], sb[e + C], sb[e + 3 * C], sb[e + 4 * C]);
         if (f >= kHalo && f < kHalo + kTileT) pj += v * v;
       }
       r3loc[q] = sj * v;
@@ -112,7 +115,7 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   // adjoint of d5: (D^T r)[k] = (r[k] - 8 r[k-1] + 8 r[k-3] - r[k-4]) / 12  with r = 0 outside its range.
   // r2 = D^T r3 (index range T-8), accumulate into registers, then r1 = D^T r2 + sv*vel (range T-4), g = D^T r1.
   auto adj = [&](const float* r, int e, int f) -> float {
-    const int c1 = (int)C;
+    const int c1 = C;
     const float r0 = r[e];
     const float r1 = (f >= 1) ? r[e - c1] : 0.f;
     const float r3 = (f >= 3) ? r[e - 3 * c1] : 0.f;
@@ -122,7 +125,7 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   {
     int q = 0;
     for (int e = tid; e < n; e += 256, ++q) {
-      const int f = e / (int)C;
+      const int f = e / C;
       const int64_t k = t0 - kHalo + f;
       r3loc[q] = (k >= 0 && k < T - 8) ? adj(sb, e, f) : 0.f;  // r2
     }
@@ -136,7 +139,7 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
   {
     int q = 0;
     for (int e = tid; e < n; e += 256, ++q) {
-      const int f = e / (int)C;
+      const int f = e / C;
       const int64_t k = t0 - kHalo + f;
       r3loc[q] = (k >= 0 && k < T - 4) ? adj(sb, e, f) + sv * sa[e] : 0.f;  // r1 = D^T r2 + sv * vel
     }
@@ -147,18 +150,18 @@ smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth
     for (int e = tid; e < n; e += 256, ++q) sa[e] = r3loc[q];  // sa = r1
   }
   __syncthreads();
-  for (int e = tid; e < kTileT * (int)C; e += 256) {
-    const int f = kHalo + e / (int)C, c = e % (int)C;
-    const int64_t t = t0 + e / (int)C;
+  for (int e = tid; e < kTileT * C; e += 256) {
+    const int f = kHalo + e / C, c = e % C;
+    const int64_t t = t0 + e / C;
     if (t >= Tmax) continue;
     if (t >= T) { dcp_smooth[(t * B + b) * C + c] = 0.f; continue; }
-    const int idx = f * (int)C + c;
+    const int idx = f * C + c;
     float g = adj(sa, idx, f);
     // local-linear adjoint: ll[i] = x[i+1] - (x[i] + x[i+2])/2, i in [0,T-2); g_ll[t] = sl*(ll[t-1] - ll[t]/2 - ll[t-2]/2)
     auto ll_at = [&](int64_t i, int fi) -> float {  // ll with centre frame fi (global centre i+1)
       if (i < 0 || i >= T - 2) return 0.f;
-      const int id = fi * (int)C + c;
-      return __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[id]), sx[id - (int)C]), sx[id + (int)C]), 2.0f);
+      const int id = fi * C + c;
+      return __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[id]), sx[id - C]), sx[id + C]), 2.0f);
     };
     const float lc = ll_at(t - 1, f), lm = ll_at(t - 2, f - 1), lp = ll_at(t, f + 1);
     g += sl * (lc - 0.5f * lm - 0.5f * lp);
@@ -204,11 +207,23 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
   const bool use_mel = objective != PAULE_OBJ_SEMVEC, use_sem = objective != PAULE_OBJ_ACOUSTIC;
   float sm = 0.f;
   const int64_t nm = Tm * Cm;
-  for (int64_t e = tid; e < nm; e += 256) {
-    const int64_t t = e / Cm, c = e % Cm;
-    const int64_t off = (t * B + b) * Cm + c;
-    const float d = mel[off] - tmel[off];
-    sm += d * d;
+  // thread = (channel tid % 64, frame tid / 64 + 4 i): a warp reads one 240-byte mel row segment per step, no division
+  const int mc = tid & 63;
+  const bool mcl = mc < (int)Cm && Cm <= 64;
+  if (Cm <= 64) {
+    if (mcl)
+      for (int64_t t = tid >> 6; t < Tm; t += 4) {
+        const int64_t off = (t * B + b) * Cm + mc;
+        const float d = mel[off] - tmel[off];
+        sm += d * d;
+      }
+  } else {
+    for (int64_t e = tid; e < nm; e += 256) {
+      const int64_t t = e / Cm, c = e % Cm;
+      const int64_t off = (t * B + b) * Cm + c;
+      const float d = mel[off] - tmel[off];
+      sm += d * d;
+    }
   }
   sm = block_sum_256(sm, sh);
   float ss = 0.f;
@@ -242,10 +257,18 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
   }
   // d(w*sqrt(mean(e^2)))/de = w*e/(N*rmse); eps = 0 -> NaN at zero error, as in the reference (paule.py:68)
   const float gm = use_mel ? kMelWeight / ((float)nm * rmse_m) : 0.f;
-  for (int64_t e = tid; e < Tm_max * Cm; e += 256) {   // padded mel frames get a zero gradient
-    const int64_t t = e / Cm, c = e % Cm;
-    const int64_t off = (t * B + b) * Cm + c;
-    dmel[off] = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
+  if (Cm <= 64) {
+    if (mcl)
+      for (int64_t t = tid >> 6; t < Tm_max; t += 4) {   // padded mel frames get a zero gradient
+        const int64_t off = (t * B + b) * Cm + mc;
+        dmel[off] = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
+      }
+  } else {
+    for (int64_t e = tid; e < Tm_max * Cm; e += 256) {
+      const int64_t t = e / Cm, c = e % Cm;
+      const int64_t off = (t * B + b) * Cm + c;
+      dmel[off] = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
+    }
   }
   if (dsv != nullptr) {
     const float gs = (use_sem && sv != nullptr) ? kSemWeight / ((float)S * rmse_s) : 0.f;
@@ -376,8 +399,12 @@ int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const
   PAULE_REQUIRE(objective >= 0 && objective <= 2);
   if (objective != PAULE_OBJ_ACOUSTIC) PAULE_REQUIRE(sv && tsv && dsv);
   const int n_tiles = (int)ceil_div(T, (int64_t)kTileT);
-  smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B,
-                                                                                 C, n_tiles);
+  if (C == 30)
+    smooth_terms_kernel<30><<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
+                                                                                       n_tiles);
+  else
+    smooth_terms_kernel<0><<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
+                                                                                      n_tiles);
   PAULE_LAUNCH_CHECK("smooth_terms_kernel");
   word_loss_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(mel, tmel, sv, tsv, scratch, n_tiles, terms,
                                                                step_count, slots, dmel, dsv, T, Tm, word_T, B, C, Cm,
