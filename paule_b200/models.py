@@ -61,11 +61,28 @@ def _check_input(x: torch.Tensor, name: str) -> torch.Tensor:
     return x.float().contiguous()
 
 
-def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights]) -> torch.Tensor:
-    """x [B,T,I] batch-first -> top layer's h, TIME-MAJOR [T,B,H]."""
+def _learning(params) -> bool:
+    """True when a weight gradient is wanted: grad mode on and a parameter requires grad (continue-learning of the models,
+    paule/paule.py:1372-1377).  Planning runs under requires_grad=False weights or no_grad and takes the cached operands."""
+    return torch.is_grad_enabled() and any(p.requires_grad for p in params)
+
+
+def _param(p: torch.Tensor) -> torch.Tensor:
+    return p if (p.dtype == torch.float32 and p.is_contiguous()) else p.float().contiguous()
+
+
+def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights], lstm: nn.LSTM = None) -> torch.Tensor:
+    """x [B,T,I] batch-first -> top layer's h, TIME-MAJOR [T,B,H].  With ``lstm`` given and a weight gradient wanted, the
+    live parameters go into the ops (so autograd reaches them) instead of the cached, detached operand pack."""
     h = x
+    learn = lstm is not None and _learning(lstm.parameters())
     for k, L in enumerate(layers):
-        h, _, _ = ops.lstm_layer_fwd(h, k == 0, L.w_ih, L.w_hh, L.bias)
+        if learn:
+            w_ih, w_hh = _param(getattr(lstm, f"weight_ih_l{k}")), _param(getattr(lstm, f"weight_hh_l{k}"))
+            bias = _param(getattr(lstm, f"bias_ih_l{k}")) + _param(getattr(lstm, f"bias_hh_l{k}"))
+            h, _, _ = ops.lstm_layer_fwd(h, k == 0, w_ih, w_hh, bias)
+        else:
+            h, _, _ = ops.lstm_layer_fwd(h, k == 0, L.w_ih, L.w_hh, L.bias)
     return h
 
 
@@ -83,7 +100,10 @@ class ForwardModel(nn.Module):
 
     def forward(self, x, *args):
         x = _check_input(x, "ForwardModel.forward(x)")
-        h = lstm_stack(x, self._pack.get())
+        h = lstm_stack(x, self._pack.get(), self.lstm)
+        if _learning(self.post_linear.parameters()):
+            return ops.linear_tm(h, _param(self.post_linear.weight), _param(self.post_linear.bias),
+                                 bool(self.apply_half_sequence), True)
         return ops.linear_tm(h, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias),
                              bool(self.apply_half_sequence), True)
 

@@ -146,8 +146,8 @@ def _(x, batch_first_in, w_ih, w_hh, bias):
 
 @torch.library.custom_op("paule_b200::lstm_layer_bwd", mutates_args=())
 def lstm_layer_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, w_ih_t: torch.Tensor,
-                   w_hh_t: torch.Tensor, batch_first_out: bool) -> torch.Tensor:
-    """Input-gradient BPTT: dh [T,B,H] -> dx [T,B,I] (or [B,T,I] if batch_first_out)."""
+                   w_hh_t: torch.Tensor, batch_first_out: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Input-gradient BPTT: dh [T,B,H] -> (dx [T,B,I] (or [B,T,I] if batch_first_out), da [T,B,4H] = d loss / d pre-activations)."""
     _chk(dh, "dh"); _chk(gates, "gates"); _chk(c, "c")
     T, B, H = dh.shape
     I = w_ih_t.shape[0]
@@ -155,35 +155,48 @@ def lstm_layer_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, w_ih_
     scratch = torch.empty((B, H), device=dh.device, dtype=torch.float32)
     dx = torch.empty((B, T, I) if batch_first_out else (T, B, I), device=dh.device, dtype=torch.float32)
     if T * B == 0:
-        return dx
+        return dx, da
     _lib.check(_lib.load().paule_lstm_seq_bwd_f32(da.data_ptr(), c.data_ptr(), w_hh_t.data_ptr(), dh.data_ptr(), 1,
                                                   None, scratch.data_ptr(), T, B, H, _stream()),
                "paule_lstm_seq_bwd_f32")
     c_map = (B, I, T * I) if batch_first_out else (1, I, 0)
     linear_rows_(dx, da, w_ih_t, None, T * B, (1, 4 * H, 0), c_map)
-    return dx
+    return dx, da
 
 
 @lstm_layer_bwd.register_fake
 def _(dh, gates, c, w_ih_t, w_hh_t, batch_first_out):
     T, B, _ = dh.shape
     I = w_ih_t.shape[0]
-    return dh.new_empty((B, T, I) if batch_first_out else (T, B, I))
+    return dh.new_empty((B, T, I) if batch_first_out else (T, B, I)), torch.empty_like(gates)
 
 
 def _lstm_layer_setup(ctx, inputs, output):
     x, batch_first_in, w_ih, w_hh, bias = inputs
     h, gates, c = output
-    ctx.save_for_backward(gates, c, w_ih, w_hh)
+    ctx.weight_grads = any(ctx.needs_input_grad[2:5])
+    if ctx.weight_grads:   # continue-learning (paule/paule.py:1372-1377): also keep the operands of the dW GEMMs
+        ctx.save_for_backward(gates, c, w_ih, w_hh, x, h)
+    else:
+        ctx.save_for_backward(gates, c, w_ih, w_hh)
     ctx.batch_first_in = batch_first_in
 
 
 def _lstm_layer_backward(ctx, dh, dgates, dc):
-    gates, c, w_ih, w_hh = ctx.saved_tensors
+    gates, c, w_ih, w_hh = ctx.saved_tensors[:4]
     if dh is None:
         return None, None, None, None, None
-    dx = lstm_layer_bwd(dh.contiguous(), gates, c, w_ih.t().contiguous(), w_hh.t().contiguous(), ctx.batch_first_in)
-    return dx, None, None, None, None          # input gradients only: weight gradients are not needed to plan
+    dx, da = lstm_layer_bwd(dh.contiguous(), gates, c, w_ih.t().contiguous(), w_hh.t().contiguous(), ctx.batch_first_in)
+    if not ctx.weight_grads:
+        return dx, None, None, None, None      # planning needs input gradients only
+    # weight gradients: plain GEMMs over the saved operands (library GEMMs; they are outer-loop work, not the hot path)
+    x, h = ctx.saved_tensors[4:6]
+    T, B, G = da.shape
+    x_tm = x.transpose(0, 1) if ctx.batch_first_in else x
+    da2 = da.reshape(T * B, G)
+    d_w_ih = da2.t() @ x_tm.reshape(T * B, -1)
+    d_w_hh = da[1:].reshape((T - 1) * B, G).t() @ h[:-1].reshape((T - 1) * B, -1) if T > 1 else torch.zeros_like(w_hh)
+    return dx, None, d_w_ih, d_w_hh, da2.sum(0)
 
 
 lstm_layer_fwd.register_autograd(_lstm_layer_backward, setup_context=_lstm_layer_setup)
@@ -247,16 +260,29 @@ def _(dy, w_t, T, pool_pairs, batch_first_out):
 
 def _linear_tm_setup(ctx, inputs, output):
     x, w, bias, pool_pairs, batch_first_out = inputs
-    ctx.save_for_backward(w)
+    ctx.weight_grads = any(ctx.needs_input_grad[1:3])
+    if ctx.weight_grads:
+        ctx.save_for_backward(w, x)
+    else:
+        ctx.save_for_backward(w)
     ctx.T = x.shape[0]
     ctx.pool_pairs = pool_pairs
     ctx.batch_first_out = batch_first_out
 
 
 def _linear_tm_backward(ctx, dy):
-    (w,) = ctx.saved_tensors
+    w = ctx.saved_tensors[0]
     dx = linear_tm_bwd(dy.contiguous(), w.t().contiguous(), ctx.T, ctx.pool_pairs, ctx.batch_first_out)
-    return dx, None, None, None, None
+    if not ctx.weight_grads:
+        return dx, None, None, None, None
+    x = ctx.saved_tensors[1]                                  # [T,B,K] time-major
+    dy_tm = dy.transpose(0, 1) if ctx.batch_first_out else dy     # [T',B,N]
+    if ctx.pool_pairs:
+        To = dy_tm.shape[0]
+        x = 0.5 * (x[0:2 * To:2] + x[1:2 * To:2])
+    N = dy_tm.shape[-1]
+    d_w = dy_tm.reshape(-1, N).t() @ x.reshape(-1, x.shape[-1])
+    return dx, d_w, dy_tm.reshape(-1, N).sum(0), None, None
 
 
 linear_tm.register_autograd(_linear_tm_backward, setup_context=_linear_tm_setup)

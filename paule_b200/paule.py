@@ -61,12 +61,15 @@ class Paule():
                  tube_mel_model=None, tube_mel_optimizer=None, tube_embedder=None,
                  continue_data=None, device=torch.device('cuda'), smiling=False,
                  use_speech_classifier=False, speech_classifier=None, speech_classifier_optimizer=None,
-                 math=ops.MATH_FP32):
+                 math=ops.MATH_FP32, synthesizer=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.PauleB200Error("paule_b200.Paule runs on a B200 (device='cuda'); there is no CPU fallback")
         self.smiling = smiling
         self.math = math
+        # host-side stand-in for speak() + librosa_melspec() + normalize_mel_librosa() (paule/util.py:115-146,175-249):
+        # callable(cp [T,30] float ndarray) -> normalised log-mel [T//2,60] ndarray.  Only called at outer-loop boundaries.
+        self.synthesizer = synthesizer
         if use_somatosensory_feedback and use_speech_classifier:
             raise NotImplementedError("at the moment you have to choose either to use `use_somatosenrosry_feedback=True` OR to use `use_speech_classifier=True` or none")
         if use_somatosensory_feedback or use_speech_classifier:
@@ -96,6 +99,49 @@ class Paule():
         self.best_synthesis_acoustic = None
         self.best_synthesis_semantic = None
         self.last_planner: Optional[BatchPlanner] = None
+
+    def continue_learning_pred(self, cps, mels, *, n_epochs=10, batch_size=8, shuffle=True):
+        """Continue-learning of the predictive forward model on (cp, produced mel) pairs: the learning step of the outer
+        loop (paule/paule.py:1361-1377) -- same-size batching (create_epoch_batches(same_size_batching=True), :349-369),
+        ``Y_hat = pred_model(batch)``, RMSE criterion (:68), ``self.pred_optimizer`` -- on the GPU: forward and input-gradient
+        BPTT on the CUDA LSTM kernels, weight gradients as GEMMs over the saved operands.  ``cps[i]`` is [T_i,30], ``mels[i]``
+        [T_i // 2, 60].  Returns the mean loss of every epoch; the planner of the last plan_resynth call is repacked."""
+        if len(cps) != len(mels):
+            raise ValueError("cps and mels need the same number of samples")
+        xs = [torch.as_tensor(np.ascontiguousarray(c)).float() for c in cps]
+        ys = [torch.as_tensor(np.ascontiguousarray(m)).float() for m in mels]
+        by_len = {}
+        for i, x in enumerate(xs):
+            if ys[i].shape[0] != x.shape[0] // 2:
+                raise ValueError(f"sample {i}: {x.shape[0]} cp frames need {x.shape[0] // 2} mel frames, got {ys[i].shape[0]}")
+            by_len.setdefault(int(x.shape[0]), []).append(i)
+        was_training = self.pred_model.training
+        self.pred_model.train()
+        epoch_losses = []
+        for _ in range(int(n_epochs)):
+            batches = []
+            for length in sorted(by_len):                       # same-size batching (:349-369)
+                idx = list(by_len[length])
+                if shuffle:
+                    random.shuffle(idx)
+                batches += [idx[k:k + batch_size] for k in range(0, len(idx), batch_size)]
+            if shuffle:
+                random.shuffle(batches)
+            losses = []
+            for j in batches:
+                batch_input = torch.stack([xs[i] for i in j]).to(self.device)
+                batch_output = torch.stack([ys[i] for i in j]).to(self.device)
+                y_hat = self.pred_model(batch_input)                         # :1372
+                self.pred_optimizer.zero_grad()                              # :1374
+                pred_loss = torch.sqrt(torch.mean((y_hat - batch_output) ** 2))   # RMSELoss(eps=0), paule/util.py:570-572
+                pred_loss.backward()                                         # :1376
+                self.pred_optimizer.step()                                   # :1377
+                losses.append(float(pred_loss.item()))
+            epoch_losses.append(float(np.mean(losses)) if losses else float("nan"))
+        self.pred_model.train(was_training)
+        if self.last_planner is not None:
+            self.last_planner.refresh_weights()      # repack: the planner holds bf16 / transposed copies of the weights
+        return epoch_losses
 
     def plan_iterative(self, overlap=8):
         """Empty stub in the reference as well (paule/paule.py:383-388)."""
@@ -283,6 +329,7 @@ class Paule():
         initial_pred_mel, initial_pred_semvec = planner.forward()
 
         cp_steps, grad_steps, pred_semvec_steps, pred_mel_steps = [], [], [], []
+        pred_model_loss = []
         need_per_step = log_cps or log_gradients
         for ii_outer in range(n_outer):
             cp_steps_ii, pred_semvec_steps_ii, pred_mel_steps_ii = [], [], []
@@ -298,7 +345,24 @@ class Paule():
             cp_steps.append(cp_steps_ii)
             pred_semvec_steps.append(pred_semvec_steps_ii)
             pred_mel_steps.append(pred_mel_steps_ii)
-            # continue-learning on synthesised audio (paule.py:1243-1454) needs VocalTractLab: not part of this path
+            # continue-learning (paule.py:1243-1454): the planned cps of this outer iteration are synthesised on the host
+            # (VocalTractLab + librosa behind `synthesizer`), the produced mels train pred_model, the planner is repacked.
+            # Without a synthesizer the models stay frozen (the reference needs VocalTractLab here).
+            if continue_learning and self.synthesizer is not None:
+                cur = planner.planned_cp().detach().cpu().numpy()
+                if lengths is not None:
+                    cur_list = [cur[b, :L] for b, L in enumerate(lengths)]
+                else:
+                    cur_list = [cur[b] for b in range(cur.shape[0])]
+                prod = [np.asarray(self.synthesizer(c), dtype=np.float32) for c in cur_list]
+                train_cps, train_mels = list(cur_list), list(prod)
+                if add_training_data_pred and self.continue_data is not None and len(self.continue_data) > 0:
+                    k = min(len(self.continue_data), len(cur_list))      # 50 % known data, 50 % produced (:1256-1268)
+                    for i in random.sample(range(len(self.continue_data)), k=k):
+                        row = self.continue_data.iloc[i] if hasattr(self.continue_data, "iloc") else self.continue_data[i]
+                        train_cps.append(np.asarray(row["cp_norm"], dtype=np.float32))
+                        train_mels.append(np.asarray(row["melspec_norm_synthesized"], dtype=np.float32))
+                pred_model_loss += self.continue_learning_pred(train_cps, train_mels, n_epochs=n_epochs, batch_size=batch_size)
 
         # final predictions (paule.py:1456-1470)
         planned_cp = planner.planned_cp()
@@ -316,7 +380,7 @@ class Paule():
             None, None, out(target_mel), None, None, None, out(pred_mel), None, out(initial_pred_semvec), None,
             out(pred_semvec), list(), per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
             per_step("semvec") if sem_logged else list(), list(), cp_steps, pred_semvec_steps, list(), grad_steps,
-            list(), list(), pred_mel_steps, list(), list())
+            list(), list(), pred_mel_steps, pred_model_loss, list())
 
 
 # BASELINE.json's north_star spells the class name in capitals

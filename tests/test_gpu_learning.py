@@ -1,0 +1,129 @@
+"""Continue-learning of the predictive forward model on the GPU (reference: paule/paule.py:1361-1377): weight
+gradients of the CUDA LSTM / Linear ops against torch autograd on the reference's modules, the learning loop against the
+same loop in plain torch on the CPU, and the outer-loop hook of plan_resynth.  Run on the B200 box: python -m pytest -m gpu"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import paule_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from paule_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda:0")
+
+
+def _pair(hidden, layers, seed):
+    """(CUDA ForwardModel, reference-arithmetic CPU twin) with identical weights."""
+    import paule_b200 as P
+    torch.manual_seed(seed)
+    mine = P.ForwardModel(num_lstm_layers=layers, hidden_size=hidden)
+    ref = _TorchForward(layers, hidden)
+    ref.load_state_dict(mine.state_dict())
+    return mine, ref
+
+
+class _TorchForward(torch.nn.Module):
+    """paule/models.py:326-356 restated with torch.nn (the oracle's arithmetic)."""
+
+    def __init__(self, layers, hidden):
+        super().__init__()
+        self.half_sequence = torch.nn.AvgPool1d(2, stride=2)
+        self.lstm = torch.nn.LSTM(30, hidden, num_layers=layers, batch_first=True)
+        self.post_linear = torch.nn.Linear(hidden, 60)
+
+    def forward(self, x, *args):
+        out, _ = self.lstm(x)
+        out = self.post_linear(out)
+        return self.half_sequence(out.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+@pytest.mark.parametrize("hidden,layers,B,T", [(64, 2, 3, 20), (720, 1, 2, 14)])
+def test_weight_gradients_match_torch_autograd(dev, hidden, layers, B, T):
+    mine, ref = _pair(hidden, layers, 1)
+    mine = mine.to(dev).train()
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(B, T, 30, generator=g) - 0.5
+    y = torch.rand(B, T // 2, 60, generator=g)
+    torch.sqrt(torch.mean((ref(x) - y) ** 2)).backward()
+    out = mine(x.to(dev))
+    loss = torch.sqrt(torch.mean((out - y.to(dev)) ** 2))
+    loss.backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref(x).detach().numpy(), atol=2e-5)
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        scale = q.grad.abs().max().item() + 1e-12
+        np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.numpy(), atol=2e-4 * scale, rtol=2e-3, err_msg=n)
+
+
+def test_continue_learning_pred_matches_the_same_loop_in_torch(dev):
+    import paule_b200 as P
+    mine, ref = _pair(96, 1, 3)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=96)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=96)
+    pm = P.Paule(pred_model=mine, inv_model=inv, embedder=emb, device=dev)
+    g = torch.Generator().manual_seed(4)
+    lens = [20, 20, 20, 32, 32, 20, 32]
+    cps = [(torch.rand(L, 30, generator=g) - 0.5).numpy() for L in lens]
+    mels = [torch.rand(L // 2, 60, generator=g).numpy() for L in lens]
+    losses = pm.continue_learning_pred(cps, mels, n_epochs=3, batch_size=3, shuffle=False)
+    # the same loop on the CPU: lengths ascending, batches of <= 3 consecutive samples of one length, Adam(lr=1e-3)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.001)
+    ref_losses = []
+    for _ in range(3):
+        ep = []
+        for L in sorted(set(lens)):
+            idx = [i for i, l in enumerate(lens) if l == L]
+            for k in range(0, len(idx), 3):
+                j = idx[k:k + 3]
+                xb = torch.stack([torch.from_numpy(cps[i]) for i in j])
+                yb = torch.stack([torch.from_numpy(mels[i]) for i in j])
+                opt.zero_grad()
+                l = torch.sqrt(torch.mean((ref(xb) - yb) ** 2))
+                l.backward()
+                opt.step()
+                ep.append(float(l.detach()))
+        ref_losses.append(float(np.mean(ep)))
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-4)
+    assert losses[-1] < losses[0]
+    for (n, p), (_, q) in zip(pm.pred_model.named_parameters(), ref.named_parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().numpy(), atol=2e-5, err_msg=n)
+
+
+@pytest.mark.parametrize("math", [0, 1])
+def test_plan_resynth_outer_loop_learns_and_repacks(dev, math):
+    """continue_learning=True with a host-side synthesizer: the produced mels train pred_model between the outer iterations and
+    the planner plans the next iteration with the updated weights."""
+    import paule_b200 as P
+    torch.manual_seed(0)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=720)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=720)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=720)
+    rng = np.random.RandomState(0)
+    proj = rng.randn(30, 60).astype(np.float32) * 0.2
+
+    def synth(cp):   # deterministic stand-in for VocalTractLab + librosa: pooled frames through a fixed map
+        pooled = 0.5 * (cp[0::2][: cp.shape[0] // 2] + cp[1::2][: cp.shape[0] // 2])
+        return np.tanh(pooled @ proj) + 0.5
+
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, math=math, synthesizer=synth)
+    before = copy.deepcopy(pred.state_dict())
+    _, tmel = O.synthetic_inputs(4, 40, seed=8)
+    cp0, _ = O.synthetic_inputs(4, 40, seed=9)
+    res = pm.plan_resynth(target_acoustic=tmel.numpy(), initial_cp=cp0.numpy(), initialize_from=None, objective="acoustic_semvec",
+                          n_outer=2, n_inner=3, continue_learning=True, n_epochs=2, batch_size=2, verbose=False)
+    assert len(res.pred_model_loss) == 4 and all(np.isfinite(res.pred_model_loss))
+    assert res.pred_model_loss[-1] < res.pred_model_loss[0]
+    after = pred.state_dict()
+    assert any(not torch.equal(before[k].cpu(), after[k].cpu()) for k in before)
+    assert np.isfinite(res.planned_cp).all() and len(res.planned_loss_steps) == 6
+    # the planner now holds the UPDATED weights: its prediction for the planned cps == the updated module's own forward
+    with torch.no_grad():
+        direct = pred(torch.from_numpy(res.planned_cp).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(res.pred_mel, direct, atol=1e-5 if math == 0 else 5e-3)
