@@ -320,7 +320,7 @@ def dominant_kernel_roofline(planner, math, dev):
     st = torch.cuda.current_stream().cuda_stream
     xchg = None
     if math != 0:
-        xchg = torch.empty(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)
+        xchg = torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=dev)   # status word starts at 0
 
     def fwd():
         if math == 0:

@@ -187,7 +187,8 @@ PAULE_API int paule_tc_gemm_img(const void* a_img, const void* packed_b, const f
  * for the whole sequence, one cooperative launch per layer and 64-word group, grid barrier per time step.
  * Same contract as paule_lstm_seq_fwd_f32 / _bwd_f32 plus:
  *   packed      image from paule_tc_pack_lstm
- *   xchg        >= paule_tc_rnn_xchg_bytes(B) bytes of scratch (ping-pong exchange images + barrier words)
+ *   xchg        >= paule_tc_rnn_xchg_bytes(B) bytes of scratch (exchange blocks + status word), ZERO-FILLED once by the
+ *               caller: int32 at byte 2048 is the sticky status (0 ok, non-zero = a watchdog fired, results invalid)
  *   h_img_seq / da_img_seq   NULL, or >= paule_tc_img_seq_bytes(T, B, 1 / 4) bytes that were ZERO-FILLED once by
  *               the owner: the kernel then keeps the bf16 image of every step there (A operand of
  *               paule_tc_gemm_img) instead of ping-ponging inside xchg. */
@@ -268,6 +269,10 @@ typedef struct paule_plan {
 } paule_plan;
 
 PAULE_API size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);
+/* Byte offset inside the workspace of the int32 status word of the persistent kernels: 0 = ok, non-zero = a watchdog fired
+ * (an inter-CTA wait exceeded 4 s) and the results are invalid -- the library never hangs the GPU, the caller must check
+ * this word before trusting results.  (size_t)-1 when the configuration has no such word (fp32 math). */
+PAULE_API size_t paule_plan_status_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);
 /* forward only (no_grad predictions: paule.py:822-824, :1460-1464): fills pred_mel, pred_sv. */
 PAULE_API int paule_plan_forward(const paule_plan* p, paule_stream_t stream);
 /* one full inner step. */

@@ -162,6 +162,14 @@ extern "C" size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, in
   return carve(nullptr, B, T, H, C, Cm, S, math).floats * sizeof(float);
 }
 
+// Byte offset, inside the workspace, of the int32 status word of the persistent kernels (0 = ok, 1 / 2 = a watchdog fired:
+// an exchange / barrier wait exceeded 4 s, results are invalid).  SIZE_MAX when the configuration has no such word (fp32).
+extern "C" size_t paule_plan_status_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math) {
+  if (B <= 0 || T <= 0 || H <= 0 || math == PAULE_MATH_FP32) return (size_t)-1;
+  const Workspace w = carve(reinterpret_cast<void*>(uintptr_t(256)), B, T, H, C, Cm, S, math);
+  return (size_t)(reinterpret_cast<uintptr_t>(w.xchg) - 256) + 2048;   // kXchgErrOff
+}
+
 extern "C" int paule_plan_forward(const paule_plan* p, paule_stream_t stream) {
   PAULE_TRY(check_plan(p));
   const Workspace w = carve(p->workspace, p->B, p->T, p->H, p->C, p->Cm, p->S, p->math);

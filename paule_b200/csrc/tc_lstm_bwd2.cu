@@ -330,7 +330,7 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
   for (int64_t r0 = 0; r0 < B; r0 += pw) {
     const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
     const int ng = (int)((Bv + gw - 1) / gw);
-    PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));
+    // (the status word in the header is sticky: it starts at zero and is never cleared by a launch)
     PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)ng * 2 * 4 * NQ * kLLBlockBytes, s));
     float* gp = gates + r0 * 4 * kH;
     const float* cp = c + r0 * kH;

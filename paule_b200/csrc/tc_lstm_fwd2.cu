@@ -439,8 +439,8 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
   for (int64_t r0 = 0; r0 < B; r0 += pw) {
     const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
     const int ng = (int)((Bv + gw - 1) / gw);
-    // error flag; exchange blocks of this pass start with the phase bit set (0x4040 per value): never a valid first step
-    PAULE_CUDA(cudaMemsetAsync(xchg, 0, (size_t)kXchgHeader, s));
+    // exchange blocks of this pass start with the phase bit set (0x4040 per value): never a valid first step.  The status
+    // word in the header is NOT cleared here: it starts at zero (zero-filled scratch) and stays set once a watchdog fired.
     PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)ng * 2 * NQ * kLLBlockBytes, s));
     int Ti = (int)T, Bsi = (int)B, w0 = (int)r0, Bvi = Bv, Qtot = (int)((B + kWq - 1) / kWq);
     float* gp = gates + r0 * 4 * kH;

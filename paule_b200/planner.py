@@ -99,6 +99,8 @@ class BatchPlanner:
         ws_bytes = lib.paule_plan_workspace_bytes(B, T, H, C, Cm, S, math)
         # zero-filled ONCE: the pad rows / pad columns of the bf16 operand images inside must be exact zeros
         self.workspace = torch.zeros(ws_bytes, device=dev, dtype=torch.uint8)
+        off = lib.paule_plan_status_offset(B, T, H, C, Cm, S, math)
+        self._status_off = None if off >= ws_bytes else int(off)
         self.target_sv = torch.zeros((B, S), **f32)
         self.hp = dict(lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8, clamp=1.05)
         self.smiling, self.log_semantics = bool(smiling), bool(log_semantics)
@@ -222,8 +224,17 @@ class BatchPlanner:
         self.steps_done += n
 
     # ------------------------------------------------------------------------------------------
+    def check(self) -> None:
+        """Raise if a persistent kernel's watchdog fired (an inter-CTA wait exceeded 4 s: results are invalid).  One 4-byte
+        device->host read; called whenever results leave the planner, never inside the inner loop."""
+        if self._status_off is not None:
+            code = int(self.workspace[self._status_off:self._status_off + 4].view(torch.int32).item())
+            if code != 0:
+                raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")
+
     def planned_cp(self) -> torch.Tensor:
         """current cps, batch-first [B,T,C]."""
+        self.check()
         return ops.transpose_btc(self.cp)
 
     def set_cp(self, cp_bf: torch.Tensor) -> None:
@@ -231,6 +242,7 @@ class BatchPlanner:
 
     def losses(self) -> Dict[str, torch.Tensor]:
         """per-step, per-word loss terms logged BEFORE each update (paule/paule.py:988): tensors [steps,B]."""
+        self.check()
         log = self.loss_log[: self.steps_done]
         return {"total": log[..., 0], "mel": log[..., 1], "semvec": log[..., 2], "velocity": log[..., 3],
                 "jerk": log[..., 4], "local_linear": log[..., 5]}

@@ -348,3 +348,21 @@ def test_paule_plan_resynth_ragged_list(dev, models):
         np.testing.assert_allclose(res.planned_cp[b], solo.planned_cp, atol=1e-5)
     with pytest.raises(ValueError):
         P.BatchPlanner(pred, emb, torch.zeros(2, 40, 30, device=dev), torch.zeros(2, 20, 60, device=dev), None, lengths=[40, 12])
+
+
+def test_watchdog_status_is_checked_when_results_are_read(dev, models):
+    """The persistent kernels never hang the GPU: a stuck inter-CTA wait sets a sticky status word instead.  BatchPlanner reads
+    it whenever results leave the planner and raises -- here the word is poked by hand."""
+    from paule_b200 import BatchPlanner, _lib
+    if not _tc_available():
+        pytest.skip("tcgen05 path not built")
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(2, 40, seed=1)
+    pl = BatchPlanner(pred, emb, cp0.to(dev), tmel.to(dev), None, max_log_steps=4, math=1)
+    pl.step(2)
+    pl.planned_cp(), pl.losses()          # healthy
+    pl.workspace[pl._status_off:pl._status_off + 4].view(torch.int32).fill_(2)
+    with pytest.raises(_lib.PauleB200Error):
+        pl.planned_cp()
+    with pytest.raises(_lib.PauleB200Error):
+        pl.losses()
