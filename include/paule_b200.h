@@ -200,12 +200,19 @@ PAULE_API int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h, 
  * mel).  paule_tc_x_image turns x [T,B,I] into bf16 operand blocks (I <= 32: hi/lo split, so x itself is not rounded);
  * paule_tc_lstm_seq_fwd_x computes a_t = W_hh h_{t-1} + W_ih x_t + bias inside the recurrence (the W_ih slice comes from the
  * same paule_tc_pack_lstm image) -- `gates` is OUTPUT only (the activated-gate stash); replaces the x W_ih^T GEMM of
- * torch.nn.LSTM (paule/models.py:349,441) and its [T,B,4H] round trip through HBM.  x_img must be zero-filled once. */
+ * torch.nn.LSTM (paule/models.py:349,441) and its [T,B,4H] round trip through HBM.  x_img must be zero-filled once.
+ * h may be NULL when h_img_seq is given (the caller only consumes the bf16 images of h). */
 PAULE_API size_t paule_tc_x_image_bytes(int64_t T, int64_t B);
 PAULE_API int paule_tc_x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, paule_stream_t stream);
 PAULE_API int paule_tc_lstm_seq_fwd_x(float* gates, const void* packed, const float* bias, const void* x_img, float* h,
                           float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B, int math, paule_stream_t stream);
 PAULE_API int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* packed,
+                          const float* dh_seq, int dh_mode, const float* dh_last, void* xchg, void* da_img_seq,
+                          int64_t T, int64_t B, int math, paule_stream_t stream);
+
+/* paule_tc_lstm_seq_bwd without the fp32 d(pre-activation) written over `gates`: only the bf16 images (da_img_seq, required),
+ * which is all the tcgen05 dX GEMM consumes. */
+PAULE_API int paule_tc_lstm_seq_bwd_img(float* gates, const float* c, const void* packed,
                           const float* dh_seq, int dh_mode, const float* dh_last, void* xchg, void* da_img_seq,
                           int64_t T, int64_t B, int math, paule_stream_t stream);
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "paule_tc_x_image_bytes": (sz, [i64, i64]),
     "paule_tc_x_image": (C.c_int, [vp, vp, i64, i64, i64, vp]),
     "paule_tc_lstm_seq_fwd_x": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]),
+    "paule_tc_lstm_seq_bwd_img": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, i64, i64, C.c_int, vp]),
     "paule_tc_lstm_seq_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, i64, i64, C.c_int, vp]),
     "paule_plan_status_offset": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
     "paule_plan_workspace_bytes": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),

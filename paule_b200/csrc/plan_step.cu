@@ -101,7 +101,8 @@ int layer_backward(const paule_plan* p, const paule_lstm_layer& L, float* gates,
                    paule_stream_t s) {
   const int64_t B = p->B, H = p->H, I = L.input_size;
   if (tc(p)) {
-    PAULE_TRY(paule_tc_lstm_seq_bwd(gates, c, L.packed, dh_seq, dh_mode, dh_last, w.xchg, w.da_img, steps, B, p->math, s));
+    // only the bf16 dA images are consumed (dX GEMM on tcgen05): the fp32 copy over the stash is not written
+    PAULE_TRY(paule_tc_lstm_seq_bwd_img(gates, c, L.packed, dh_seq, dh_mode, dh_last, w.xchg, w.da_img, steps, B, p->math, s));
     return paule_tc_gemm_img(w.da_img, L.packed_ih_t, nullptr, dx, steps, B, I, 4, accumulate, s);
   }
   PAULE_TRY(paule_lstm_seq_bwd_f32(gates, c, L.w_hh_t, dh_seq, dh_mode, dh_last, w.dc, steps, B, H, s));
@@ -117,7 +118,8 @@ int project_and_recur(const paule_plan* p, const paule_lstm_layer& L, const floa
   static const bool no_fuse = getenv("PAULE_NO_FUSED_X") != nullptr;
   if (tc(p) && I <= 64 && !no_fuse) {
     PAULE_TRY(paule_tc_x_image(x, x_img, steps, B, I, s));
-    return paule_tc_lstm_seq_fwd_x(gates, L.packed, L.bias, x_img, h, c, w.xchg, h_img, steps, B, p->math, s);
+    // nobody reads this layer's fp32 h when it leaves bf16 images (post_linear / the next layer's projection run on them)
+    return paule_tc_lstm_seq_fwd_x(gates, L.packed, L.bias, x_img, h_img ? nullptr : h, c, w.xchg, h_img, steps, B, p->math, s);
   }
   PAULE_TRY(paule_linear_f32(x, L.w_ih, L.bias, gates, steps * B, 4 * H, I, 1, I, 0, 0, 1, 4 * H, 0, 0, s));
   return recur_forward(p, L, steps, gates, h, c, w, h_img, s);

@@ -14,8 +14,28 @@
 #define TRACE_DUMP(base) {}
 #endif
 
+// -DPAULE_TC_TIMELINE: CTA 0 records (event, slot, step, globaltimer) tuples of steps [kTlFirst, kTlFirst + kTlSteps) into the
+// free part of the exchange header (tools/tc_timeline.py prints them as a timeline).  Debug builds only.
+#ifdef PAULE_TC_TIMELINE
+#define TL(ev, slot, step)                                                                                      \
+  {                                                                                                             \
+    if (blockIdx.x == 0 && (step) >= kTlFirst && (step) < kTlFirst + kTlSteps) {                                 \
+      const unsigned int _i = atomicAdd(reinterpret_cast<unsigned int*>(xchg + kXchgTlOff), 1u);                  \
+      if (_i < kTlMax) {                                                                                        \
+        uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + kXchgTlOff + 16) + 2 * (size_t)_i;                     \
+        _o[0] = ((uint64_t)(ev) << 32) | ((uint64_t)(slot) << 16) | (uint64_t)(step);                            \
+        _o[1] = globaltimer_ns();                                                                                \
+      }                                                                                                          \
+    }                                                                                                            \
+  }
+#else
+#define TL(ev, slot, step) {}
+#endif
+
 namespace paule {
 namespace tc {
+constexpr int kTlFirst = 60, kTlSteps = 3, kXchgTlOff = 3072;   // = kXchgTraceOff (1 KB: 62 events)
+constexpr unsigned int kTlMax = 62;
 
 constexpr int kH = 720;                 // hidden size the tensor-core path is built for (paule/paule.py:124,167)
 constexpr int kKPad = 768;              // K padded to 12 k-blocks of 64
@@ -211,7 +231,7 @@ int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xc
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                    void* h_img_seq, int64_t T, int64_t B, cudaStream_t s);
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                  void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s);
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s);
 inline bool use_v1_fwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_FWD_V1") != nullptr; return v; }
 inline bool use_v1_bwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_BWD_V1") != nullptr; return v; }
 

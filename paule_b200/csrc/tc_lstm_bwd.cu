@@ -236,16 +236,32 @@ tc_lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, c
 using namespace paule;
 using namespace paule::tc;
 
+static int seq_bwd(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int math, int keep_da, paule_stream_t stream);
+
 extern "C" int paule_tc_lstm_seq_bwd(float* gates, const float* c, const void* packed, const float* dh_seq,
                                      int dh_mode, const float* dh_last, void* xchg, void* da_img_seq, int64_t T,
                                      int64_t B, int math, paule_stream_t stream) {
+  return seq_bwd(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, math, 1, stream);
+}
+
+// same, but the fp32 d(pre-activation) is NOT written over `gates`: only the bf16 images in da_img_seq (required) are produced
+extern "C" int paule_tc_lstm_seq_bwd_img(float* gates, const float* c, const void* packed, const float* dh_seq,
+                                         int dh_mode, const float* dh_last, void* xchg, void* da_img_seq, int64_t T,
+                                         int64_t B, int math, paule_stream_t stream) {
+  PAULE_REQUIRE(da_img_seq != nullptr);
+  return seq_bwd(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, math, 0, stream);
+}
+
+static int seq_bwd(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int math, int keep_da, paule_stream_t stream) {
   PAULE_REQUIRE(gates && c && packed && xchg && T >= 0 && B > 0);
   PAULE_REQUIRE(dh_mode == 0 || ((dh_mode == 1 || dh_mode == 2) && dh_seq));
   PAULE_REQUIRE(math == PAULE_MATH_BF16);
   if (T == 0) return PAULE_OK;
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(xchg) % 16 == 0);   // bulk copies need 16-byte aligned global addresses
   cudaStream_t s = as_stream(stream);
-  if (!use_v1_bwd()) return lstm_seq_bwd2(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
+  if (!use_v1_bwd()) return lstm_seq_bwd2(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
   static bool attr_set = false;
   const int smem = (int)sizeof(BwdSmem) + 1024;
   if (!attr_set) {

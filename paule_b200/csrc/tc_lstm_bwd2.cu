@@ -88,7 +88,7 @@ template <int NQ>
 __global__ void __launch_bounds__(kB2Threads, 1)
 tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed,
                     const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
-                    uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0) {
+                    uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0, int keep_da) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = Bwd2Smem<NQ>;
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -287,11 +287,13 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
             *reinterpret_cast<uint32_t*>(d + 2 * (size_t)kXchgImageBytes) = *reinterpret_cast<const uint32_t*>(&b_g);
             *reinterpret_cast<uint32_t*>(d + 3 * (size_t)kXchgImageBytes) = *reinterpret_cast<const uint32_t*>(&b_o);
           }
-          float* grow = gates + ((size_t)t * Bs + wp) * (4 * kH);
-          *reinterpret_cast<float2*>(grow + 0 * kH + j) = d_i;
-          *reinterpret_cast<float2*>(grow + 1 * kH + j) = d_f;
-          *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
-          *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
+          if (keep_da) {   // fp32 da_t over the stash; skipped when the caller only consumes the bf16 images (dX on tcgen05)
+            float* grow = gates + ((size_t)t * Bs + wp) * (4 * kH);
+            *reinterpret_cast<float2*>(grow + 0 * kH + j) = d_i;
+            *reinterpret_cast<float2*>(grow + 1 * kH + j) = d_f;
+            *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
+            *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
+          }
         }
         TRACE(6)
       };
@@ -316,7 +318,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 
 template <int NQ>
 int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+                void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
   static bool attr_set = false;
   const int smem = (int)sizeof(Bwd2Smem<NQ>) + 1024;
   if (!attr_set) {
@@ -354,12 +356,12 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
     uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
-                                       (int)r0);
+                                       (int)r0, keep_da);
     if (e != cudaSuccess && coop_ok) {
       cudaGetLastError();
       coop_ok = 0;
       cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0);
+      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0, keep_da);
     }
     PAULE_CUDA(e);
   }
@@ -367,12 +369,12 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
 }
 
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                  void* xchg, void* da_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
   switch (choose_nq(B, kMaxQBwd)) {
-    case 1: return launch_bwd2<1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
-    case 2: return launch_bwd2<2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
-    case 3: return launch_bwd2<3>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
-    default: return launch_bwd2<4>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, s);
+    case 1: return launch_bwd2<1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+    case 2: return launch_bwd2<2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+    case 3: return launch_bwd2<3>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+    default: return launch_bwd2<4>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
   }
 }
 

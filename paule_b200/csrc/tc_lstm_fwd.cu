@@ -282,7 +282,8 @@ extern "C" int paule_tc_x_image(const float* x, void* img, int64_t T, int64_t B,
 extern "C" int paule_tc_lstm_seq_fwd_x(float* gates, const void* packed, const float* bias, const void* x_img, float* h,
                                        float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B, int math,
                                        paule_stream_t stream) {
-  PAULE_REQUIRE(gates && packed && bias && x_img && h && c && xchg && T >= 0 && B > 0);
+  PAULE_REQUIRE(gates && packed && bias && x_img && c && xchg && T >= 0 && B > 0);
+  PAULE_REQUIRE(h != nullptr || h_img_seq != nullptr);   // h may be NULL when only its bf16 images are consumed
   PAULE_REQUIRE(math == PAULE_MATH_BF16);
   if (T == 0) return PAULE_OK;
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(xchg) % 16 == 0 && reinterpret_cast<uintptr_t>(x_img) % 16 == 0);

@@ -191,6 +191,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
         if (rows <= 0) continue;
         uint8_t* bdst = &S.b[s][(size_t)kb * kSW * 128];
         const uint64_t db = make_smem_desc_sw128(smem_u32(bdst));
+        if (kb == 3 && lane == 0) TL(1, s, t)   // loader: slot visit starts
         if (t > 0) {
           // probes: lane p < 16 watches writer warp (CTA p>>3 of the k-block's two, lane group (p>>1)&3, column half p&1): its
           // lane 0 publishes row 8 (p&1) of every quarter, units 32 (p>>3) + 8 ((p>>1)&3) of the k-block; quarters are
@@ -213,6 +214,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           TRACE(1)
           fence_proxy_async_shared();   // generic-proxy shared-memory writes -> async-proxy (tensor core) reads
           __syncwarp();
+          if (kb == 3 && lane == 0) TL(2, s, t)   // loader: k-block fetched
         }
         TRACE(2)
         mbar_wait(&S.acc_free[s], par, err);   // long complete by now: the tile was zeroed a step ago
@@ -237,6 +239,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           umma_commit(&S.mma_done[s]);
         }
         __syncwarp();
+        if (kb == 3 && lane == 0) TL(3, s, t)   // loader: MMAs issued
         TRACE(4)
 #ifdef PAULE_TC_TRACE
         mbar_wait(&S.mma_done[s], par, err);
@@ -300,8 +303,10 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
       for (int s = 0; s < NS; ++s) {
         if (grp * kGW + s * kSW >= Bv) continue;   // empty slot (uniform over the CTA)
         const bool has_acc = FUSED || t > 0;
+        if (tid == 0) TL(10, s, t)   // epilogue: starts waiting for the slot's accumulator
         if (has_acc) {
           mbar_wait(&S.mma_done[s], (uint32_t)((FUSED ? t : t - 1) & 1), err);
+          if (tid == 0) TL(11, s, t)   // epilogue: accumulator complete
           TRACE(0)
           tcgen05_fence_after();
         }
@@ -371,6 +376,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           if (t + 1 < T && pvalid)                      // critical path: the next step's operand
             xchg_store(ll + (size_t)(s * 2 + (t & 1)) * kBlk + ((size_t)((ug >> 1) * kSW + j * kWq + prow) * 64) * 2 + ll_unit,
                        payload | phase_bits(t));
+          if (tid == 0) TL(12, q, t)   // epilogue: quarter published
           TRACE(3)
           // everything below is off the critical path: the next step is already fed
           if (img_seq != nullptr && uvalid && pvalid) {
@@ -389,9 +395,10 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
               grow[3 * kH] = go[k];
               const size_t o = ((size_t)t * Bs + wp) * kH + u;
               c_out[o] = cn[k];
-              h_out[o] = hv[k];
+              if (h_out != nullptr) h_out[o] = hv[k];   // NULL: the caller only consumes the bf16 images of h
             }
           }
+          if (tid == 0) TL(13, q, t)   // epilogue: quarter's stash stores issued
           TRACE(4)
         }
       }
@@ -444,7 +451,7 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
     PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)ng * 2 * NQ * kLLBlockBytes, s));
     int Ti = (int)T, Bsi = (int)B, w0 = (int)r0, Bvi = Bv, Qtot = (int)((B + kWq - 1) / kWq);
     float* gp = gates + r0 * 4 * kH;
-    float* hp = h + r0 * kH;
+    float* hp = h ? h + r0 * kH : nullptr;
     float* cp = c + r0 * kH;
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
     uint8_t* is = reinterpret_cast<uint8_t*>(h_img_seq);
