@@ -11,7 +11,8 @@
 //   pre-packed bf16 image.  Warp-specialised, persistent over output tiles:
 //     warp 0  TMA producer  (4-stage ring of {A 16 KB, B BN x 128 B}, full/empty mbarriers)
 //     warp 1  MMA issuer    (tcgen05.mma M=128, N=BN, K=16; tcgen05.commit frees the stage / publishes the accumulator)
-//     warps 2-5 epilogue    (tcgen05.ld 32 columns at a time, + bias, fp32 rows straight to HBM)
+//     warps 2-5 epilogue    (tcgen05.ld 32 columns at a time, 32 x 32 transpose through shared memory, + bias, fp32 row
+//                           segments of 128 B to HBM)
 //   with two TMEM accumulator buffers (2 x 256 columns) so that the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -47,12 +48,17 @@ __global__ void pack_gemm_b_kernel(const float* __restrict__ W, uint8_t* __restr
   }
 }
 
+constexpr int kStageLd = 36;   // floats per staged row: 32 + 4 (16-byte aligned rows, conflict-free float4 phases)
 struct GemmBars {
   uint64_t full[kGemmStages];
   uint64_t empty[kGemmStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  // epilogue staging, one 32 x 32 tile per warp: a thread owns one accumulator ROW after tcgen05.ld, but rows of C are
+  // N floats apart -- storing from registers makes every warp store touch 32 lines at 16 bytes each (1 TB/s on the K = 720
+  // projection).  Through this transpose every store instruction writes four 128-byte row segments with full sectors.
+  alignas(16) float stage[4][32][kStageLd];
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -158,27 +164,38 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
 #pragma unroll
           for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0.f; }
         }
-        if (valid) {
-          const int n0 = nt * BN + c0;
-          const int lim = (BN - c0 >= 32) ? 32 : 16;
-          if (n0 + lim <= N && (N & 3) == 0) {
+        const int n0 = nt * BN + c0;
+        const int lim = (BN - c0 >= 32) ? 32 : 16;
+        if ((N & 3) == 0) {
+          // ---- coalesced path: own row -> staging, then 8 instructions x (4 rows x 128 B)
+          float* srow = &bars.stage[lg][lane][0];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (i >= lim) break;
-              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              if (bias) { o.x += __ldg(bias + n0 + i); o.y += __ldg(bias + n0 + i + 1); o.z += __ldg(bias + n0 + i + 2); o.w += __ldg(bias + n0 + i + 3); }
-              float4* dst = reinterpret_cast<float4*>(crow + n0 + i);
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          __syncwarp();
+          const int cc = (lane & 7) * 4, n = n0 + cc;
+          const bool col_ok = cc < lim && n < N;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), r2 = lg * 32 + rr;
+            const int t2 = 2 * sp + (r2 >> 6), b2 = grp * kRows + (r2 & 63);
+            if (col_ok && t2 < steps && b2 < B) {
+              float4 o = *reinterpret_cast<const float4*>(&bars.stage[lg][rr][cc]);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              float4* dst = reinterpret_cast<float4*>(C + ((size_t)t2 * B + b2) * N + n);
               if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
               *dst = o;
             }
-          } else {
-            for (int i = 0; i < lim; ++i) {
-              const int n = n0 + i;
-              if (n >= N) break;
-              float o = v[i] + (bias ? __ldg(bias + n) : 0.f);
-              if (accumulate) o += crow[n];
-              crow[n] = o;
-            }
+          }
+          __syncwarp();   // the staging tile is rewritten by the next chunk
+        } else if (valid) {
+          for (int i = 0; i < lim; ++i) {
+            const int n = n0 + i;
+            if (n >= N) break;
+            float o = v[i] + (bias ? __ldg(bias + n) : 0.f);
+            if (accumulate) o += crow[n];
+            crow[n] = o;
           }
         }
       }
@@ -221,7 +238,7 @@ extern "C" int paule_tc_gemm_img(const void* a_img, const void* packed_b, const 
   const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
   const int n_groups = (int)((B + kRows - 1) / kRows), n_pairs = (int)((steps + 1) / 2);
   const int64_t total = (int64_t)n_groups * n_pairs * (np / bn);
-  const int smem = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024;
+  const int smem = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
   static int smem_set = 0;
   if (smem > smem_set) {
     PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
