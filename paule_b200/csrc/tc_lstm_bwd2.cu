@@ -243,6 +243,15 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
       };
       // stage 2 of quarter q: sum the four partials, cell adjoint, publish da_t
       auto finalize_q = [&](int q) {
+        // cell adjoint (oracle: manual_lstm_backward_input).  It is linear in (dh, dc): every factor that only depends on the
+        // stash is computed BEFORE the wait for the partial sums, so that the critical path after the wait is a handful of FMAs:
+        //   do = dh * k_o;  dc' = dc + dh * k_c;  d_i = dc' * k_i;  d_f = dc' * k_f;  d_g = dc' * k_g;  dc <- dc' * s_f
+        const float tc0 = fast_tanh(fminf(fmaxf(ct.x, -15.f), 15.f)), tc1 = fast_tanh(fminf(fmaxf(ct.y, -15.f), 15.f));
+        const float2 k_o = make_float2(tc0 * s_o.x * (1.f - s_o.x), tc1 * s_o.y * (1.f - s_o.y));
+        const float2 k_c = make_float2(s_o.x * (1.f - tc0 * tc0), s_o.y * (1.f - tc1 * tc1));
+        const float2 k_i = make_float2(s_g.x * s_i.x * (1.f - s_i.x), s_g.y * s_i.y * (1.f - s_i.y));
+        const float2 k_f = make_float2(cp.x * s_f.x * (1.f - s_f.x), cp.y * s_f.y * (1.f - s_f.y));
+        const float2 k_g = make_float2(s_i.x * (1.f - s_g.x * s_g.x), s_i.y * (1.f - s_g.y * s_g.y));
         if (it > 0) {
           mbar_wait_cluster(&S.red_full[q], (uint32_t)((it - 1) & 1), err);
           TRACE(4)
@@ -252,16 +261,13 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
             dh.y += S.red[q][s][2 * a + 1][w];
           }
         }
-        // cell adjoint (oracle: manual_lstm_backward_input)
         float2 d_i, d_f, d_g, d_o;
         {
-          const float tc0 = fast_tanh(fminf(fmaxf(ct.x, -15.f), 15.f)), tc1 = fast_tanh(fminf(fmaxf(ct.y, -15.f), 15.f));
-          const float do0 = dh.x * tc0, do1 = dh.y * tc1;
-          const float dc0 = dc[q][0] + dh.x * s_o.x * (1.f - tc0 * tc0), dc1 = dc[q][1] + dh.y * s_o.y * (1.f - tc1 * tc1);
-          d_i = make_float2(dc0 * s_g.x * s_i.x * (1.f - s_i.x), dc1 * s_g.y * s_i.y * (1.f - s_i.y));
-          d_f = make_float2(dc0 * cp.x * s_f.x * (1.f - s_f.x), dc1 * cp.y * s_f.y * (1.f - s_f.y));
-          d_g = make_float2(dc0 * s_i.x * (1.f - s_g.x * s_g.x), dc1 * s_i.y * (1.f - s_g.y * s_g.y));
-          d_o = make_float2(do0 * s_o.x * (1.f - s_o.x), do1 * s_o.y * (1.f - s_o.y));
+          const float dc0 = dc[q][0] + dh.x * k_c.x, dc1 = dc[q][1] + dh.y * k_c.y;
+          d_i = make_float2(dc0 * k_i.x, dc1 * k_i.y);
+          d_f = make_float2(dc0 * k_f.x, dc1 * k_f.y);
+          d_g = make_float2(dc0 * k_g.x, dc1 * k_g.y);
+          d_o = make_float2(dh.x * k_o.x, dh.y * k_o.y);
           dc[q][0] = dc0 * s_f.x;
           dc[q][1] = dc1 * s_f.y;
         }
