@@ -29,6 +29,16 @@ B_PER_GPU, T_FRAMES, HIDDEN = 64, 200, 720
 METRIC, UNIT = "inner planning steps x words per second", "steps*words/s"
 
 
+def synthetic_inputs(B, T, seed=5):
+    """SURVEY 8(d) synthetic workload (the same generator the oracle uses for its checks): cp0 ~ U(-0.5, 0.5) iid [B,T,30]
+    (the well-conditioned regime), target_mel ~ U(0, 1) [B,T//2,60], both drawn in float64 from one seeded generator."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cp0 = torch.rand(B, T, 30, generator=g, dtype=torch.float64) - 0.5
+    tmel = torch.rand(B, T // 2, 60, generator=g, dtype=torch.float64)
+    return cp0.float(), tmel.float()
+
+
 def flops_per_word_step(T):
     """forward + input-gradient backward, weight-gradient FLOPs excluded."""
     return 21.6e6 * T + 0.864e6
@@ -142,7 +152,7 @@ def run_ours(args):
     import torch.distributed as dist
     import paule_b200 as P
     from paule_b200 import _lib, ops
-    from oracle import paule_oracle as O   # only for the synthetic-input generator and the cpu_baseline leg
+    # oracle/ is touched by the cpu_baseline leg only (cpu_reference_run); the GPU arm generates its own inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -161,7 +171,7 @@ def run_ours(args):
     torch.manual_seed(0)
     pred = P.ForwardModel(num_lstm_layers=1, hidden_size=HIDDEN).to(dev)
     emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=HIDDEN).to(dev)
-    cp0, tmel = O.synthetic_inputs(B, T, seed=5 + rank)
+    cp0, tmel = synthetic_inputs(B, T, seed=5 + rank)
     K, W = args.steps, args.warmup
     planner = P.BatchPlanner(pred, emb, cp0.to(dev), tmel.to(dev), None, max_log_steps=W + K + 8, math=math)
 
@@ -233,7 +243,7 @@ def run_ours(args):
     extra = {}
     if rank == 0:
         def timed(Bx, Tx, steps):
-            cpx, tmx = O.synthetic_inputs(Bx, Tx, seed=77)
+            cpx, tmx = synthetic_inputs(Bx, Tx, seed=77)
             pl = P.BatchPlanner(pred, emb, cpx.to(dev), tmx.to(dev), None, max_log_steps=steps + 4, math=math)
             pl.step(3)
             torch.cuda.synchronize()
