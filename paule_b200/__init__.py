@@ -10,7 +10,7 @@ All compute runs in libpaule_b200.so (hand-written sm_100a CUDA behind a C ABI, 
 from . import _lib, ops, models, planner, paule, distributed  # noqa: F401
 from .paule import Paule, PAULE, PlanningResults  # noqa: F401
 from .models import (ForwardModel, EmbeddingModel, InverseModelMelTimeSmoothResidual,  # noqa: F401
-                     InverseModel, MelEmbeddingModel)
+                     InverseModel, MelEmbeddingModel, MelEmbeddingModelMelSmoothResidualUpsampling)
 from .planner import BatchPlanner  # noqa: F401
 
 __version__ = "0.1.0"

@@ -239,5 +239,50 @@ class InverseModelMelTimeSmoothResidual(nn.Module):
 
 
 # names used by BASELINE.json's north_star
+class MelEmbeddingModelMelSmoothResidualUpsampling(nn.Module):
+    """Mel -> semantic-vector embedder with mel-channel smoothing and a post-upsampling layer (reference:
+    paule/models.py:362-409; defined there but not instantiated by ``Paule``, which uses ``EmbeddingModel``).  Forward only;
+    same ``state_dict`` keys as the reference.  Supported: ``mel_smooth_filter_size=3``, Identity ``mel_resid_activation``."""
+
+    def __init__(self, input_size=60, output_size=300, hidden_size=180, num_lstm_layers=4, mel_smooth_layers=3,
+                 mel_smooth_filter_size=3, mel_resid_activation=torch.nn.Identity(), post_activation=torch.nn.LeakyReLU(),
+                 post_upsampling_size=8192):
+        super().__init__()
+        if not isinstance(mel_resid_activation, torch.nn.Identity) or mel_smooth_filter_size != 3:
+            raise NotImplementedError("CUDA path supports mel_smooth_filter_size=3 and the Identity mel_resid_activation")
+        self.mel_resid_activation = mel_resid_activation
+        self.MelBlocks = nn.ModuleList([_MelChannelConv1D(input_size, mel_smooth_filter_size)
+                                        for _ in range(mel_smooth_layers)])
+        self.lstm = nn.LSTM(input_size, hidden_size, num_layers=num_lstm_layers, batch_first=True)
+        self.post_linear = nn.Linear(hidden_size, post_upsampling_size)
+        self.upsampling = nn.Linear(post_upsampling_size, output_size)
+        self.post_activation = post_activation
+        self._pack = _PackedLSTM(self.lstm)
+
+    @torch.no_grad()
+    def forward(self, x, lens, *args):
+        x = _check_input(x, "MelEmbeddingModelMelSmoothResidualUpsampling.forward(x)")
+        lib = _lib.load()
+        st = ops._stream()
+        B, Tm, Cm = x.shape
+        cur = x
+        for blk in self.MelBlocks:                                            # x = x + conv(x), models.py:391-397
+            w, b = blk.packed()
+            nxt = torch.empty_like(cur)
+            _lib.check(lib.paule_melconv_res_f32(cur.data_ptr(), w.data_ptr(), b.data_ptr(), nxt.data_ptr(), B, Tm, Cm,
+                                                 st), "paule_melconv_res_f32")
+            cur = nxt
+        h = lstm_stack(cur, self._pack.get())                                  # [T,B,H]
+        idx = torch.as_tensor([int(l) - 1 for l in lens], device=x.device, dtype=torch.long)
+        if idx.numel() != B:
+            raise ValueError(f"lens has {idx.numel()} entries for a batch of {B}")
+        last = h[idx, torch.arange(B, device=x.device)].contiguous().unsqueeze(0)      # models.py:403
+        z = ops.linear_tm(last, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias), False, False)
+        z = self.post_activation(z)
+        return ops.linear_tm(z.contiguous(), _f32c(self.upsampling.weight), _f32c(self.upsampling.bias), False, False)[0]
+
+
 InverseModel = InverseModelMelTimeSmoothResidual
+# BASELINE.json's north_star says "MelEmbeddingModel" for the mel-to-embedding model of the planning loop, which in the reference
+# is EmbeddingModel (paule/paule.py:167); the class the reference calls MelEmbeddingModel... is available under its own name.
 MelEmbeddingModel = EmbeddingModel

@@ -236,3 +236,16 @@ def test_cpu_tensors_are_rejected(dev):
     pred = P.ForwardModel(num_lstm_layers=1, hidden_size=32)
     with pytest.raises(_lib.PauleB200Error):
         pred(torch.zeros(1, 20, 30))
+
+
+def test_mel_embedding_model_matches_reference_golden(dev):
+    """MelEmbeddingModelMelSmoothResidualUpsampling forward (mel-channel residual convs -> LSTM stack -> h at lens-1 ->
+    post_linear -> LeakyReLU -> upsampling) against the reference's own output on the same seeded weights, ragged lens."""
+    import os
+    import paule_b200 as P
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mel_embedder_golden.npz"))
+    torch.manual_seed(7)
+    m = P.MelEmbeddingModelMelSmoothResidualUpsampling(hidden_size=96, num_lstm_layers=2, post_upsampling_size=256).to(dev)
+    y = m(torch.from_numpy(g["x"]).to(dev), [int(l) for l in g["lens"]])
+    np.testing.assert_allclose(_np(y), g["y64"], atol=2e-5)
+    np.testing.assert_allclose(_np(y), g["y32"].astype(np.float64), atol=2e-5)

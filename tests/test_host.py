@@ -212,3 +212,19 @@ def test_ragged_sharded_plan_equals_words_planned_alone_gloo_world2():
             solo.step(3)
             np.testing.assert_array_equal(planned[b], solo.planned_cp()[0].numpy())
             np.testing.assert_allclose(loss[:, b], torch.stack(solo.log)[:, 0].numpy(), rtol=1e-6)
+
+
+def test_mel_embedding_model_state_dict_matches_reference_keys():
+    """MelEmbeddingModelMelSmoothResidualUpsampling (paule/models.py:362-409): same parameter names and seeded init as the
+    reference (golden generated by tests/golden/make_mel_embedder_golden.py from the reference class)."""
+    import hashlib
+    import paule_b200 as P
+    g = np.load(os.path.join(REPO, "tests", "golden", "mel_embedder_golden.npz"))
+    torch.manual_seed(7)
+    m = P.MelEmbeddingModelMelSmoothResidualUpsampling(hidden_size=96, num_lstm_layers=2, post_upsampling_size=256)
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == list(g["keys"])
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode()); h.update(sd[k].detach().cpu().float().numpy().tobytes())
+    assert h.hexdigest() == str(g["digest"])
