@@ -234,10 +234,10 @@ def _full_size_check(dev, pred, emb, cp0, tmel, n_steps, math, probe):
 
 @pytest.mark.parametrize("math", math_params())
 def test_full_size_properties_cfg2(dev, models, math):
-    """BASELINE config 2: B=64 words, 0.5 s utterances (T=200)."""
+    """BASELINE config 2 exactly: B=64 words, 0.5 s utterances (T=200), 50 inner steps; word 7 against the oracle over all 50."""
     pred, emb, _ = models
     cp0, tmel = O.synthetic_inputs(64, 200, seed=5)
-    _full_size_check(dev, pred, emb, cp0, tmel, 10, math, probe=7)
+    _full_size_check(dev, pred, emb, cp0, tmel, 50, math, probe=7)
 
 
 @pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
