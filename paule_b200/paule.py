@@ -100,6 +100,38 @@ class Paule():
         self.best_synthesis_semantic = None
         self.last_planner: Optional[BatchPlanner] = None
 
+    # ---- host-side synthesis pipeline (reference: speak() + librosa_melspec() + normalize, paule.py:1097-1113)
+    def _submit_synthesis(self, cps_np):
+        """One synthesis job per word on a thread pool (VocalTractLab runs behind ctypes and releases the GIL).  Returns the
+        futures; the GPU keeps planning while they run."""
+        import concurrent.futures
+        import os
+        if getattr(self, "_synth_pool", None) is None:
+            self._synth_pool = concurrent.futures.ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1))
+        return [self._synth_pool.submit(self.synthesizer, c) for c in cps_np]
+
+    @staticmethod
+    def _synthesis_result(fut):
+        """synthesizer may return the normalised log-mel [Tm,60] or (sig, sr, mel)."""
+        r = fut.result()
+        if isinstance(r, tuple) and len(r) == 3:
+            return r[0], r[1], np.asarray(r[2], dtype=np.float32)
+        return None, None, np.asarray(r, dtype=np.float32)
+
+    def _produced_metrics(self, prod_mels, target_mels, target_semvec):
+        """prod_loss = 5 rmse(prod_mel, target_mel) (paule.py:1109-1111), prod_semvec = embedder(prod_mel),
+        prod_semvec_loss = 10 rmse(prod_semvec, target_semvec) (:1139-1146), per word.  Tiny, runs on the GPU with torch ops."""
+        B = len(prod_mels)
+        lens = [int(m.shape[0]) for m in prod_mels]
+        pad = torch.zeros((B, max(lens), prod_mels[0].shape[1]), device=self.device)
+        for b, m in enumerate(prod_mels):
+            pad[b, :lens[b]] = torch.from_numpy(m).to(self.device)
+        mel_loss = torch.stack([5.0 * torch.sqrt(torch.mean((pad[b, :lens[b]] - target_mels[b][:lens[b]]) ** 2)) for b in range(B)])
+        with torch.no_grad():
+            sv = self.embedder(pad, lens)
+        sem_loss = 10.0 * torch.sqrt(torch.mean((sv - target_semvec) ** 2, dim=1))
+        return mel_loss.cpu().numpy(), sv.cpu().numpy(), sem_loss.cpu().numpy()
+
     def continue_learning_pred(self, cps, mels, *, n_epochs=10, batch_size=8, shuffle=True):
         """Continue-learning of the predictive forward model on (cp, produced mel) pairs: the learning step of the outer
         loop (paule/paule.py:1361-1377) -- same-size batching (create_epoch_batches(same_size_batching=True), :349-369),
@@ -328,6 +360,18 @@ class Paule():
         # initial predictions (paule.py:822-824)
         initial_pred_mel, initial_pred_semvec = planner.forward()
 
+        def word_cps():
+            cur = planner.planned_cp().detach().cpu().numpy()
+            return [cur[b, :L] for b, L in enumerate(lengths)] if lengths is not None else [cur[b] for b in range(cur.shape[0])]
+
+        # produced side (paule.py:826-870, :1097-1164): synthesised on the host at the outer-loop boundaries, overlapped with
+        # the GPU's next outer iteration; pending = [(outer index or -1 for the initial cps, cps, futures)]
+        synth = self.synthesizer is not None
+        pending, produced = [], []
+        if synth:
+            cps_init = word_cps()
+            pending.append((-1, cps_init, self._submit_synthesis(cps_init)))
+
         cp_steps, grad_steps, pred_semvec_steps, pred_mel_steps = [], [], [], []
         pred_model_loss = []
         need_per_step = log_cps or log_gradients
@@ -348,13 +392,11 @@ class Paule():
             # continue-learning (paule.py:1243-1454): the planned cps of this outer iteration are synthesised on the host
             # (VocalTractLab + librosa behind `synthesizer`), the produced mels train pred_model, the planner is repacked.
             # Without a synthesizer the models stay frozen (the reference needs VocalTractLab here).
-            if continue_learning and self.synthesizer is not None:
-                cur = planner.planned_cp().detach().cpu().numpy()
-                if lengths is not None:
-                    cur_list = [cur[b, :L] for b, L in enumerate(lengths)]
-                else:
-                    cur_list = [cur[b] for b in range(cur.shape[0])]
-                prod = [np.asarray(self.synthesizer(c), dtype=np.float32) for c in cur_list]
+            if synth:
+                cur_list = word_cps()
+                pending.append((ii_outer, cur_list, self._submit_synthesis(cur_list)))   # runs while the GPU plans on
+            if continue_learning and synth:
+                prod = [self._synthesis_result(f)[2] for f in pending[-1][2]]         # the learning step needs them now
                 train_cps, train_mels = list(cur_list), list(prod)
                 if add_training_data_pred and self.continue_data is not None and len(self.continue_data) > 0:
                     k = min(len(self.continue_data), len(cur_list))      # 50 % known data, 50 % produced (:1256-1268)
@@ -367,6 +409,38 @@ class Paule():
         # final predictions (paule.py:1456-1470)
         planned_cp = planner.planned_cp()
         pred_mel, pred_semvec = planner.forward()
+
+        # collect the produced side: losses and semvecs per synthesis, best synthesis per word (:1158-1164)
+        prod_loss_steps, prod_semvec_loss_steps, prod_mel_steps, prod_semvec_steps, sig_steps = [], [], [], [], []
+        initial_prod_mel = initial_prod_semvec = prod_mel_out = prod_semvec_out = prod_sig = prod_sr = None
+        if synth:
+            tm = planner.target_mel.transpose(0, 1)                      # [B,Tm,60]
+            t_mels = [tm[b] for b in range(B)]
+            for idx, cps_k, futs in pending:
+                res = [self._synthesis_result(f) for f in futs]
+                mels_k = [r[2] for r in res]
+                mel_loss, sv, sem_loss = self._produced_metrics(mels_k, t_mels, planner.target_sv)
+                wrap = (lambda v: v) if batched else (lambda v: v[0])
+                if idx < 0:
+                    initial_prod_mel, initial_prod_semvec = wrap(mels_k), wrap(sv)
+                    continue
+                prod_loss_steps.append(wrap(mel_loss)); prod_semvec_loss_steps.append(wrap(sem_loss))
+                prod_mel_steps.append(wrap(mels_k)); prod_semvec_steps.append(wrap(sv))
+                if log_signals:
+                    sig_steps.append(wrap([r[0] for r in res]))
+                prod_mel_out, prod_semvec_out = wrap(mels_k), wrap(sv)
+                prod_sig, prod_sr = wrap([r[0] for r in res]), res[0][1]
+                for b in range(B):      # best synthesis so far, per word
+                    if self.best_synthesis_acoustic is None:
+                        self.best_synthesis_acoustic = [None] * B
+                        self.best_synthesis_semantic = [None] * B
+                    if len(self.best_synthesis_acoustic) != B:
+                        self.best_synthesis_acoustic, self.best_synthesis_semantic = [None] * B, [None] * B
+                    ba, bs = self.best_synthesis_acoustic[b], self.best_synthesis_semantic[b]
+                    if ba is None or ba.mel_loss > float(mel_loss[b]):
+                        self.best_synthesis_acoustic[b] = BestSynthesisAcoustic(float(mel_loss[b]), cps_k[b], res[b][0], mels_k[b], None)
+                    if bs is None or bs.semvec_loss > float(sem_loss[b]):
+                        self.best_synthesis_semantic[b] = BestSynthesisSemantic(float(sem_loss[b]), cps_k[b], res[b][0], sv[b], None)
         logs = {k: v.detach().cpu().numpy() for k, v in planner.losses().items()}   # ONE device->host copy
 
         def per_step(name):
@@ -375,12 +449,13 @@ class Paule():
 
         sem_logged = objective in ('acoustic_semvec', 'semvec') or log_semantics
         return PlanningResults(
-            out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None, None, None,
-            out(initial_pred_mel),
-            None, None, out(target_mel), None, None, None, out(pred_mel), None, out(initial_pred_semvec), None,
-            out(pred_semvec), list(), per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
-            per_step("semvec") if sem_logged else list(), list(), cp_steps, pred_semvec_steps, list(), grad_steps,
-            list(), list(), pred_mel_steps, pred_model_loss, list())
+            out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None, None,
+            initial_prod_mel, out(initial_pred_mel),
+            None, None, out(target_mel), prod_sig, prod_sr, prod_mel_out, out(pred_mel), initial_prod_semvec,
+            out(initial_pred_semvec), prod_semvec_out,
+            out(pred_semvec), prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
+            per_step("semvec") if sem_logged else list(), prod_semvec_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps,
+            grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, list())
 
 
 # BASELINE.json's north_star spells the class name in capitals

@@ -127,3 +127,47 @@ def test_plan_resynth_outer_loop_learns_and_repacks(dev, math):
     with torch.no_grad():
         direct = pred(torch.from_numpy(res.planned_cp).to(dev)).cpu().numpy()
     np.testing.assert_allclose(res.pred_mel, direct, atol=1e-5 if math == 0 else 5e-3)
+
+
+def test_host_synthesis_pipeline_fills_the_produced_fields(dev):
+    """with a host-side synthesizer the planned cps are synthesised at every outer-loop boundary on a thread
+    pool (overlapped with the GPU's next outer iteration) and PlanningResults carries the produced side: prod_mel,
+    prod_semvec, 5 rmse / 10 rmse losses per synthesis (paule.py:1109-1111, :1139-1146), best synthesis per word (:1158-1164)."""
+    import threading
+    import time
+    import paule_b200 as P
+    torch.manual_seed(0)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=720)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=720)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=720)
+    proj = np.random.RandomState(1).randn(30, 60).astype(np.float32) * 0.2
+    threads = set()
+
+    def synth(cp):
+        threads.add(threading.get_ident())
+        time.sleep(0.02)                                   # a (very fast) VocalTractLab
+        pooled = 0.5 * (cp[0::2][: cp.shape[0] // 2] + cp[1::2][: cp.shape[0] // 2])
+        return (np.zeros(8, dtype=np.float32), 44100, np.tanh(pooled @ proj) + 0.5)     # (sig, sr, mel)
+
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, synthesizer=synth)
+    _, tmel = O.synthetic_inputs(5, 40, seed=8)
+    cp0, _ = O.synthetic_inputs(5, 40, seed=9)
+    res = pm.plan_resynth(target_acoustic=tmel.numpy(), initial_cp=cp0.numpy(), initialize_from=None, objective="acoustic_semvec",
+                          n_outer=3, n_inner=2, continue_learning=False, log_signals=True, verbose=False)
+    assert len(threads) > 1, "synthesis jobs must run on the pool, not serially on the caller's thread"
+    assert len(res.prod_loss_steps) == 3 and len(res.prod_semvec_loss_steps) == 3 and len(res.sig_steps) == 3
+    for b in range(5):
+        np.testing.assert_allclose(res.prod_mel[b], synth(res.planned_cp[b])[2], atol=1e-6)
+        np.testing.assert_allclose(res.initial_prod_mel[b], synth(cp0[b].numpy())[2], atol=1e-6)
+        want = 5.0 * np.sqrt(np.mean((res.prod_mel[b] - tmel[b].numpy()) ** 2))
+        np.testing.assert_allclose(res.prod_loss_steps[-1][b], want, rtol=1e-5)
+        assert pm.best_synthesis_acoustic[b].mel_loss == pytest.approx(min(s[b] for s in res.prod_loss_steps), rel=1e-6)
+        assert pm.best_synthesis_semantic[b].semvec_loss == pytest.approx(min(s[b] for s in res.prod_semvec_loss_steps), rel=1e-6)
+    with torch.no_grad():
+        sv = emb(torch.from_numpy(np.stack(res.prod_mel)).to(dev), [20] * 5).cpu().numpy()
+    np.testing.assert_allclose(res.prod_semvec, sv, atol=1e-5)
+    assert res.prod_sr == 44100 and res.pred_model_loss == []
+    # single word: reference-shaped (unbatched) produced fields
+    one = pm.plan_resynth(target_acoustic=tmel[0].numpy(), initial_cp=cp0[0].numpy(), initialize_from=None, objective="acoustic",
+                          n_outer=2, n_inner=2, continue_learning=False, verbose=False)
+    assert one.prod_mel.shape == (20, 60) and one.prod_semvec.shape == (300,) and np.ndim(one.prod_loss_steps[0]) == 0
