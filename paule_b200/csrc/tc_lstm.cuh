@@ -114,6 +114,15 @@ inline int64_t pass_words(int64_t B, int max_groups, int nq) {
   return (per + gw - 1) / gw * gw;
 }
 
+// Probe polling variants, measured at 64 words (forward step 2.42 us with the defaults): two probe loads in flight 2.75 us
+// (more polling traffic slows every exchange), a 40 / 120 ns back-off between failed probes 2.39 / 2.41 us (neutral).
+#ifndef PAULE_PROBE_PIPELINE
+#define PAULE_PROBE_PIPELINE 0
+#endif
+#ifndef PAULE_PROBE_BACKOFF_NS
+#define PAULE_PROBE_BACKOFF_NS 0
+#endif
+
 #ifdef __CUDACC__
 // Weight image of one CTA as tcgen05.st wants it: [48 column octets][128 rows][8 x u32]; u32 column c of row m holds the
 // bf16 pair (k = 2c, 2c+1).  Warp w (lanes 32w..32w+31) copies its rows with one 32-byte load + one x8 store per octet.
@@ -149,9 +158,22 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
     const uint8_t* pp = src + probe_off;
     uint64_t t0 = 0;
     bool ok = !prober;
+#if PAULE_PROBE_PIPELINE
+    // two probe loads in flight: the second is issued before the first is examined, which halves the sampling period
+    uint32_t nxt = ok ? 0u : xchg_load(pp);
+    for (unsigned int spin = 0;; ++spin) {
+      const uint32_t cur = nxt;
+      if (!ok) nxt = xchg_load(pp);
+      if (!ok) ok = (cur & kPhaseMask) == phase;
+      if (__all_sync(0xffffffffu, ok)) break;
+#else
     for (unsigned int spin = 0;; ++spin) {
       if (!ok) ok = (xchg_load(pp) & kPhaseMask) == phase;
       if (__all_sync(0xffffffffu, ok)) break;
+#if PAULE_PROBE_BACKOFF_NS > 0
+      __nanosleep(PAULE_PROBE_BACKOFF_NS);   // fewer polls in flight -> shorter L2 queues for the loads that matter
+#endif
+#endif
       if ((spin & 1023u) == 1023u) {
         if (t0 == 0) t0 = globaltimer_ns();
         if (*err != 0) return false;
