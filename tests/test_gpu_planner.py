@@ -366,3 +366,26 @@ def test_watchdog_status_is_checked_when_results_are_read(dev, models):
         pl.planned_cp()
     with pytest.raises(_lib.PauleB200Error):
         pl.losses()
+
+
+@pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
+@pytest.mark.parametrize("B,T,steps", [(64, 200, 300), (100, 60, 150), (1, 200, 200), (200, 40, 100)])
+def test_soak_many_steps_no_watchdog_and_repeatable(dev, models, B, T, steps):
+    """Soak of the exchange protocol of the persistent kernels (latency layout, 2- and 3-quarter CTAs, multi-pass): hundreds
+    of steps = 10^5 .. 10^6 inter-CTA exchanges per run; the watchdog word must stay clear, the loss finite and falling, and
+    two runs of the same job must agree up to the bf16 rounding flips of the arrival-ordered accumulation."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    cp0, tmel = O.synthetic_inputs(B, T, seed=123)
+    outs = []
+    for _ in range(2):
+        pl = BatchPlanner(pred, emb, cp0.to(dev), tmel.to(dev), None, max_log_steps=steps, math=1)
+        pl.step(steps)
+        pl.check()
+        L = pl.losses()["total"]
+        assert torch.isfinite(L).all()
+        assert (L[-1] < L[0]).all() and (L[10:].mean(1)[1:] <= L[10:].mean(1)[:-1] * 1.001).all()
+        outs.append((pl.planned_cp().clone(), L.clone()))
+        pl.close()
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 2e-3
+    np.testing.assert_allclose(_np(outs[0][1][-1]), _np(outs[1][1][-1]), rtol=1e-3)
