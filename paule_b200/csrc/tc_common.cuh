@@ -118,33 +118,6 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// issue-only variant: several loads can be in flight before one tmem_ld_wait()
-__device__ __forceinline__ void tmem_ld_x16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// 32 lanes x 32 bit, 4 consecutive columns
-__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
-  uint32_t r[4];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_zero_x4(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
-}
-
 // 32 lanes x 32 bit, 8 consecutive columns
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -176,26 +149,6 @@ __device__ __forceinline__ void tmem_zero_x16(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// sum of kTiles accumulator tiles (32 columns apart), 16 columns each, loads batched four at a time
-template <int kTiles>
-__device__ __forceinline__ void tmem_ld_sum_x16(uint32_t taddr, float (&acc)[16]) {
-  static_assert(kTiles % 4 == 0 || kTiles == 1 || kTiles == 2, "tile count");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  constexpr int kBatch = kTiles >= 4 ? 4 : kTiles;
-#pragma unroll
-  for (int b = 0; b < kTiles; b += kBatch) {
-    uint32_t r[kBatch][16];
-#pragma unroll
-    for (int m = 0; m < kBatch; ++m) tmem_ld_x16_issue(taddr + (uint32_t)((b + m) * 32), r[m]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int m = 0; m < kBatch; ++m)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[m][i]);
-  }
-}
 
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -269,24 +222,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// multicast variant: the same bytes land at the same shared-memory offset of every CTA in `cta_mask` of the cluster,
-// and complete_tx is signalled on the mbarrier at the same offset in each of them (one L2 read feeds all).
-__device__ __forceinline__ void bulk_g2s_mcast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank_u32() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
-}
-__device__ __forceinline__ void cluster_barrier_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Orders this thread's generic-proxy view of GLOBAL memory (the acquire that observed the producers' release) before
