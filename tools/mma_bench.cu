@@ -13,21 +13,6 @@
 
 using namespace paule::tc;
 
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-
 struct Smem {
   uint8_t a[12][128 * 128];   // A k-blocks [128 rows][128 B] (192 KB)
   uint8_t b[64 * 128];        // one B k-block, up to 64 rows (8 KB)
@@ -74,7 +59,8 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(const __nv_bfloat16* __re
           const __nv_bfloat16 lo = m < M ? A[m * 64 + k] : __float2bfloat16(0.f), hi = m < M ? A[m * 64 + k + 1] : __float2bfloat16(0.f);
           r[i] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
         }
-        tmem_st_x8(tmem + ((uint32_t)(warp * 32) << 16) + 128 + kb * 32 + c0, r);
+        tmem_st_x8(tmem + ((uint32_t)(warp * 32) << 16) + 128 + kb * 32 + c0, make_uint4(r[0], r[1], r[2], r[3]),
+                   make_uint4(r[4], r[5], r[6], r[7]));
       }
     tmem_st_wait();
   }
