@@ -139,6 +139,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         uint8_t* bdst = &S.b[q][(size_t)kb * kWq * 128];
         const uint64_t db = make_smem_desc_sw128(smem_u32(bdst));
         const uint8_t* src = ll + (size_t)((q * 2 + ((it - 1) & 1)) * 4 + g) * kLLBlockBytes + (size_t)kb * (kWq * 128);
+        if (kb == 3 && lane == 0) TL(1, q, it)   // loader: quarter visit starts
 #ifdef PAULE_TC_TRACE
         uint64_t ftr[2] = {0, 0};
         if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr)) break;
@@ -150,6 +151,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 #endif
         fence_proxy_async_shared();
         __syncwarp();
+        if (kb == 3 && lane == 0) TL(2, q, it)   // loader: k-block fetched
         mbar_wait(&S.acc_free[q], (uint32_t)((it - 1) & 1), err);
         tcgen05_fence_after();
         TRACE(2)
@@ -159,6 +161,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           umma_commit(&S.mma_done[q]);
         }
         __syncwarp();
+        if (kb == 3 && lane == 0) TL(3, q, it)   // loader: MMAs issued
         TRACE(3)
 #ifdef PAULE_TC_TRACE
         mbar_wait(&S.mma_done[q], (uint32_t)((it - 1) & 1), err);
@@ -225,7 +228,9 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         float p[8];
         if (tid == 0) mbar_arrive_expect_tx(&S.red_full[q], kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
         TRACE(0)
+        if (tid == 0) TL(10, q, it)   // epilogue: starts waiting for the accumulator
         mbar_wait(&S.mma_done[q], (uint32_t)((it - 1) & 1), err);
+        if (tid == 0) TL(11, q, it)   // epilogue: accumulator complete
         TRACE(1)
         tcgen05_fence_after();
         tmem_ld_x8(taddr + (uint32_t)(q * kWq), p);
@@ -239,6 +244,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         st_async_v4(red_dst + (uint32_t)(q * 4 * 32 * kRedStride * 4) + 16, p[4], p[5], p[6], p[7], bar_dst + (uint32_t)(q * 8));
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.acc_free[q]);
+        if (tid == 0) TL(14, q, it)   // epilogue: partial sums pushed
         TRACE(3)
       };
       // stage 2 of quarter q: sum the four partials, cell adjoint, publish da_t
@@ -254,6 +260,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         const float2 k_g = make_float2(s_i.x * (1.f - s_g.x * s_g.x), s_i.y * (1.f - s_g.y * s_g.y));
         if (it > 0) {
           mbar_wait_cluster(&S.red_full[q], (uint32_t)((it - 1) & 1), err);
+          if (tid == 0) TL(15, q, it)   // epilogue: partial sums of all four siblings arrived
           TRACE(4)
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
@@ -281,6 +288,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
           xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
         }
+        if (tid == 0) TL(12, q, it)   // epilogue: quarter published
         TRACE(5)
         if (jvalid && wvalid) {   // off the critical path: bf16 images (A operand of the dX GEMM) and fp32 da_t over the stash
           if (img_seq != nullptr) {
@@ -301,6 +309,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
             *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
           }
         }
+        if (tid == 0) TL(13, q, it)   // epilogue: image / stash stores issued
         TRACE(6)
       };
       // software pipeline over the quarters: quarter q's push overlaps quarter q-1's wait for its partial sums
