@@ -271,9 +271,12 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_val, cpu_s, cores = cpu_reference_run(16, 3, 1)
+            one_val, one_s, _ = cpu_reference_run(1, 3, 1)      # how the reference is used: one word per call
             cpu = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "16 of the 64 words x 3 inner steps (1 warm-up), T=200, torch CPU fp32 oracle port "
-                             "(nn.LSTM/oneDNN + autograd + optim.Adam)"}
+                             "(nn.LSTM/oneDNN + autograd + optim.Adam), batched with per-word losses (the stronger baseline)",
+                   "batch1": {"value": one_val, "ms_per_inner_step": one_s * 1e3,
+                              "sample": "1 word x 3 inner steps: the reference plans one word per call (paule/paule.py:539)"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
