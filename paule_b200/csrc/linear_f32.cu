@@ -171,41 +171,56 @@ linear_skinny_f32_kernel(const float* __restrict__ A, const float* __restrict__ 
   }
 }
 
-// Few-row projection (M <= 64 rows, e.g. the heads: one row per word): a CTA owns 8 output columns, keeps their weight
-// rows in shared memory and gives every warp a share of the rows; a row's dot products are split over the lanes along K
-// (coalesced reads of x) and reduced with shuffles.  The generic tile kernel needs 45 dependent load/sync rounds here.
+// Few-row projection (M <= 64 rows, e.g. the heads: one row per word): a CTA owns 8 output columns x 8 rows, keeps the
+// weight rows in shared memory and gives every warp ONE row; the row's dot products are split over the lanes along K
+// (coalesced, unrolled reads of x) and reduced with shuffles.  grid = (N / 8, M / 8): a single wave of short CTAs -- the
+// generic tile kernel needs 45 dependent load/sync rounds on 5 CTAs here.
 __global__ void __launch_bounds__(256)
 linear_fewrows_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                           float* __restrict__ C, int M, int64_t N, int K, int accumulate) {
   extern __shared__ __align__(16) float fr_smem[];   // [8][K]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n0 = (int64_t)blockIdx.x * 8;
+  const int m = blockIdx.y * 8 + warp;
+  // this warp's row of x: issued before the weight tile so that both loads overlap
+  const float* arow = A + (size_t)(m < M ? m : 0) * K;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (m < M && lane + 32 * i < K) ? __ldg(arow + lane + 32 * i) : 0.f;
   for (int e = tid; e < 8 * K; e += 256) {
     const int j = e / K, kk = e - j * K;
     fr_smem[e] = (n0 + j < N) ? __ldg(W + (n0 + j) * K + kk) : 0.f;
   }
   __syncthreads();
-  for (int m = warp; m < M; m += 8) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* arow = A + (size_t)m * K;
-    for (int kk = lane; kk < K; kk += 32) {
-      const float a = __ldg(arow + kk);
+  if (m >= M) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 256) {   // 8 x 32 elements of the row per round, prefetched one round ahead
+    float an[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, fr_smem[j * K + kk], acc[j]);
+    for (int i = 0; i < 8; ++i) an[i] = (k0 + 256 + lane + 32 * i < K) ? __ldg(arow + k0 + 256 + lane + 32 * i) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kk = k0 + lane + 32 * i;
+      if (kk < K) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[i], fr_smem[j * K + kk], acc[j]);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int i = 0; i < 8; ++i) a[i] = an[i];
+  }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    if (lane < 8 && n0 + lane < N) {
-      float v = 0.f;
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v = (lane == j) ? acc[j] : v;
-      v += bias ? __ldg(bias + n0 + lane) : 0.f;
-      float* dst = C + (size_t)m * N + n0 + lane;
-      if (accumulate) v += *dst;
-      *dst = v;
-    }
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (lane < 8 && n0 + lane < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v = (lane == j) ? acc[j] : v;
+    v += bias ? __ldg(bias + n0 + lane) : 0.f;
+    float* dst = C + (size_t)m * N + n0 + lane;
+    if (accumulate) v += *dst;
+    *dst = v;
   }
 }
 
@@ -242,8 +257,8 @@ extern "C" int paule_linear_f32(const float* A, const float* W, const float* bia
       PAULE_CUDA(cudaFuncSetAttribute(linear_fewrows_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4));
       attr_set = true;
     }
-    linear_fewrows_f32_kernel<<<(unsigned)ceil_div(N, 8), 256, smem, as_stream(stream)>>>(A, W, bias, C, (int)M, N, (int)K,
-                                                                                          accumulate);
+    linear_fewrows_f32_kernel<<<dim3((unsigned)ceil_div(N, 8), (unsigned)ceil_div(M, 8)), 256, smem, as_stream(stream)>>>(
+        A, W, bias, C, (int)M, N, (int)K, accumulate);
   } else if (plain && K <= 64 && M >= 256 && N >= 64) {
     const size_t smem = (size_t)K * (kSkM + kSkPad + kSkN + kSkPad) * sizeof(float);
     static bool attr_set = false;
