@@ -18,156 +18,173 @@ constexpr int kTileT = 64;   // output frames per CTA of the smoothness kernel
 constexpr int kHalo = 12;    // three nested 5-point stencils reach 6 frames, their adjoints another 6
 constexpr int kMaxC = 32;    // channels (30 in PAULE)
 
-// d5(v)[i] = (-v[i+4] + 8 v[i+3] - 8 v[i+1] + v[i]) / 12   -- same operation order as util.py:600, no FMA
-// contraction so that the value matches the reference's separately rounded tensor ops.
+// d5(v)[i] = (-v[i+4] + 8 v[i+3] - 8 v[i+1] + v[i]) / 12   -- same operation order as util.py:600, no FMA contraction of the
+// sum so that it matches the reference's separately rounded tensor ops.  The division by the constant 12 is a multiply
+// by RN(1/12) followed by one FMA residual correction (q + (s - 12 q) r): the correctly rounded quotient except for
+// measure-zero corner cases, in 3 instructions -- __fdiv_rn is ~35 and made this kernel instruction-bound (223 M warp
+// instructions at 1024 words x 400 frames).
+__device__ __forceinline__ float div12(float s) {
+  constexpr float r = 1.0f / 12.0f;
+  const float q = __fmul_rn(s, r);
+  return __fmaf_rn(__fmaf_rn(-12.0f, q, s), r, q);
+}
 __device__ __forceinline__ float d5(float v0, float v1, float v3, float v4) {
   float s = __fadd_rn(-v4, __fmul_rn(8.0f, v3));
   s = __fsub_rn(s, __fmul_rn(8.0f, v1));
   s = __fadd_rn(s, v0);
-  return __fdiv_rn(s, 12.0f);
+  return div12(s);
 }
 
 // Smoothness terms of one (word, time tile): vel/jerk/local-linear partial sums and their gradient.
-// Buffers in shared memory hold frames [t0-12, t0+kTileT+12) of the word, all C channels.
 //   x -> vel (valid: T-4) -> acc (T-8) -> jerk (T-12);  r3 = s_j*jerk; r2 = D^T r3; r1 = D^T r2 + s_v*vel; g = D^T r1 + ll part
-// CT: compile-time channel count (30 in PAULE: the e / C, e % C index splits become multiply-shift), 0 = runtime C.
-template <int CT>
+// Shared-memory tiles hold frames [t0-12, t0+kTileT+12) of the word as [88 frames][32 channel slots].  Thread = (channel =
+// lane, run of 11 consecutive frames = warp): every stage pulls its run plus a 4-frame apron into registers (15 shared
+// loads for 11 results, conflict-free: a warp reads one 128-byte row per load) and writes 11 results back -- no index
+// division, the nested stencils keep the reference's stage-by-stage rounding (d5 of d5 of d5, util.py:634-636).
+constexpr int kSmW = kTileT + 2 * kHalo;   // 88 frames
+constexpr int kRun = kSmW / 8;             // 11 frames per warp
+static_assert(kRun * 8 == kSmW, "the frame window splits evenly over the 8 warps");
+
 __global__ void __launch_bounds__(256)
 smooth_terms_kernel(const float* __restrict__ cp, float* __restrict__ dcp_smooth, float* __restrict__ partial,
-                    int64_t Tmax, const int32_t* __restrict__ word_T, int64_t B, int64_t C_rt, int n_tiles) {
-  const int C = CT ? CT : C_rt;
-  constexpr int W = kTileT + 2 * kHalo;  // 88 frames
-  __shared__ float sx[W * kMaxC];
-  __shared__ float sa[W * kMaxC];
-  __shared__ float sb[W * kMaxC];
+                    int64_t Tmax, const int32_t* __restrict__ word_T, int64_t B, int64_t C, int n_tiles) {
+  __shared__ float sx[kSmW * 32];   // x
+  __shared__ float sv[kSmW * 32];   // vel
+  __shared__ float s1[kSmW * 32];   // acc, later r2
+  __shared__ float s2[kSmW * 32];   // r3, later r1
   __shared__ float sred[3][8];
   const int64_t b = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * kTileT;
-  const int tid = threadIdx.x;
-  const int n = W * C;
+  const int tid = threadIdx.x, c = tid & 31, wq = tid >> 5;
+  const int f0 = wq * kRun;                      // first frame of this thread's run inside the window
+  const int64_t i0 = t0 - kHalo + f0;            // ... and its global frame index
+  const bool cl = c < (int)C;
   // ragged batches: word b has T frames; frames [T, Tmax) are padding and get a zero gradient
   const int64_t T = word_T ? (int64_t)word_T[b] : Tmax;
-  const float sv = 2.0f * kVelWeight / (float)((T - 4) * C);
-  const float sj = 2.0f * kJerkWeight / (float)((T - 12) * C);
-  const float sl = 2.0f * kLocalLinearWeight / (float)((T - 2) * C);
+  const float kv = 2.0f * kVelWeight / (float)((T - 4) * C);
+  const float kj = 2.0f * kJerkWeight / (float)((T - 12) * C);
+  const float kl = 2.0f * kLocalLinearWeight / (float)((T - 2) * C);
+  auto own = [&](int f) { return f >= kHalo && f < kHalo + kTileT; };   // frames this CTA sums over and writes
 
-  // frame index f in [0,W) <-> global t = t0 - kHalo + f
-  for (int e = tid; e < n; e += 256) {
-    const int f = e / C, c = e % C;
-    const int64_t t = t0 - kHalo + f;
-    sx[e] = (t >= 0 && t < T) ? __ldg(cp + (t * B + b) * C + c) : 0.f;
-  }
-  __syncthreads();
-  // vel[i] uses x[i..i+4], i in [0, T-4): stored at frame of global index i  -> sa
-  for (int e = tid; e < n; e += 256) {
-    const int f = e / C, c = e % C;
-    const int64_t i = t0 - kHalo + f;
-    float v = 0.f;
-    if (i >= 0 && i < T - 4 && f + 4 < W)
-      v = d5(sx[e], sx[e + C], sx[e + 3 * C], sx[e + 4 * C]);
-    sa[e] = v;
-  }
-  __syncthreads();
-  // local partial sums of vel^2 and ll^2 over the frames this CTA owns
-  float pv = 0.f, pj = 0.f, pl = 0.f;
-  for (int e = tid; e < kTileT * C; e += 256) {
-    const int f = kHalo + e / C, c = e % C;
-    const int64_t i = t0 + e / C;
-    const int idx = f * C + c;
-    if (i < T - 4) pv += sa[idx] * sa[idx];
-    if (i >= 1 && i < T - 1) {
-      // ll[i-1] = (2 x[i] - x[i-1] - x[i+1]) / 2   (util.py:614)
-      const float l = __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[idx]), sx[idx - C]), sx[idx + C]), 2.0f);
-      pl += l * l;
-    }
-  }
-  // acc[i] = d5(vel)[i], i in [0, T-8) -> sb
-  for (int e = tid; e < n; e += 256) {
-    const int f = e / C;
-    const int64_t i = t0 - kHalo + f;
-    float v = 0.f;
-    if (i >= 0 && i < T - 8 && f + 4 < W)
-      v = d5(sa[e], sa[e + C], sa[e + 3 * C], sa[e + 4 * C]);
-    sb[e] = v;
-  }
-  __syncthreads();
-  // jerk[i] = d5(acc)[i], i in [0, T-12); r3 = sj * jerk -> kept in registers then written over sb (after sync)
-  float r3loc[(W * kMaxC + 255) / 256];
+  // ---- stage 0: x.  Unconditional loads from clamped addresses, all issued before the first use: written as
+  // `cond ? load : 0` per frame the loads stay behind their branches and the 11 DRAM round trips serialise (17 us per CTA).
   {
-    int q = 0;
-    for (int e = tid; e < n; e += 256, ++q) {
-      const int f = e / C;
-      const int64_t i = t0 - kHalo + f;
-      float v = 0.f;
-      if (i >= 0 && i < T - 12 && f + 4 < W) {
-        v = d5(sb[e], sb[e + C], sb[e + 3 * C], sb[e + 4 * C]);
-        if (f >= kHalo && f < kHalo + kTileT) pj += v * v;
-      }
-      r3loc[q] = sj * v;
+    float xin[kRun];
+    const int cc = cl ? c : 0;
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      int64_t t = i0 + u;
+      t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+      xin[u] = __ldg(cp + (t * B + b) * C + cc);
+    }
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      const int64_t t = i0 + u;
+      sx[(f0 + u) * 32 + c] = (cl && t >= 0 && t < T) ? xin[u] : 0.f;
     }
   }
   __syncthreads();
-  {
-    int q = 0;
-    for (int e = tid; e < n; e += 256, ++q) sb[e] = r3loc[q];
-  }
-  __syncthreads();
-  // adjoint of d5: (D^T r)[k] = (r[k] - 8 r[k-1] + 8 r[k-3] - r[k-4]) / 12  with r = 0 outside its range.
-  // r2 = D^T r3 (index range T-8), accumulate into registers, then r1 = D^T r2 + sv*vel (range T-4), g = D^T r1.
-  auto adj = [&](const float* r, int e, int f) -> float {
-    const int c1 = C;
-    const float r0 = r[e];
-    const float r1 = (f >= 1) ? r[e - c1] : 0.f;
-    const float r3 = (f >= 3) ? r[e - 3 * c1] : 0.f;
-    const float r4 = (f >= 4) ? r[e - 4 * c1] : 0.f;
-    return (r0 - 8.0f * r1 + 8.0f * r3 - r4) * (1.0f / 12.0f);
+  // a run plus its forward apron (frames f0 .. f0+14; beyond the window: 0)
+  auto load_fwd = [&](const float* sm, float (&r)[kRun + 4]) {
+#pragma unroll
+    for (int u = 0; u < kRun + 4; ++u) r[u] = (f0 + u < kSmW) ? sm[(f0 + u) * 32 + c] : 0.f;
   };
-  {
-    int q = 0;
-    for (int e = tid; e < n; e += 256, ++q) {
-      const int f = e / C;
-      const int64_t k = t0 - kHalo + f;
-      r3loc[q] = (k >= 0 && k < T - 8) ? adj(sb, e, f) : 0.f;  // r2
+  // a run plus its backward apron (frames f0-4 .. f0+10; before the window: 0); r[u] = value at frame f0 - 4 + u
+  auto load_bwd = [&](const float* sm, float (&r)[kRun + 4]) {
+#pragma unroll
+    for (int u = 0; u < kRun + 4; ++u) r[u] = (f0 - 4 + u >= 0) ? sm[(f0 - 4 + u) * 32 + c] : 0.f;
+  };
+  // adjoint of d5: (D^T r)[k] = (r[k] - 8 r[k-1] + 8 r[k-3] - r[k-4]) / 12 with r = 0 outside its range
+  auto adj = [](float r0, float r1, float r3, float r4) { return (r0 - 8.0f * r1 + 8.0f * r3 - r4) * (1.0f / 12.0f); };
+
+  float pv = 0.f, pj = 0.f, pl = 0.f;
+  float xr[kRun + 4];
+  load_fwd(sx, xr);
+  // ---- stage 1: vel[i] = d5(x[i..i+4]), i in [0, T-4); local-linear partial sums (util.py:614) on the owned frames
+#pragma unroll
+  for (int u = 0; u < kRun; ++u) {
+    const int64_t i = i0 + u;
+    const float v = (i >= 0 && i < T - 4 && f0 + u + 4 < kSmW) ? d5(xr[u], xr[u + 1], xr[u + 3], xr[u + 4]) : 0.f;
+    sv[(f0 + u) * 32 + c] = v;
+    if (own(f0 + u)) {
+      if (i < T - 4) pv += v * v;
+      if (i >= 1 && i < T - 1) {   // ll centred at frame i = (2 x[i] - x[i-1] - x[i+1]) / 2
+        const float xm = (u > 0) ? xr[u - 1] : sx[(f0 - 1) * 32 + c];   // an owned frame is never the window's first
+        const float l = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, xr[u]), xm), xr[u + 1]), 0.5f)   /* / 2 is exact */;
+        pl += l * l;
+      }
     }
   }
   __syncthreads();
+  // ---- stage 2: acc[i] = d5(vel[i..i+4]), i in [0, T-8)
   {
-    int q = 0;
-    for (int e = tid; e < n; e += 256, ++q) sb[e] = r3loc[q];  // sb = r2
-  }
-  __syncthreads();
-  {
-    int q = 0;
-    for (int e = tid; e < n; e += 256, ++q) {
-      const int f = e / C;
-      const int64_t k = t0 - kHalo + f;
-      r3loc[q] = (k >= 0 && k < T - 4) ? adj(sb, e, f) + sv * sa[e] : 0.f;  // r1 = D^T r2 + sv * vel
+    float r[kRun + 4];
+    load_fwd(sv, r);
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      const int64_t i = i0 + u;
+      s1[(f0 + u) * 32 + c] = (i >= 0 && i < T - 8 && f0 + u + 4 < kSmW) ? d5(r[u], r[u + 1], r[u + 3], r[u + 4]) : 0.f;
     }
   }
   __syncthreads();
+  // ---- stage 3: jerk[i] = d5(acc[i..i+4]), i in [0, T-12); r3 = kj * jerk
   {
-    int q = 0;
-    for (int e = tid; e < n; e += 256, ++q) sa[e] = r3loc[q];  // sa = r1
+    float r[kRun + 4];
+    load_fwd(s1, r);
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      const int64_t i = i0 + u;
+      const float jk = (i >= 0 && i < T - 12 && f0 + u + 4 < kSmW) ? d5(r[u], r[u + 1], r[u + 3], r[u + 4]) : 0.f;
+      if (own(f0 + u)) pj += jk * jk;
+      s2[(f0 + u) * 32 + c] = kj * jk;
+    }
   }
   __syncthreads();
-  for (int e = tid; e < kTileT * C; e += 256) {
-    const int f = kHalo + e / C, c = e % C;
-    const int64_t t = t0 + e / C;
-    if (t >= Tmax) continue;
-    if (t >= T) { dcp_smooth[(t * B + b) * C + c] = 0.f; continue; }
-    const int idx = f * C + c;
-    float g = adj(sa, idx, f);
-    // local-linear adjoint: ll[i] = x[i+1] - (x[i] + x[i+2])/2, i in [0,T-2); g_ll[t] = sl*(ll[t-1] - ll[t]/2 - ll[t-2]/2)
-    auto ll_at = [&](int64_t i, int fi) -> float {  // ll with centre frame fi (global centre i+1)
-      if (i < 0 || i >= T - 2) return 0.f;
-      const int id = fi * C + c;
-      return __fdiv_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[id]), sx[id - C]), sx[id + C]), 2.0f);
+  // ---- stage 4: r2 = D^T r3, k in [0, T-8)
+  {
+    float r[kRun + 4];
+    load_bwd(s2, r);
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      const int64_t k = i0 + u;
+      s1[(f0 + u) * 32 + c] = (k >= 0 && k < T - 8) ? adj(r[u + 4], r[u + 3], r[u + 1], r[u]) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- stage 5: r1 = D^T r2 + kv * vel, k in [0, T-4)
+  {
+    float r[kRun + 4];
+    load_bwd(s1, r);
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      const int64_t k = i0 + u;
+      s2[(f0 + u) * 32 + c] = (k >= 0 && k < T - 4) ? adj(r[u + 4], r[u + 3], r[u + 1], r[u]) + kv * sv[(f0 + u) * 32 + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- stage 6: g = D^T r1 + local-linear adjoint, owned frames only
+  {
+    float r[kRun + 4];
+    load_bwd(s2, r);
+    // ll centred at frame index fi (global centre t): 0 outside [1, T-1)
+    auto ll_c = [&](int64_t t, int fi) -> float {
+      if (t < 1 || t >= T - 1 || fi < 1 || fi + 1 >= kSmW) return 0.f;
+      return __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, sx[fi * 32 + c]), sx[(fi - 1) * 32 + c]), sx[(fi + 1) * 32 + c]), 0.5f);
     };
-    const float lc = ll_at(t - 1, f), lm = ll_at(t - 2, f - 1), lp = ll_at(t, f + 1);
-    g += sl * (lc - 0.5f * lm - 0.5f * lp);
-    dcp_smooth[(t * B + b) * C + c] = g;
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) {
+      const int f = f0 + u;
+      const int64_t t = i0 + u;
+      if (!own(f) || t >= Tmax || !cl) continue;
+      float g = 0.f;
+      if (t < T) {
+        // g_ll[t] = kl * (ll[t] - ll[t-1] / 2 - ll[t+1] / 2) with ll indexed by its centre frame
+        g = adj(r[u + 4], r[u + 3], r[u + 1], r[u]) + kl * (ll_c(t, f) - 0.5f * ll_c(t - 1, f - 1) - 0.5f * ll_c(t + 1, f + 1));
+      }
+      dcp_smooth[(t * B + b) * C + c] = g;
+    }
   }
-  // block reduce the three partial sums (fixed order -> deterministic)
+  // block reduce the three partial sums (fixed order -> deterministic; idle lanes hold zeros)
   for (int o = 16; o > 0; o >>= 1) {
     pv += __shfl_down_sync(0xffffffffu, pv, o);
     pj += __shfl_down_sync(0xffffffffu, pj, o);
@@ -211,12 +228,14 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
   const int mc = tid & 63;
   const bool mcl = mc < (int)Cm && Cm <= 64;
   if (Cm <= 64) {
-    if (mcl)
-      for (int64_t t = tid >> 6; t < Tm; t += 4) {
+    if (mcl) {
+#pragma unroll 8
+      for (int64_t t = tid >> 6; t < Tm; t += 4) {   // independent loads: eight frames in flight per thread
         const int64_t off = (t * B + b) * Cm + mc;
-        const float d = mel[off] - tmel[off];
+        const float d = __ldg(mel + off) - __ldg(tmel + off);
         sm += d * d;
       }
+    }
   } else {
     for (int64_t e = tid; e < nm; e += 256) {
       const int64_t t = e / Cm, c = e % Cm;
@@ -258,11 +277,13 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
   // d(w*sqrt(mean(e^2)))/de = w*e/(N*rmse); eps = 0 -> NaN at zero error, as in the reference (paule.py:68)
   const float gm = use_mel ? kMelWeight / ((float)nm * rmse_m) : 0.f;
   if (Cm <= 64) {
-    if (mcl)
+    if (mcl) {
+#pragma unroll 8
       for (int64_t t = tid >> 6; t < Tm_max; t += 4) {   // padded mel frames get a zero gradient
         const int64_t off = (t * B + b) * Cm + mc;
-        dmel[off] = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
+        dmel[off] = (use_mel && t < Tm) ? gm * (__ldg(mel + off) - __ldg(tmel + off)) : 0.f;
       }
+    }
   } else {
     for (int64_t e = tid; e < Tm_max * Cm; e += 256) {
       const int64_t t = e / Cm, c = e % Cm;
@@ -399,12 +420,8 @@ int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const
   PAULE_REQUIRE(objective >= 0 && objective <= 2);
   if (objective != PAULE_OBJ_ACOUSTIC) PAULE_REQUIRE(sv && tsv && dsv);
   const int n_tiles = (int)ceil_div(T, (int64_t)kTileT);
-  if (C == 30)
-    smooth_terms_kernel<30><<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
-                                                                                       n_tiles);
-  else
-    smooth_terms_kernel<0><<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
-                                                                                      n_tiles);
+  smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
+                                                                                 n_tiles);
   PAULE_LAUNCH_CHECK("smooth_terms_kernel");
   word_loss_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(mel, tmel, sv, tsv, scratch, n_tiles, terms,
                                                                step_count, slots, dmel, dsv, T, Tm, word_T, B, C, Cm,
