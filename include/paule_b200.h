@@ -273,6 +273,18 @@ typedef struct paule_plan {
      (paule/models.py:353 AvgPool1d(2,2)), its semvec is taken at that last frame (models.py:442), every loss term is a
      mean over the word's own frames, and frames beyond it are padding that receives a zero gradient.  NULL: all T. */
   const int32_t* word_frames;
+  /* optional loss branches, all NULL = the plain criterion.
+     Speech classifier (paule/paule.py:210-225,603-622: LinearClassifier, paule/models.py:887-911): z_b = mean over the word's
+     mel frames of (cls_w . pred_mel[t,b,:]) + cls_b[0]; term 0.1 * BCEWithLogits(z_b, 0) = 0.1 softplus(z_b), fused into the
+     criterion kernel together with its gradient 0.1 sigmoid(z_b) cls_w / Tm_b on every mel frame. */
+  const float* cls_w;         /* [Cm] */
+  const float* cls_b;         /* [1]  */
+  /* Loss terms evaluated outside the fused step (somatosensory branch, paule/paule.py:227-273,916-931,624-645:
+     cp -> tube -> mel / semvec through three more LSTM models on the same kernels): their per-word values, already
+     weighted, are added to the logged total and their gradient d(terms)/d(cp) to the step's gradient before Adam. */
+  const float* extra_terms;   /* [B,2]: tube_mel_loss, tube_semvec_loss, or NULL */
+  const float* extra_grad;    /* [T,B,C] time-major, or NULL */
+  float* aux_log;             /* [log_slot_count, B, 3]: speech_classifier, tube_mel, tube_semvec terms, or NULL */
 } paule_plan;
 
 PAULE_API size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);

@@ -43,6 +43,9 @@ VELOCITY_WEIGHT = 80.0
 JERK_WEIGHT = 400.0
 SEMANTIC_WEIGHT = 10.0
 LOCAL_LINEAR_WEIGHT = 100_000.0
+SPEECH_CLASSIFIER_WEIGHT = 0.1
+TUBE_MEL_WEIGHT = MEL_WEIGHT
+TUBE_SEMANTIC_WEIGHT = SEMANTIC_WEIGHT
 CLAMP = 1.05  # paule/paule.py:1202
 
 
@@ -200,6 +203,29 @@ def build_reference_models(seed: int = 0, hidden_size: int = 720, dtype=torch.fl
     return pred, emb, inv
 
 
+def build_branch_models(dtype=torch.float32):
+    """Seeded random-init models of the optional branches, as ``tests/golden/make_branches_golden.py::branch_models``
+    builds them from the reference classes (paule/paule.py:227-273 hyper-parameters; tube embedder without dropout;
+    classifier weight x30 so that its gradient matters): (cp_tube, tube_mel, tube_embedder, speech_classifier)."""
+    torch.manual_seed(1)
+    cp_tube = OracleForwardModel(num_lstm_layers=1, hidden_size=360, output_size=10, input_size=30,
+                                 apply_half_sequence=False)
+    tube_mel = OracleForwardModel(num_lstm_layers=1, hidden_size=360, output_size=60, input_size=10,
+                                  apply_half_sequence=True)
+    tube_emb = OracleEmbeddingModel(input_size=10, num_lstm_layers=2, hidden_size=720, dropout=0.0,
+                                    post_upsampling_size=0)
+    torch.manual_seed(2)
+    cls = OracleLinearClassifier(input_dim=60, output_dim=1)
+    with torch.no_grad():
+        cls.linear.weight.mul_(30.0)
+    mods = (cp_tube, tube_mel, tube_emb, cls)
+    for m in mods:
+        m.to(dtype)
+        for p in m.parameters():
+            p.requires_grad_(False)
+    return mods
+
+
 def state_dict_digest(module: nn.Module) -> str:
     h = hashlib.sha256()
     for k, v in module.state_dict().items():
@@ -314,6 +340,87 @@ def plan_inner_loop(pred: nn.Module, emb: nn.Module, cp0: torch.Tensor, target_m
     out["target_semvec"] = tsv
     out["loss"] = torch.stack(out["loss"]) if out["loss"] else torch.zeros(0, B)
     out["terms"] = torch.stack(out["terms"]) if out["terms"] else torch.zeros(0, B, 5)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# optional loss branches: speech classifier and somatosensory feedback
+# ----------------------------------------------------------------------------------------------
+class OracleLinearClassifier(nn.Module):
+    """paule/models.py:887-911 without src_lens: Linear(60->1) per mel frame, mean over time -> one logit per word."""
+
+    def __init__(self, input_dim=60, output_dim=1):
+        super().__init__()
+        self.linear = nn.Linear(input_dim, output_dim)
+
+    def forward(self, x, *, src_lens=None):
+        return self.linear(x).squeeze(2).mean(dim=1)
+
+
+def plan_inner_loop_branches(pred: nn.Module, emb: nn.Module, cp0: torch.Tensor, target_mel: torch.Tensor,
+                             n_steps: int, *, objective: str = "acoustic_semvec", lr: float = 0.01,
+                             speech_classifier: Optional[nn.Module] = None, cp_tube_model: Optional[nn.Module] = None,
+                             tube_mel_model: Optional[nn.Module] = None, tube_embedder: Optional[nn.Module] = None,
+                             target_semvec: Optional[torch.Tensor] = None, log_grads: bool = False) -> Dict[str, object]:
+    """Batched inner loop with ONE of the optional branches of paule/paule.py:
+
+    * speech classifier (:210-225, :915, criterion :603-622 / :664-682 / :719-737):
+      + 0.1 * BCEWithLogits(classifier(pred_mel), 0), per word;
+    * somatosensory feedback (:227-273, :916-931, criterion :624-645; only the acoustic_semvec variant runs in the reference,
+      the two others reference undefined names): pred_tube = cp_tube_model(cp), + 5 rmse(tube_mel_model(pred_tube), target_mel)
+      + 10 rmse(tube_embedder(pred_tube), target_semvec).  The tube embedder is evaluated without dropout.
+
+    Returns per-step ``loss`` [steps,B], ``terms`` [steps,B,5], ``aux`` [steps,B,3] (classifier, tube_mel, tube_semvec)."""
+    B, T, _ = cp0.shape
+    lens = tuple(torch.tensor(target_mel.shape[1]) for _ in range(B))
+    tube_lens = tuple(torch.tensor(T) for _ in range(B))
+    soma = cp_tube_model is not None
+    if soma and objective != "acoustic_semvec":
+        raise NotImplementedError("the reference's somatosensory criterion only runs for objective='acoustic_semvec'")
+    with torch.no_grad():
+        tsv = emb(target_mel, lens) if target_semvec is None else target_semvec
+    x = cp0.clone().requires_grad_()
+    opt = torch.optim.Adam([x], lr=lr)
+    out: Dict[str, object] = {"loss": [], "terms": [], "aux": [], "grads": []}
+    zero = torch.zeros(B, dtype=cp0.dtype)
+    for _ in range(n_steps):
+        opt.zero_grad()
+        mel = pred(x)
+        sv = emb(mel, lens)
+        _, terms = per_word_losses(mel, target_mel, sv, tsv, x, objective)
+        l_mel, l_sem, l_v, l_j, l_ll = terms.unbind(1)
+        l_cls, l_tm, l_ts = zero, zero, zero
+        if speech_classifier is not None:
+            z = speech_classifier(mel)                                                      # :915
+            l_cls = SPEECH_CLASSIFIER_WEIGHT * F.binary_cross_entropy_with_logits(z, torch.zeros_like(z), reduction="none")
+            if objective == "acoustic_semvec":
+                total = l_mel + l_v + l_j + l_sem + l_cls + l_ll                              # :621
+            elif objective == "acoustic":
+                total = l_mel + l_v + l_j + l_ll + l_cls                                      # :681
+            else:
+                total = l_v + l_j + l_sem + l_cls + l_ll                                      # :736
+        elif soma:
+            tube = cp_tube_model(x)                                                         # :917
+            tube_mel = tube_mel_model(tube)                                                 # :919
+            tube_sv = tube_embedder(tube, tube_lens)                                        # :929
+            l_tm = TUBE_MEL_WEIGHT * _wmean((tube_mel - target_mel) ** 2).sqrt()
+            l_ts = TUBE_SEMANTIC_WEIGHT * _wmean((tube_sv - tsv) ** 2).sqrt()
+            total = l_mel + l_v + l_j + l_sem + l_ll + l_tm + l_ts                            # :643
+        else:
+            raise ValueError("give speech_classifier or the three tube models")
+        out["loss"].append(total.detach().clone())
+        out["terms"].append(terms.detach().clone())
+        out["aux"].append(torch.stack((l_cls, l_tm, l_ts), dim=1).detach().clone())
+        total.sum().backward()
+        if log_grads:
+            out["grads"].append(x.grad.detach().clone())
+        opt.step()
+        with torch.no_grad():
+            x.data = x.data.clamp(-CLAMP, CLAMP)
+    out["planned_cp"] = x.detach().clone()
+    out["target_semvec"] = tsv
+    for k in ("loss", "terms", "aux"):
+        out[k] = torch.stack(out[k])
     return out
 
 

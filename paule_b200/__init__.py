@@ -7,10 +7,11 @@ Public surface mirrors the reference package for that path:
   paule_b200.distributed                                   (word sharding over GPUs + final gather)
 All compute runs in libpaule_b200.so (hand-written sm_100a CUDA behind a C ABI, include/paule_b200.h).
 """
-from . import _lib, ops, models, planner, paule, distributed  # noqa: F401
+from . import _lib, ops, models, planner, branches, paule, distributed  # noqa: F401
 from .paule import Paule, PAULE, PlanningResults  # noqa: F401
 from .models import (ForwardModel, EmbeddingModel, InverseModelMelTimeSmoothResidual,  # noqa: F401
-                     InverseModel, MelEmbeddingModel, MelEmbeddingModelMelSmoothResidualUpsampling)
+                     InverseModel, MelEmbeddingModel, MelEmbeddingModelMelSmoothResidualUpsampling,
+                     LinearClassifier, Generator)
 from .planner import BatchPlanner  # noqa: F401
 
 __version__ = "0.1.0"

@@ -36,6 +36,7 @@ class Plan(C.Structure):
         ("loss_log", vp), ("pred_mel", vp), ("pred_sv", vp), ("grad_out", vp),
         ("workspace", vp), ("workspace_bytes", sz),
         ("word_frames", vp),
+        ("cls_w", vp), ("cls_b", vp), ("extra_terms", vp), ("extra_grad", vp), ("aux_log", vp),
     ]
 
 

@@ -51,6 +51,7 @@ constexpr float kVelWeight = 80.0f;
 constexpr float kJerkWeight = 400.0f;
 constexpr float kSemWeight = 10.0f;
 constexpr float kLocalLinearWeight = 100000.0f;
+constexpr float kClassifierWeight = 0.1f;   // SPEECH_CLASSIFIER_WEIGHT, paule/paule.py:596
 
 int sm_count();
 

@@ -215,25 +215,30 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
                  const float* __restrict__ tsv, const float* __restrict__ partial, int n_tiles,
                  float* __restrict__ terms, const int32_t* __restrict__ step_count, int slots,
                  float* __restrict__ dmel, float* __restrict__ dsv, int64_t Tmax, int64_t Tm_max,
-                 const int32_t* __restrict__ word_T, int64_t B, int64_t C, int64_t Cm, int64_t S, int objective) {
+                 const int32_t* __restrict__ word_T, int64_t B, int64_t C, int64_t Cm, int64_t S, int objective,
+                 const float* __restrict__ cls_w, const float* __restrict__ cls_b,
+                 const float* __restrict__ extra_terms, float* __restrict__ aux_log) {
   __shared__ float sh[8];
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
   const int64_t T = word_T ? (int64_t)word_T[b] : Tmax;        // this word's cp frames
   const int64_t Tm = word_T ? (int64_t)(word_T[b] / 2) : Tm_max;  // ... and mel frames
   const bool use_mel = objective != PAULE_OBJ_SEMVEC, use_sem = objective != PAULE_OBJ_ACOUSTIC;
-  float sm = 0.f;
+  float sm = 0.f, sz = 0.f;   // sz: speech-classifier logit (LinearClassifier, models.py:887-911), summed over frames
   const int64_t nm = Tm * Cm;
   // thread = (channel tid % 64, frame tid / 64 + 4 i): a warp reads one 240-byte mel row segment per step, no division
   const int mc = tid & 63;
   const bool mcl = mc < (int)Cm && Cm <= 64;
   if (Cm <= 64) {
     if (mcl) {
+      const float wz = cls_w ? __ldg(cls_w + mc) : 0.f;
 #pragma unroll 8
       for (int64_t t = tid >> 6; t < Tm; t += 4) {   // independent loads: eight frames in flight per thread
         const int64_t off = (t * B + b) * Cm + mc;
-        const float d = __ldg(mel + off) - __ldg(tmel + off);
+        const float pm = __ldg(mel + off);
+        const float d = pm - __ldg(tmel + off);
         sm += d * d;
+        sz = fmaf(wz, pm, sz);
       }
     }
   } else {
@@ -242,9 +247,16 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
       const int64_t off = (t * B + b) * Cm + c;
       const float d = mel[off] - tmel[off];
       sm += d * d;
+      if (cls_w) sz = fmaf(cls_w[c], mel[off], sz);
     }
   }
   sm = block_sum_256(sm, sh);
+  float l_cls = 0.f, g_cls = 0.f;
+  if (cls_w != nullptr) {   // 0.1 * BCEWithLogits(z, 0) = 0.1 softplus(z); d/dz = 0.1 sigmoid(z)   (paule.py:596,610-620)
+    const float z = block_sum_256(sz, sh) / (float)Tm + (cls_b ? __ldg(cls_b) : 0.f);
+    l_cls = kClassifierWeight * (fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))));
+    g_cls = kClassifierWeight / (1.f + expf(-z)) / (float)Tm;
+  }
   float ss = 0.f;
   if (sv != nullptr)
     for (int64_t e = tid; e < S; e += 256) {
@@ -267,12 +279,25 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
   const float l_ll = kLocalLinearWeight * (pl / (float)((T - 2) * C));
   if (tid == 0) {
     float total;
-    if (objective == PAULE_OBJ_ACOUSTIC_SEMVEC) total = l_mel + l_vel + l_jerk + l_sem + l_ll;  // paule.py:660
+    if (cls_w != nullptr) {   // summation order of the classifier variants, paule.py:621,681,736
+      if (objective == PAULE_OBJ_ACOUSTIC_SEMVEC) total = l_mel + l_vel + l_jerk + l_sem + l_cls + l_ll;
+      else if (objective == PAULE_OBJ_ACOUSTIC) total = l_mel + l_vel + l_jerk + l_ll + l_cls;
+      else total = l_vel + l_jerk + l_sem + l_cls + l_ll;
+    } else if (objective == PAULE_OBJ_ACOUSTIC_SEMVEC) total = l_mel + l_vel + l_jerk + l_sem + l_ll;  // paule.py:660
     else if (objective == PAULE_OBJ_ACOUSTIC) total = l_mel + l_vel + l_jerk + l_ll;            // :715
     else total = l_vel + l_jerk + l_sem + l_ll;                                                  // :771
+    float x0 = 0.f, x1 = 0.f;
+    if (extra_terms != nullptr) {   // somatosensory terms, evaluated by the caller: ... + tube_mel + tube_semvec (paule.py:643)
+      x0 = extra_terms[b * 2 + 0]; x1 = extra_terms[b * 2 + 1];
+      total = total + x0 + x1;
+    }
     const int64_t slot = step_count ? (int64_t)((*step_count - 1) % slots + slots) % slots : 0;
     float* o = terms + (slot * B + b) * 6;
     o[0] = total; o[1] = l_mel; o[2] = l_sem; o[3] = l_vel; o[4] = l_jerk; o[5] = l_ll;
+    if (aux_log != nullptr) {
+      float* a = aux_log + (slot * B + b) * 3;
+      a[0] = l_cls; a[1] = x0; a[2] = x1;
+    }
   }
   // d(w*sqrt(mean(e^2)))/de = w*e/(N*rmse); eps = 0 -> NaN at zero error, as in the reference (paule.py:68)
   const float gm = use_mel ? kMelWeight / ((float)nm * rmse_m) : 0.f;
@@ -281,14 +306,18 @@ word_loss_kernel(const float* __restrict__ mel, const float* __restrict__ tmel, 
 #pragma unroll 8
       for (int64_t t = tid >> 6; t < Tm_max; t += 4) {   // padded mel frames get a zero gradient
         const int64_t off = (t * B + b) * Cm + mc;
-        dmel[off] = (use_mel && t < Tm) ? gm * (__ldg(mel + off) - __ldg(tmel + off)) : 0.f;
+        float gval = (use_mel && t < Tm) ? gm * (__ldg(mel + off) - __ldg(tmel + off)) : 0.f;
+        if (cls_w != nullptr && t < Tm) gval = fmaf(g_cls, __ldg(cls_w + mc), gval);
+        dmel[off] = gval;
       }
     }
   } else {
     for (int64_t e = tid; e < Tm_max * Cm; e += 256) {
       const int64_t t = e / Cm, c = e % Cm;
       const int64_t off = (t * B + b) * Cm + c;
-      dmel[off] = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
+      float gval = (use_mel && t < Tm) ? gm * (mel[off] - tmel[off]) : 0.f;
+      if (cls_w != nullptr && t < Tm) gval = fmaf(g_cls, cls_w[c], gval);
+      dmel[off] = gval;
     }
   }
   if (dsv != nullptr) {
@@ -319,7 +348,7 @@ __global__ void scatter_last_kernel(const float* __restrict__ rows, const int32_
 //   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); x.addcdiv_(m, sqrt(v)/sqrt(bc2) + eps, -lr/bc1)
 __global__ void __launch_bounds__(256)
 adam_clamp_kernel(float* __restrict__ cp, const float* __restrict__ g_a, const float* __restrict__ g_b,
-                  float* __restrict__ m, float* __restrict__ v, const int32_t* __restrict__ step_count, float lr,
+                  const float* __restrict__ g_c, float* __restrict__ m, float* __restrict__ v, const int32_t* __restrict__ step_count, float lr,
                   float beta1, float beta2, float eps, float clampv, int smiling, const float* __restrict__ past_cp,
                   int64_t past_n, float* __restrict__ grad_out, int64_t n, int C) {
   __shared__ float s_step_size, s_bc2_sqrt;
@@ -350,11 +379,15 @@ adam_clamp_kernel(float* __restrict__ cp, const float* __restrict__ g_a, const f
         const float4 G2 = *reinterpret_cast<const float4*>(g_b + e0);
         g[0] += G2.x; g[1] += G2.y; g[2] += G2.z; g[3] += G2.w;
       }
+      if (g_c) {   // gradient of loss branches evaluated outside the fused step (somatosensory, paule.py:624-645)
+        const float4 G3 = *reinterpret_cast<const float4*>(g_c + e0);
+        g[0] += G3.x; g[1] += G3.y; g[2] += G3.z; g[3] += G3.w;
+      }
     } else {
       for (int i = 0; i < 4; ++i) {
         const bool ok = e0 + i < n;
         x[i] = ok ? cp[e0 + i] : 0.f;
-        g[i] = ok ? g_a[e0 + i] + (g_b ? g_b[e0 + i] : 0.f) : 0.f;
+        g[i] = ok ? g_a[e0 + i] + (g_b ? g_b[e0 + i] : 0.f) + (g_c ? g_c[e0 + i] : 0.f) : 0.f;
         mm[i] = ok ? m[e0 + i] : 0.f;
         vv[i] = ok ? v[e0 + i] : 0.f;
       }
@@ -413,7 +446,8 @@ int scatter_last(const float* rows, const int32_t* word_T, float* seq, int64_t T
 int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const float* tsv, const float* cp,
                      float* terms, const int32_t* step_count, int slots, float* dmel, float* dsv, float* dcp_smooth,
                      float* scratch, int64_t T, int64_t Tm, const int32_t* word_T, int64_t B, int64_t C, int64_t Cm,
-                     int64_t S, int objective, paule_stream_t stream) {
+                     int64_t S, int objective, paule_stream_t stream, const float* cls_w, const float* cls_b,
+                     const float* extra_terms, float* aux_log) {
   PAULE_REQUIRE(mel && tmel && cp && terms && dmel && dcp_smooth && scratch && slots >= 1);
   PAULE_REQUIRE((sv == nullptr) == (tsv == nullptr));
   PAULE_REQUIRE(T >= 13 && Tm >= 1 && B >= 1 && C >= 1 && C <= kMaxC && Cm >= 1 && S >= 1);
@@ -425,25 +459,26 @@ int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const
   PAULE_LAUNCH_CHECK("smooth_terms_kernel");
   word_loss_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(mel, tmel, sv, tsv, scratch, n_tiles, terms,
                                                                step_count, slots, dmel, dsv, T, Tm, word_T, B, C, Cm,
-                                                               S, objective);
+                                                               S, objective, cls_w, cls_b, extra_terms, aux_log);
   PAULE_LAUNCH_CHECK("word_loss_kernel");
   return PAULE_OK;
 }
 
 int adam_clamp_logged(float* cp, const float* g_a, const float* g_b, float* m, float* v, const int32_t* step_count,
                       float lr, float beta1, float beta2, float eps, float clamp, int smiling, const float* past_cp,
-                      int64_t past_T, float* grad_out, int64_t T, int64_t B, int64_t C, paule_stream_t stream) {
+                      int64_t past_T, float* grad_out, int64_t T, int64_t B, int64_t C, paule_stream_t stream,
+                      const float* g_c) {
   PAULE_REQUIRE(cp && g_a && m && v && step_count && T >= 0 && B > 0 && C > 0);
   PAULE_REQUIRE(past_T >= 0 && past_T <= T && (past_T == 0 || past_cp));
   PAULE_REQUIRE(!smiling || C > 4);
   const int64_t n = T * B * C;
   if (n == 0) return PAULE_OK;
   PAULE_REQUIRE((reinterpret_cast<uintptr_t>(cp) | reinterpret_cast<uintptr_t>(g_a) | reinterpret_cast<uintptr_t>(m) |
-                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g_b)) % 16 == 0);
+                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g_b) | reinterpret_cast<uintptr_t>(g_c)) % 16 == 0);
   int64_t blocks = ceil_div(n, (int64_t)256 * 4);
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  adam_clamp_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cp, g_a, g_b, m, v, step_count, lr, beta1, beta2,
+  adam_clamp_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cp, g_a, g_b, g_c, m, v, step_count, lr, beta1, beta2,
                                                                      eps, clamp, smiling, past_T ? past_cp : nullptr,
                                                                      past_T * B * C, grad_out, n, (int)C);
   PAULE_LAUNCH_CHECK("adam_clamp_kernel");

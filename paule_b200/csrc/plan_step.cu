@@ -192,7 +192,7 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
   PAULE_TRY(plan_loss_logged(p->pred_mel, p->target_mel, need_sv ? p->pred_sv : nullptr,
                              need_sv ? p->target_sv : nullptr, p->cp, p->loss_log, p->step_count, p->log_slot_count,
                              w.dmel, w.dsv, w.dcp_smooth, w.partial, T, Tm, p->word_frames, B, C, Cm, S, p->objective,
-                             s));  // :986
+                             s, p->cls_w, p->cls_b, p->extra_terms, p->aux_log));  // :986
   if (use_sem) {                                                                   // discrepancy.backward(), :1052
     // head: dh1[Tm-1] = dsv W_head
     PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));
@@ -211,6 +211,7 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
   PAULE_TRY(layer_backward(p, p->fwd, w.gates_f, w.c_f, w.dhp, 2, nullptr, T, w.dcp_lstm, 0, w, s));
   // optimizer.step() + clamp + smiling + past_cp (paule.py:1199-1211)
   PAULE_TRY(adam_clamp_logged(p->cp, w.dcp_lstm, w.dcp_smooth, p->adam_m, p->adam_v, p->step_count, p->lr, p->beta1,
-                              p->beta2, p->eps, p->clamp, p->smiling, p->past_cp, p->past_T, p->grad_out, T, B, C, s));
+                              p->beta2, p->eps, p->clamp, p->smiling, p->past_cp, p->past_T, p->grad_out, T, B, C, s,
+                              p->extra_grad));
   return PAULE_OK;
 }

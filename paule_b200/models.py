@@ -282,6 +282,59 @@ class MelEmbeddingModelMelSmoothResidualUpsampling(nn.Module):
         return ops.linear_tm(z.contiguous(), _f32c(self.upsampling.weight), _f32c(self.upsampling.bias), False, False)[0]
 
 
+class LinearClassifier(nn.Module):
+    """Speech / non-speech classifier on log-mel frames (reference: paule/models.py:887-911): Linear(input_dim -> 1) per frame,
+    averaged over the word's frames -> one logit per word.  In the planner its loss term is fused into the criterion kernel
+    (``paule_plan.cls_w``); this ``forward`` serves the produced side and stand-alone use."""
+
+    def __init__(self, input_dim, output_dim):
+        super().__init__()
+        self.linear = nn.Linear(input_dim, output_dim)
+
+    def forward(self, input_, *, src_lens=None):
+        x = _check_input(input_, "LinearClassifier.forward(input_)")                 # [B,Tm,input_dim]
+        y = ops.linear_tm(ops.transpose_btc(x), _f32c(self.linear.weight), _f32c(self.linear.bias), False, True)
+        y = torch.squeeze(y, 2)                                                      # [B,Tm]
+        if src_lens is None:
+            return y.mean(dim=1)
+        lens = torch.as_tensor([int(l) for l in src_lens], device=y.device)
+        keep = torch.arange(y.shape[1], device=y.device).unsqueeze(0) < lens.unsqueeze(1)   # padded frames count as 0
+        return (y * keep).sum(dim=1) / lens
+
+
+class Generator(nn.Module):
+    """Conditional GAN generator semvec (+ noise) -> cp or mel trajectory (reference: paule/models.py:594-652), used ONLY in the
+    prologue of ``plan_resynth`` (``initialize_from='semvec'`` :558-565, missing acoustic target :515-522) -- once per call,
+    outside the planning loop.  Same parameter names / ``state_dict`` as the reference; the forward is a short chain of
+    library ops on the device (conv / batch-norm / linear upsampling), not a hand-written kernel."""
+
+    def __init__(self, channel_noise=100, embed_size=300, fc_size=1024, inital_seq_length=4, hidden_size=256,
+                 num_res_blocks=5, output_size=30):
+        super().__init__()
+        self.fc_size, self.hidden_size = fc_size, hidden_size
+        self.fc_reshaped_size = int(fc_size / inital_seq_length)
+        self.fully_connected = nn.Linear(channel_noise + embed_size, fc_size)
+        chans = [self.fc_reshaped_size] + [hidden_size] * num_res_blocks
+        self.res_blocks = nn.ModuleList(
+            nn.Sequential(nn.Conv1d(c_in, c_out, kernel_size=5, stride=1, padding=2), nn.BatchNorm1d(c_out), nn.LeakyReLU(0.2))
+            for c_in, c_out in zip(chans[:-1], chans[1:]))
+        self.post_linear = nn.Linear(hidden_size, output_size)
+        self.final_smoothing = nn.Conv1d(output_size, output_size, kernel_size=5, padding=2, groups=output_size)
+        self.output_activation = nn.Tanh()
+
+    def forward(self, x, length, vector):
+        z = self.fully_connected(torch.cat([x, vector.unsqueeze(1)], dim=2))         # [B,1,fc]
+        z = z.view(len(x), self.fc_reshaped_size, -1)                                # [B,fc/4,4]
+        n = len(self.res_blocks)
+        for i, block in enumerate(self.res_blocks):                                  # grow the sequence to `length` in n stages
+            z = nn.functional.interpolate(z, size=int(length / (n - i)), mode='linear', align_corners=False)
+            y = block(z)
+            z = y + z if (i > 0 or self.fc_reshaped_size == self.hidden_size) else y
+        z = self.post_linear(z.permute(0, 2, 1)).permute(0, 2, 1)                    # [B,out,length]
+        z = self.final_smoothing(z) + z
+        return self.output_activation(z.permute(0, 2, 1))
+
+
 InverseModel = InverseModelMelTimeSmoothResidual
 # BASELINE.json's north_star says "MelEmbeddingModel" for the mel-to-embedding model of the planning loop, which in the reference
 # is EmbeddingModel (paule/paule.py:167); the class the reference calls MelEmbeddingModel... is available under its own name.

@@ -24,13 +24,16 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .models import EmbeddingModel, ForwardModel, InverseModelMelTimeSmoothResidual
+from .models import EmbeddingModel, ForwardModel, InverseModelMelTimeSmoothResidual, LinearClassifier
 from .planner import BatchPlanner
 
 DIR = os.path.dirname(__file__)
 
 # field list of paule/paule.py:57 (33 names)
 PlanningResults = namedtuple('PlanningResults', "planned_cp, initial_cp, initial_sig, initial_sr, initial_prod_mel,initial_pred_mel, target_sig, target_sr, target_mel, prod_sig, prod_sr, prod_mel, pred_mel, initial_prod_semvec, initial_pred_semvec, prod_semvec, pred_semvec, prod_loss_steps, planned_loss_steps, planned_mel_loss_steps, vel_loss_steps, jerk_loss_steps, pred_semvec_loss_steps, prod_semvec_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, inv_model_loss")
+# field lists of paule/paule.py:58-59
+PlanningResultsWithSpeechClassifier = namedtuple('PlanningResultsWithSpeechClassifier', "planned_cp, initial_cp, initial_sig, initial_sr, initial_prod_mel, initial_pred_mel, target_sig, target_sr, target_mel, prod_sig, prod_sr, prod_mel, pred_mel, initial_prod_semvec, initial_pred_semvec, prod_semvec, pred_semvec, prod_loss_steps, planned_loss_steps, planned_mel_loss_steps, vel_loss_steps, jerk_loss_steps, pred_semvec_loss_steps, prod_semvec_loss_steps, pred_speech_classifier_loss_steps, prod_speech_classifier_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, inv_model_loss")
+PlanningResultsWithSomatosensory = namedtuple('PlanningResultsWithSomatosensory', "planned_cp, initial_cp, initial_sig, initial_sr, initial_prod_mel,initial_pred_mel, initial_prod_tube, initial_pred_tube, initial_prod_tube_mel, initial_pred_tube_mel, target_sig, target_sr, target_mel, prod_sig, prod_sr, prod_mel, pred_mel, prod_tube, pred_tube, prod_tube_mel, pred_tube_mel, initial_prod_semvec, initial_pred_semvec, initial_prod_tube_semvec, initial_pred_tube_semvec, prod_semvec, pred_semvec, prod_tube_semvec, pred_tube_semvec, prod_loss_steps, planned_loss_steps, planned_mel_loss_steps, vel_loss_steps, jerk_loss_steps, pred_semvec_loss_steps, prod_semvec_loss_steps, prod_tube_loss_steps, pred_tube_mel_loss_steps,prod_tube_mel_loss_steps, pred_tube_semvec_loss_steps, prod_tube_semvec_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, prod_tube_steps, pred_tube_steps, prod_tube_mel_steps, pred_tube_mel_steps, prod_tube_semvec_steps, pred_tube_semvec_steps, pred_model_loss, inv_model_loss, tube_model_loss, tube_mel_model_loss")
 BestSynthesisAcoustic = namedtuple('BestSynthesisAcoustic', "mel_loss, planned_cp, prod_sig, prod_mel, pred_mel")
 BestSynthesisSemantic = namedtuple('BestSynthesisSemantic', "semvec_loss, planned_cp, prod_sig, prod_semvec, pred_semvec")
 SubLosses = namedtuple('SubLosses', "mel_loss, semvec_loss, velocity_loss, jerk_loss, local_linear_loss, speech_classifier_loss, tube_mel_loss, tube_semvec_loss")
@@ -39,6 +42,11 @@ _PRETRAINED = {   # file names of paule/paule.py:126,148,169
     "pred": "pretrained_models/predictive/pred_model_common_voice_1_720_lr_0001_50_00001_50_000001_50_0000001_200.pt",
     "inv": "pretrained_models/inverse/inv_model_common_voice_3_1_720_5_lr_0001_50_00001_50_000001_50_0000001_200.pt",
     "emb": "pretrained_models/embedder/embed_model_common_voice_syn_rec_2_720_0_dropout_07_noise_6e05_rmse_lr_00001_200.pt",
+    # optional branches, paule/paule.py:218,238,250,263
+    "cls": "pretrained_models/speech_classifier/linear_model_rec_as_nonspeech.pt",
+    "cp_tube": "pretrained_models/somatosensory/cp_to_tube_model_1_360_lr_0001_50_00001_100.pt",
+    "tube_mel": "pretrained_models/somatosensory/tube_to_mel_model_1_360_lr_0001_50_00001_100.pt",
+    "tube_emb": "pretrained_models/somatosensory/tube_to_vector_model_2_720_0_dropout_07_noise_6e05_rmse_lr_00001_200.pt",
 }
 
 
@@ -72,11 +80,8 @@ class Paule():
         self.synthesizer = synthesizer
         if use_somatosensory_feedback and use_speech_classifier:
             raise NotImplementedError("at the moment you have to choose either to use `use_somatosenrosry_feedback=True` OR to use `use_speech_classifier=True` or none")
-        if use_somatosensory_feedback or use_speech_classifier:
-            raise NotImplementedError("the somatosensory and speech-classifier loss branches (paule/paule.py:210-273) "
-                                      "are outside the B200 hot path (SURVEY.md section 8f, row N4)")
-        self.use_somatosensory_feedback = False
-        self.use_speech_classifier = False
+        self.use_somatosensory_feedback = bool(use_somatosensory_feedback)
+        self.use_speech_classifier = bool(use_speech_classifier)
 
         self.pred_model = pred_model if pred_model else _load_pretrained(
             ForwardModel(num_lstm_layers=1, hidden_size=720), "pred", self.device)
@@ -91,6 +96,27 @@ class Paule():
         # :558-565); they are kept as injected (any torch module on the device), never constructed here.
         self.cp_gen_model = cp_gen_model.to(self.device) if cp_gen_model is not None else None
         self.mel_gen_model = mel_gen_model.to(self.device) if mel_gen_model is not None else None
+
+        # optional loss branches (paule.py:210-273)
+        if self.use_speech_classifier:
+            self.speech_classifier = speech_classifier if speech_classifier else _load_pretrained(
+                LinearClassifier(input_dim=60, output_dim=1), "cls", self.device)
+            self.speech_classifier = self.speech_classifier.to(self.device)
+            self.speech_classifier.eval()
+        if self.use_somatosensory_feedback:
+            self.cp_tube_model = cp_tube_model if cp_tube_model else _load_pretrained(
+                ForwardModel(num_lstm_layers=1, hidden_size=360, output_size=10, input_size=30,
+                             apply_half_sequence=False), "cp_tube", self.device)
+            self.tube_mel_model = tube_mel_model if tube_mel_model else _load_pretrained(
+                ForwardModel(num_lstm_layers=1, hidden_size=360, output_size=60, input_size=10,
+                             apply_half_sequence=True), "tube_mel", self.device)
+            self.tube_embedder = tube_embedder if tube_embedder else _load_pretrained(
+                EmbeddingModel(input_size=10, num_lstm_layers=2, hidden_size=720, dropout=0.7, post_upsampling_size=0),
+                "tube_emb", self.device)
+            self.cp_tube_model = self.cp_tube_model.to(self.device)
+            self.tube_mel_model = self.tube_mel_model.to(self.device)
+            self.tube_embedder = self.tube_embedder.to(self.device)
+            self.tube_embedder.eval()
 
         self.continue_data = continue_data
         self.continue_data_limit = 1000
@@ -347,8 +373,19 @@ class Paule():
                                lr=learning_rate_planning, objective=objective, smiling=self.smiling, past_cp=past_t,
                                log_semantics=log_semantics, log_gradients=log_gradients,
                                max_log_steps=max(n_steps, 1), math=self.math,
-                               use_cuda_graph=True, lengths=lengths)
+                               use_cuda_graph=True, lengths=lengths,
+                               speech_classifier=self.speech_classifier if self.use_speech_classifier else None,
+                               somatosensory=(self.cp_tube_model, self.tube_mel_model, self.tube_embedder)
+                               if self.use_somatosensory_feedback else None)
         self.last_planner = planner
+        soma = planner.soma
+
+        def tube_predictions():       # no_grad cp -> tube -> (mel, semvec) of the current cps (paule.py:1472-1487)
+            with torch.no_grad():
+                tube, tube_mel, tube_sv = soma.forward(planner.cp)
+            return ops.transpose_btc(tube), ops.transpose_btc(tube_mel), tube_sv
+        if soma is not None:
+            initial_pred_tube, initial_pred_tube_mel, initial_pred_tube_semvec = tube_predictions()
 
         def out(t):
             a = t.detach().cpu().numpy()
@@ -448,6 +485,39 @@ class Paule():
             return [r if batched else float(r[0]) for r in rows]
 
         sem_logged = objective in ('acoustic_semvec', 'semvec') or log_semantics
+        sem_steps = per_step("semvec") if sem_logged else list()
+        if self.use_speech_classifier:
+            # produced side of the classifier term (paule.py:1116-1125): 0.1 BCEWithLogits(classifier(prod_mel), 0) per synthesis
+            prod_cls = []
+            if synth:
+                for mels_k in prod_mel_steps:
+                    lst = mels_k if batched else [mels_k]
+                    with torch.no_grad():
+                        z = torch.stack([self.speech_classifier(torch.from_numpy(np.asarray(m, dtype=np.float32))
+                                                                .to(self.device).unsqueeze(0))[0] for m in lst])
+                    v = (0.1 * torch.nn.functional.softplus(z)).cpu().numpy()
+                    prod_cls.append(v if batched else float(v[0]))
+            return PlanningResultsWithSpeechClassifier(
+                out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None,
+                None, initial_prod_mel, out(initial_pred_mel), None, None, out(target_mel), prod_sig, prod_sr, prod_mel_out,
+                out(pred_mel), initial_prod_semvec, out(initial_pred_semvec), prod_semvec_out, out(pred_semvec),
+                prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"), sem_steps,
+                prod_semvec_loss_steps, per_step("speech_classifier"), prod_cls, cp_steps, pred_semvec_steps,
+                prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, list())
+        if self.use_somatosensory_feedback:
+            # the produced tube side needs VocalTractLab's tube extraction (paule.py:1070-1095), which stays host-side and does
+            # not ship: those fields are None / empty
+            pred_tube, pred_tube_mel, pred_tube_semvec = tube_predictions()
+            return PlanningResultsWithSomatosensory(
+                out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None,
+                None, initial_prod_mel, out(initial_pred_mel), None, out(initial_pred_tube), None, out(initial_pred_tube_mel),
+                None, None, out(target_mel), prod_sig, prod_sr, prod_mel_out, out(pred_mel), None, out(pred_tube), None,
+                out(pred_tube_mel), initial_prod_semvec, out(initial_pred_semvec), None, out(initial_pred_tube_semvec),
+                prod_semvec_out, out(pred_semvec), None, out(pred_tube_semvec),
+                prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"), sem_steps,
+                prod_semvec_loss_steps, list(), per_step("tube_mel"), list(), per_step("tube_semvec"), list(), cp_steps,
+                pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, list(), list(),
+                list(), list(), list(), list(), pred_model_loss, list(), list(), list())
         return PlanningResults(
             out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None, None,
             initial_prod_mel, out(initial_pred_mel),

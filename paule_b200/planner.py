@@ -29,13 +29,18 @@ class BatchPlanner:
     ``target_mel`` are then padded to the longest word; word b is planned exactly as if it were alone (the reference plans
     one word per call): its mel / semvec / smoothness terms are means over its own ``lengths[b]`` (``lengths[b] // 2`` mel)
     frames, its semvec is read at its own last mel frame, and the padding frames receive a zero gradient.
+
+    Optional loss branches (mutually exclusive as in paule/paule.py:117-118): ``speech_classifier`` -- a
+    ``LinearClassifier`` whose term 0.1 BCEWithLogits(classifier(pred_mel), 0) is fused into the criterion kernel;
+    ``somatosensory`` -- ``(cp_tube_model, tube_mel_model, tube_embedder)``, see ``branches.SomatosensoryBranch``.
     """
 
     def __init__(self, pred_model: ForwardModel, embedder: EmbeddingModel, initial_cp: torch.Tensor,
                  target_mel: torch.Tensor, target_semvec: Optional[torch.Tensor] = None, *, lr: float = 0.01,
                  objective: str = "acoustic_semvec", smiling: bool = False, past_cp: Optional[torch.Tensor] = None,
                  log_semantics: bool = True, log_gradients: bool = False, max_log_steps: int = 1024,
-                 math: int = ops.MATH_FP32, use_cuda_graph: bool = True, lengths=None):
+                 math: int = ops.MATH_FP32, use_cuda_graph: bool = True, lengths=None,
+                 speech_classifier=None, somatosensory=None):
         _lib.require_device()
         if objective not in ops.OBJECTIVES:
             raise ValueError("objective has to be one of 'acoustic_semvec', 'acoustic' or 'semvec'")
@@ -95,6 +100,24 @@ class BatchPlanner:
         self.pred_mel = torch.empty((Tm, B, Cm), **f32)
         self.pred_sv = torch.zeros((B, S), **f32)
         self.grad_out = torch.empty_like(self.cp) if log_gradients else None
+        # ---- optional loss branches
+        if speech_classifier is not None and somatosensory is not None:
+            raise NotImplementedError("at the moment you have to choose either to use `use_somatosenrosry_feedback=True` OR to use `use_speech_classifier=True` or none")
+        self.cls_w = self.cls_b = self.soma = self.aux_log = None
+        if speech_classifier is not None:
+            from .branches import classifier_operands
+            self.cls_w, self.cls_b = classifier_operands(speech_classifier, Cm, dev)
+        if somatosensory is not None:
+            if objective != "acoustic_semvec":
+                # the reference's 'acoustic' / 'semvec' somatosensory criteria use undefined names (paule/paule.py:697,:750)
+                raise NotImplementedError("somatosensory feedback is defined for objective='acoustic_semvec' only "
+                                          "(paule/paule.py:624-645)")
+            if self.lengths is not None:
+                raise NotImplementedError("somatosensory feedback with ragged batches")
+            from .branches import SomatosensoryBranch
+            self.soma = SomatosensoryBranch(*somatosensory, B=B, T=T, C=C, device=dev)
+        if self.cls_w is not None or self.soma is not None:
+            self.aux_log = torch.zeros((self.max_log_steps, B, 3), **f32)
         lib = _lib.load()
         ws_bytes = lib.paule_plan_workspace_bytes(B, T, H, C, Cm, S, math)
         # zero-filled ONCE: the pad rows / pad columns of the bf16 operand images inside must be exact zeros
@@ -165,6 +188,11 @@ class BatchPlanner:
         s.grad_out = None if self.grad_out is None else self.grad_out.data_ptr()
         s.workspace, s.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         s.word_frames = None if self.word_frames is None else self.word_frames.data_ptr()
+        s.cls_w = None if self.cls_w is None else self.cls_w.data_ptr()
+        s.cls_b = None if self.cls_b is None else self.cls_b.data_ptr()
+        s.extra_terms = None if self.soma is None else self.soma.extra_terms.data_ptr()
+        s.extra_grad = None if self.soma is None else self.soma.extra_grad.data_ptr()
+        s.aux_log = None if self.aux_log is None else self.aux_log.data_ptr()
         self._struct = s
 
     def struct_ref(self):
@@ -190,6 +218,8 @@ class BatchPlanner:
         return ops.transpose_btc(self.pred_mel), self.pred_sv.clone()
 
     def _one_step(self) -> None:
+        if self.soma is not None:   # tube terms + their d/d(cp) for the CURRENT cps, consumed by the fused step below
+            self.soma.run(self.cp, self.target_mel, self.target_sv)
         ops.plan_step(self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log, self.pred_mel, self.pred_sv,
                       self.workspace, self._key)
 
@@ -199,21 +229,24 @@ class BatchPlanner:
             return
         if self.steps_done + n > self.max_log_steps:
             raise ValueError(f"loss log holds {self.max_log_steps} steps; construct with a larger max_log_steps")
-        if self._use_graph and self._graph is None:
+        if self._use_graph and self._graph is None and not (self.soma is not None and self.soma.stochastic):
             # warm up on a side stream, then capture one step; Adam's step counter and the log slot live on the
             # device, so a replay is a full, correct step.
-            snap = [t.clone() for t in (self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log)]
+            state = [self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log]
+            if self.aux_log is not None:
+                state.append(self.aux_log)
+            snap = [t.clone() for t in state]
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
                 self._one_step()
             torch.cuda.current_stream(self.device).wait_stream(s)
-            for dst, src in zip((self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log), snap):
+            for dst, src in zip(state, snap):
                 dst.copy_(src)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._one_step()
-            for dst, src in zip((self.cp, self.adam_m, self.adam_v, self.step_count, self.loss_log), snap):
+            for dst, src in zip(state, snap):
                 dst.copy_(src)
             self._graph = g
         for _ in range(n):
@@ -244,8 +277,12 @@ class BatchPlanner:
         """per-step, per-word loss terms logged BEFORE each update (paule/paule.py:988): tensors [steps,B]."""
         self.check()
         log = self.loss_log[: self.steps_done]
-        return {"total": log[..., 0], "mel": log[..., 1], "semvec": log[..., 2], "velocity": log[..., 3],
-                "jerk": log[..., 4], "local_linear": log[..., 5]}
+        out = {"total": log[..., 0], "mel": log[..., 1], "semvec": log[..., 2], "velocity": log[..., 3],
+               "jerk": log[..., 4], "local_linear": log[..., 5]}
+        if self.aux_log is not None:
+            aux = self.aux_log[: self.steps_done]
+            out.update({"speech_classifier": aux[..., 0], "tube_mel": aux[..., 1], "tube_semvec": aux[..., 2]})
+        return out
 
     def last_grad(self) -> Optional[torch.Tensor]:
         return None if self.grad_out is None else ops.transpose_btc(self.grad_out)

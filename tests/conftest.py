@@ -17,3 +17,11 @@ def golden():
     import numpy as np
     path = os.path.join(REPO, "tests", "golden", "paule_golden.npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def golden_branches():
+    """vectors of the speech-classifier / somatosensory branches from the real reference (make_branches_golden.py)"""
+    import numpy as np
+    path = os.path.join(REPO, "tests", "golden", "branches_golden.npz")
+    return dict(np.load(path, allow_pickle=False))

@@ -228,3 +228,20 @@ def test_mel_embedding_model_state_dict_matches_reference_keys():
     for k in sorted(sd):
         h.update(k.encode()); h.update(sd[k].detach().cpu().float().numpy().tobytes())
     assert h.hexdigest() == str(g["digest"])
+
+
+def test_generator_matches_the_reference_output():
+    """paule_b200.models.Generator (prologue-only, library ops) == the reference's Generator on seeded weights
+    (tests/golden/make_generator_golden.py); pure torch, so it runs on the CPU here."""
+    import os
+    import numpy as np
+    import torch
+    from paule_b200.models import Generator
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "generator_golden.npz")))
+    for tag, osz, length in (("cp", 30, 46), ("mel", 60, 23)):
+        torch.manual_seed(4)
+        gen = Generator(output_size=osz).eval()
+        with torch.no_grad():
+            y = gen(torch.from_numpy(g[f"{tag}_noise"]), length, torch.from_numpy(g[f"{tag}_vec"]))
+        assert y.shape == (2, length, osz)
+        np.testing.assert_allclose(y.numpy(), g[f"{tag}_y"], atol=1e-6)

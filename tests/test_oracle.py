@@ -126,3 +126,35 @@ def test_edge_cases():
         exact = pred(cp0)
     r2 = O.plan_inner_loop(pred, emb, cp0, exact, 1, objective="acoustic")
     assert torch.isnan(r2["planned_cp"]).any()
+
+
+# ---- optional loss branches against the real plan_resynth with use_speech_classifier / use_somatosensory_feedback
+def test_branch_weights_regenerate_bit_identically(golden_branches):
+    mods = O.build_branch_models(torch.float64)
+    assert [O.state_dict_digest(m) for m in mods] == list(golden_branches["digest64"])
+    np.testing.assert_array_equal(mods[3].linear.weight.numpy(), golden_branches["cls_w"])
+
+
+@pytest.mark.parametrize("objective", ["acoustic_semvec", "acoustic", "semvec"])
+def test_classifier_branch_matches_real_plan_resynth_fp64(golden_branches, models64, objective):
+    g, (pred, emb, _) = golden_branches, models64
+    cls = O.build_branch_models(torch.float64)[3]
+    tag = f"cls_{objective}"
+    n = len(g[f"{tag}_loss"])
+    r = O.plan_inner_loop_branches(pred, emb, torch.from_numpy(g["cp0"]), torch.from_numpy(g["tmel"]), n,
+                                   objective=objective, speech_classifier=cls)
+    np.testing.assert_allclose(r["loss"][:, 0].numpy(), g[f"{tag}_loss"], rtol=1e-12)
+    np.testing.assert_allclose(r["aux"][:, 0, 0].numpy(), g[f"{tag}_cls"], rtol=1e-12)
+    np.testing.assert_allclose(r["planned_cp"][0].numpy(), g[f"{tag}_planned_cp"], atol=1e-14)
+
+
+def test_somatosensory_branch_matches_real_plan_resynth_fp64(golden_branches, models64):
+    g, (pred, emb, _) = golden_branches, models64
+    cp_tube, tube_mel, tube_emb, _ = O.build_branch_models(torch.float64)
+    n = len(g["soma_loss"])
+    r = O.plan_inner_loop_branches(pred, emb, torch.from_numpy(g["cp0"]), torch.from_numpy(g["tmel"]), n,
+                                   cp_tube_model=cp_tube, tube_mel_model=tube_mel, tube_embedder=tube_emb)
+    np.testing.assert_allclose(r["loss"][:, 0].numpy(), g["soma_loss"], rtol=1e-12)
+    np.testing.assert_allclose(r["aux"][:, 0, 1].numpy(), g["soma_tube_mel"], rtol=1e-12)
+    np.testing.assert_allclose(r["aux"][:, 0, 2].numpy(), g["soma_tube_sem"], rtol=1e-12)
+    np.testing.assert_allclose(r["planned_cp"][0].numpy(), g["soma_planned_cp"], atol=1e-14)
