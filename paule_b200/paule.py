@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .models import EmbeddingModel, ForwardModel, InverseModelMelTimeSmoothResidual, LinearClassifier
+from .models import EmbeddingModel, ForwardModel, Generator, InverseModelMelTimeSmoothResidual, LinearClassifier
 from .planner import BatchPlanner
 
 DIR = os.path.dirname(__file__)
@@ -42,6 +42,8 @@ _PRETRAINED = {   # file names of paule/paule.py:126,148,169
     "pred": "pretrained_models/predictive/pred_model_common_voice_1_720_lr_0001_50_00001_50_000001_50_0000001_200.pt",
     "inv": "pretrained_models/inverse/inv_model_common_voice_3_1_720_5_lr_0001_50_00001_50_000001_50_0000001_200.pt",
     "emb": "pretrained_models/embedder/embed_model_common_voice_syn_rec_2_720_0_dropout_07_noise_6e05_rmse_lr_00001_200.pt",
+    "cp_gen": "pretrained_models/cp_gan/conditional_trained_cp_generator_whole_critic_it_5_10_20_40_80_100_415.pt",
+    "mel_gen": "pretrained_models/mel_gan/conditional_trained_mel_generator_synthesized_critic_it_5_10_20_40_80_100_400.pt",
     # optional branches, paule/paule.py:218,238,250,263
     "cls": "pretrained_models/speech_classifier/linear_model_rec_as_nonspeech.pt",
     "cp_tube": "pretrained_models/somatosensory/cp_to_tube_model_1_360_lr_0001_50_00001_100.pt",
@@ -92,10 +94,17 @@ class Paule():
         self.embedder = embedder if embedder else _load_pretrained(
             EmbeddingModel(num_lstm_layers=2, hidden_size=720), "emb", self.device)
         self.embedder = self.embedder.to(self.device)
-        # generative models are only used for initialize_from='semvec' / missing acoustic targets (paule.py:515-522,
-        # :558-565); they are kept as injected (any torch module on the device), never constructed here.
-        self.cp_gen_model = cp_gen_model.to(self.device) if cp_gen_model is not None else None
-        self.mel_gen_model = mel_gen_model.to(self.device) if mel_gen_model is not None else None
+        # generative models (paule.py:186-208): only used in the prologue, for initialize_from='semvec' (:558-565) and for a
+        # missing acoustic target (:515-522).  Injected, or the pretrained ones when their files are present; otherwise None
+        # and the two prologue modes that need them raise.
+        def _gen(given, key, output_size):
+            if given is not None:
+                return given.to(self.device).float().eval()   # planning is fp32 (the reference ships fp64 modules)
+            if os.path.exists(os.path.join(DIR, _PRETRAINED[key])):
+                return _load_pretrained(Generator(output_size=output_size), key, self.device).to(self.device).eval()
+            return None
+        self.cp_gen_model = _gen(cp_gen_model, "cp_gen", 30)
+        self.mel_gen_model = _gen(mel_gen_model, "mel_gen", 60)
 
         # optional loss branches (paule.py:210-273)
         if self.use_speech_classifier:
@@ -309,9 +318,10 @@ class Paule():
                 raise NotImplementedError("planning without an acoustic target needs mel_gen_model (paule.py:515-522)")
             if not isinstance(target_semvec, torch.Tensor):
                 target_semvec = torch.tensor(np.asarray(target_semvec), device=self.device)
-            sv = target_semvec.reshape(-1, 300).detach().clone().to(self.device)
-            noise = torch.randn(sv.shape[0], 1, 100, device=self.device, dtype=sv.dtype)
-            target_mel = self.mel_gen_model(noise, target_seq_length, sv).detach().clone()
+            sv = target_semvec.reshape(-1, 300).detach().clone().to(self.device).float()
+            noise = torch.randn(sv.shape[0], 1, 100, device=self.device)
+            with torch.no_grad():
+                target_mel = self.mel_gen_model(noise, target_seq_length, sv).detach().clone()
             batched = sv.shape[0] != 1
 
         target_mel = target_mel.to(self.device).float().contiguous()
@@ -334,7 +344,8 @@ class Paule():
                     with torch.no_grad():
                         target_semvec = self.embedder(target_mel, tuple(target_mel.shape[1] for _ in range(B)))
                 noise = torch.randn(B, 1, 100, device=self.device)
-                cp0 = self.cp_gen_model(noise, 2 * target_seq_length, target_semvec.reshape(B, 300)).detach().float()
+                with torch.no_grad():
+                    cp0 = self.cp_gen_model(noise, 2 * target_seq_length, target_semvec.reshape(B, 300)).detach().float()
             else:
                 raise ValueError("initialize_from has to be either 'acoustic' or 'semvec'")
         else:

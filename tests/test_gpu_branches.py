@@ -230,3 +230,36 @@ def test_dropout_tube_embedder_plans_without_graph(dev, models, branch_models, g
     assert pl._graph is None
     tot = _np(pl.losses()["total"])
     assert np.isfinite(tot).all() and (tot[-1] < tot[0]).all()
+
+
+def test_generator_prologue_modes(dev, models, golden):
+    """initialize_from='semvec' (cp GAN generator, paule/paule.py:558-565) and a missing acoustic target (mel GAN generator,
+    :515-522): the prologue draws noise [B,1,100] on the device and runs the injected generators; planning then proceeds."""
+    import paule_b200 as P
+    pred, emb, inv = models
+    torch.manual_seed(4)
+    cp_gen, mel_gen = P.Generator(output_size=30), P.Generator(output_size=60)
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, cp_gen_model=cp_gen, mel_gen_model=mel_gen, device=dev)
+    tmel = torch.from_numpy(golden["b3_tmel"]).to(dev)                  # [3,20,60]
+    B, Tm = tmel.shape[0], tmel.shape[1]
+    res = pm.plan_resynth(target_acoustic=tmel, initialize_from="semvec", objective="acoustic_semvec", n_outer=1, n_inner=3,
+                          continue_learning=False, verbose=False, seed=123)
+    with torch.no_grad():
+        tsv = emb(tmel, [Tm] * B)
+        torch.manual_seed(123)
+        noise = torch.randn(B, 1, 100, device=dev)
+        want = pm.cp_gen_model(noise, 2 * Tm, tsv)
+    np.testing.assert_allclose(res.initial_cp, _np(want), atol=1e-6)
+    assert res.planned_cp.shape == (B, 2 * Tm, 30)
+    tot = np.asarray(res.planned_loss_steps)
+    assert np.isfinite(tot).all() and (tot[-1] < tot[0]).all()
+    # no acoustic target: the mel generator makes one from the semvec
+    res2 = pm.plan_resynth(target_acoustic=None, target_semvec=tsv, target_seq_length=Tm, initialize_from="acoustic",
+                           objective="acoustic_semvec", n_outer=1, n_inner=2, continue_learning=False, verbose=False,
+                           seed=5)
+    with torch.no_grad():
+        torch.manual_seed(5)
+        noise = torch.randn(B, 1, 100, device=dev)
+        want_mel = pm.mel_gen_model(noise, Tm, tsv)
+    np.testing.assert_allclose(res2.target_mel, _np(want_mel), atol=1e-6)
+    assert np.isfinite(np.asarray(res2.planned_loss_steps)).all()
