@@ -32,8 +32,8 @@ struct Bwd2Smem {
   uint32_t tmem_base;
 };
 
-constexpr int kB2EpiWarps = 8;
-constexpr int kB2Threads = 32 * (kB2EpiWarps + kNumKB);   // 640
+constexpr int kB2EpiWarps = 8;                            // cell warps of ONE epilogue group
+__host__ __device__ constexpr int b2_threads(int EG) { return 32 * (kB2EpiWarps * EG + kNumKB); }   // 640 / 896
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
@@ -84,8 +84,11 @@ __device__ __forceinline__ void cluster_sync_all2() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int NQ>
-__global__ void __launch_bounds__(kB2Threads, 1)
+// EG: epilogue groups (see tc_lstm_fwd2.cu): with EG = 2 a second group of 8 warps owns the second half of the CTA's quarters
+// (contiguous halves, in the loaders' visiting order: an interleaved split delays quarter q's publication behind the MMAs of
+// quarter q + 2 and measured 20 % slower), so two quarters' reductions and cell adjoints run concurrently.
+template <int NQ, int EG>
+__global__ void __launch_bounds__(b2_threads(EG), 1)
 tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed,
                     const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
                     uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0, int keep_da) {
@@ -93,6 +96,9 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   using Smem = Bwd2Smem<NQ>;
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kGW = kWq * NQ;                        // words per CTA group (NQ independent quarters, see tc_lstm_fwd2.cu)
+  constexpr int kEpiW = kB2EpiWarps * EG, kB2Threads = b2_threads(EG);
+  static_assert(EG == 1 || EG == 2, "one or two epilogue groups");
+  constexpr int kQPG = (NQ + EG - 1) / EG;             // quarters per epilogue group: group eg owns [eg kQPG, (eg + 1) kQPG)
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int g = (int)cluster_ctarank_u32();                 // gate handled by this CTA's K slice
   const int cl = blockIdx.x >> 2;
@@ -110,7 +116,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   }
   for (int i = tid; i < NQ * kV2BBytes / 16; i += kB2Threads) reinterpret_cast<uint4*>(&S.b[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_shared();
-  if (warp == kB2EpiWarps) tmem_alloc<512>(&S.tmem_base);
+  if (warp == kEpiW) tmem_alloc<512>(&S.tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -122,9 +128,9 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   tcgen05_fence_after();
   cluster_sync_all2();   // every sibling's mbarriers are initialised before any st.async targets them
 
-  if (warp >= kB2EpiWarps) {
+  if (warp >= kEpiW) {
     // ===================== loader + MMA issuer of k-block kb =====================
-    const int kb = warp - kB2EpiWarps;
+    const int kb = warp - kEpiW;
     const uint32_t idesc = make_idesc_bf16(kV2M, kWq);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);
     // probes: lane p < 16 watches cell warp p&7 (rows 2(p&7), 2(p&7)+1) of writer CTA p>>3 of the k-block's two
@@ -173,12 +179,15 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   } else {
     // ===================== cell adjoint =====================
     // TMEM read role: lane group lg = the 32 units sibling lg finalises, column half ch = 8 words of a quarter
-    const int lg = warp & 3, ch = warp >> 2;
+    const int eg = warp >> 3, w8 = warp & 7;        // epilogue group (owns the quarters q / kQPG == eg), warp inside the group
+    const bool leader = w8 == 0 && lane == 0;       // arms the group's reduction barriers
+    const bool tl0 = leader && eg == 0;             // timeline / trace thread
+    const int lg = w8 & 3, ch = w8 >> 2;
     const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(kV2AccCol + ch * 8);
     const uint32_t red_dst = mapa_u32(smem_u32(&S.red[0][g][lane][ch * 8]), (uint32_t)lg);
     const uint32_t bar_dst = mapa_u32(smem_u32(&S.red_full[0]), (uint32_t)lg);
     // cell role: unit pair a (units j, j+1) of word w of every quarter
-    const int a = lane & 15, w = (lane >> 4) + 2 * warp;
+    const int a = lane & 15, w = (lane >> 4) + 2 * w8;
     const int j = ugb * kV2M + g * 32 + 2 * a;
     const bool jvalid = j < kH;
     const size_t ll_off = ((size_t)((j >> 6) * kWq + w) * 64 + (size_t)(j & 63)) * 2;
@@ -187,12 +196,14 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 #pragma unroll
     for (int q = 0; q < NQ; ++q) dc[q][0] = dc[q][1] = 0.f;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
+    for (int q = 0; q < NQ; ++q)
+      if (q / kQPG == eg) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
     tmem_st_wait();
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int q = 0; q < NQ; ++q) mbar_arrive(&S.acc_free[q]);
+      for (int q = 0; q < NQ; ++q)
+        if (q / kQPG == eg) mbar_arrive(&S.acc_free[q]);
 
     TRACE_DECL
     for (int it = 0; it < T; ++it) {
@@ -226,11 +237,11 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
       // complete on the sibling's mbarrier)
       auto push_q = [&](int q) {
         float p[8];
-        if (tid == 0) mbar_arrive_expect_tx(&S.red_full[q], kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
+        if (leader) mbar_arrive_expect_tx(&S.red_full[q], kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
         TRACE(0)
-        if (tid == 0) TL(10, q, it)   // epilogue: starts waiting for the accumulator
+        if (tl0) TL(10, q, it)   // epilogue: starts waiting for the accumulator
         mbar_wait(&S.mma_done[q], (uint32_t)((it - 1) & 1), err);
-        if (tid == 0) TL(11, q, it)   // epilogue: accumulator complete
+        if (tl0) TL(11, q, it)   // epilogue: accumulator complete
         TRACE(1)
         tcgen05_fence_after();
         tmem_ld_x8(taddr + (uint32_t)(q * kWq), p);
@@ -244,7 +255,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         st_async_v4(red_dst + (uint32_t)(q * 4 * 32 * kRedStride * 4) + 16, p[4], p[5], p[6], p[7], bar_dst + (uint32_t)(q * 8));
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.acc_free[q]);
-        if (tid == 0) TL(14, q, it)   // epilogue: partial sums pushed
+        if (tl0) TL(14, q, it)   // epilogue: partial sums pushed
         TRACE(3)
       };
       // stage 2 of quarter q: sum the four partials, cell adjoint, publish da_t
@@ -260,7 +271,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         const float2 k_g = make_float2(s_i.x * (1.f - s_g.x * s_g.x), s_i.y * (1.f - s_g.y * s_g.y));
         if (it > 0) {
           mbar_wait_cluster(&S.red_full[q], (uint32_t)((it - 1) & 1), err);
-          if (tid == 0) TL(15, q, it)   // epilogue: partial sums of all four siblings arrived
+          if (tl0) TL(15, q, it)   // epilogue: partial sums of all four siblings arrived
           TRACE(4)
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
@@ -288,7 +299,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
           xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
         }
-        if (tid == 0) TL(12, q, it)   // epilogue: quarter published
+        if (tl0) TL(12, q, it)   // epilogue: quarter published
         TRACE(5)
         if (jvalid && wvalid) {   // off the critical path: bf16 images (A operand of the dX GEMM) and fp32 da_t over the stash
           if (img_seq != nullptr) {
@@ -309,35 +320,36 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
             *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
           }
         }
-        if (tid == 0) TL(13, q, it)   // epilogue: image / stash stores issued
+        if (tl0) TL(13, q, it)   // epilogue: image / stash stores issued
         TRACE(6)
       };
-      // software pipeline over the quarters: quarter q's push overlaps quarter q-1's wait for its partial sums
-      load_q(0);
+      // software pipeline over this group's quarters: quarter q's push overlaps quarter q-1's wait for its partial sums
+      load_q(eg * kQPG);
 #pragma unroll
       for (int st = 0; st <= NQ; ++st) {
-        if (st < NQ && it > 0 && (grp * NQ + st) * kWq < Bv) push_q(st);
-        if (st >= 1 && (grp * NQ + st - 1) * kWq < Bv) {
+        const bool own_st = st < NQ && st / kQPG == eg;
+        if (own_st && it > 0 && (grp * NQ + st) * kWq < Bv) push_q(st);
+        if (st >= 1 && (st - 1) / kQPG == eg && (grp * NQ + st - 1) * kWq < Bv) {
           finalize_q(st - 1);
-          if (st < NQ) load_q(st);
+          if (own_st) load_q(st);
         }
       }
     }
-    if (blockIdx.x == 0 && tid == 0) TRACE_DUMP(8)
+    if (blockIdx.x == 0 && tl0) TRACE_DUMP(8)
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kB2EpiWarps) tmem_dealloc<512>(tmem);
+  if (warp == kEpiW) tmem_dealloc<512>(tmem);
   cluster_sync_all2();   // no CTA exits while a sibling may still address its shared memory
 }
 
-template <int NQ>
+template <int NQ, int EG>
 int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                 void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
   static bool attr_set = false;
   const int smem = (int)sizeof(Bwd2Smem<NQ>) + 1024;
   if (!attr_set) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   // cooperative + cluster launch accepted by this driver?  (Nsight Compute rejects the combination with LaunchFailed;
@@ -355,7 +367,7 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
     const float* dlp = dh_last ? dh_last + r0 * kH : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(kBwd2Groups * 4 * ng);
-    cfg.blockDim = dim3(kB2Threads);
+    cfg.blockDim = dim3(b2_threads(EG));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = s;
     cudaLaunchAttribute attrs[2];
@@ -370,13 +382,13 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
     uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
                                        (int)r0, keep_da);
     if (e != cudaSuccess && coop_ok) {
       cudaGetLastError();
       coop_ok = 0;
       cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0, keep_da);
+      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0, keep_da);
     }
     PAULE_CUDA(e);
   }
@@ -385,12 +397,16 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
 
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
-  switch (choose_nq(B, kMaxQBwd)) {
-    case 1: return launch_bwd2<1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-    case 2: return launch_bwd2<2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-    case 3: return launch_bwd2<3>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-    default: return launch_bwd2<4>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-  }
+  // two quarters per CTA: two epilogue groups, one quarter each (4.57 -> 3.62 us per step at 128 words).  With three or four
+  // quarters a second group measured 4-6 % SLOWER (contiguous halves; 20 % slower interleaved) and is not used.
+  // PAULE_RNN_EG=1 restores one group everywhere (A/B timing).
+  static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
+  const int nq = choose_nq(B, kMaxQBwd);
+  if (nq == 1) return launch_bwd2<1, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+  if (nq == 2 && !one_group) return launch_bwd2<2, 2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+  if (nq == 2) return launch_bwd2<2, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+  if (nq == 3) return launch_bwd2<3, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+  return launch_bwd2<4, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
 }
 
 }  // namespace tc

@@ -109,8 +109,8 @@ struct Fwd2Smem {
   alignas(1024) uint8_t xb[2][NS * QS][kXBlockBytes];   // x_t / x_{t+1} operand blocks (double-buffered)
 };
 
-constexpr int kF2EpiWarps = 8;
-constexpr int kF2Threads = 32 * (kF2EpiWarps + kNumKB);   // 640
+constexpr int kF2EpiWarps = 8;                            // cell warps of ONE epilogue group: 4 TMEM lane groups x 2 column halves
+__host__ __device__ constexpr int f2_threads(int EG) { return 32 * (kF2EpiWarps * EG + kNumKB); }   // 640 (one group) / 896 (two)
 
 // A CTA carries NS x QS word quarters (16 words each) behind its resident weights.  The NS SLOTS are INDEPENDENT
 // recurrences (own accumulator, barriers, operand buffer, exchange blocks) visited round-robin by the loader and epilogue
@@ -123,8 +123,14 @@ constexpr int kF2Threads = 32 * (kF2EpiWarps + kNumKB);   // 640
 // real hidden units, i.e. one useful MMA -- issues the four x MMAs into the same accumulator; the epilogue adds the bias
 // from registers.  `gates` is then output only (the activated-gate stash): the [T,B,2880] pre-activation tensor is never
 // written to or read from HBM, and the x MMAs do not wait for the exchange.
-template <int NS, int QS, bool FUSED>
-__global__ void __launch_bounds__(kF2Threads, 1)
+//
+// EG: epilogue groups.  A quarter's cell pass is a dependent chain (TMEM load -> quad transpose -> activations -> publish ->
+// stash stores, ~1.25 us) that one group of 8 warps runs for the CTA's quarters one after the other; in the multi-slot layouts
+// that chain, not the tensor core or the exchange, bounds the CTA.  With EG = 2 a second group of 8
+// warps runs concurrently: it takes the SECOND quarter of every lock-step pair (QS = 2: both quarters of a slot are then
+// published after one cell pass instead of two, which is what the other CTAs wait for), or the odd slots when QS = 1.
+template <int NS, int QS, bool FUSED, int EG>
+__global__ void __launch_bounds__(f2_threads(EG), 1)
 tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed, float* __restrict__ h_out,
                     float* __restrict__ c_out, uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv,
                     int Bs, int w0, const uint8_t* __restrict__ packed_x, const uint8_t* __restrict__ x_img,
@@ -135,20 +141,24 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
   constexpr int kSW = kWq * QS;                        // words per slot (the MMA N)
   constexpr int kGW = kSW * NS;                        // words per CTA group
   constexpr int kBlk = QS * kLLBlockBytes;             // exchange block of one (slot, parity): [12 kb][16 QS rows][128 B]
+  constexpr int kEpiW = kF2EpiWarps * EG;              // epilogue warps of the CTA; loader warp kb is warp kEpiW + kb
+  constexpr int kF2Threads = f2_threads(EG);
+  static_assert(EG == 1 || EG == 2, "one or two epilogue groups");
+  constexpr bool kByQ = EG > 1 && QS == EG;            // group eg owns quarter eg of every slot (else: the slots s % EG == eg)
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int ug = blockIdx.x % kFwd2Groups, grp = blockIdx.x / kFwd2Groups;
   volatile int* err = reinterpret_cast<volatile int*>(xchg + kXchgErrOff);
   uint8_t* ll = xchg + kXchgHeader + (size_t)grp * NS * 2 * kBlk;   // [slot][parity] blocks of this group
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&S.mma_done[s], kNumKB); mbar_init(&S.acc_free[s], kF2EpiWarps); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&S.mma_done[s], kNumKB); mbar_init(&S.acc_free[s], kF2EpiWarps * (kByQ ? EG : 1)); }
     mbar_init(&S.xfull[0], 1);
     mbar_init(&S.xfull[1], 1);
     fence_mbar_init();
   }
   for (int i = tid; i < NS * QS * kV2BBytes / 16; i += kF2Threads) reinterpret_cast<uint4*>(&S.b[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_shared();
-  if (warp == kF2EpiWarps) tmem_alloc<512>(&S.tmem_base);
+  if (warp == kEpiW) tmem_alloc<512>(&S.tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -162,9 +172,9 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
   __syncthreads();
   tcgen05_fence_after();
 
-  if (warp >= kF2EpiWarps) {
+  if (warp >= kEpiW) {
     // ===================== loader + MMA issuer of k-block kb =====================
-    const int kb = warp - kF2EpiWarps;
+    const int kb = warp - kEpiW;
     const uint32_t idesc = make_idesc_bf16(kV2M, kSW);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);   // A operand: 32 columns per k-block, 8 per K = 16
     const bool xwarp = FUSED && kb == kNumKB - 1;   // this warp also feeds the fused input projection
@@ -196,6 +206,8 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           // probes: lane p < 16 watches writer warp (CTA p>>3 of the k-block's two, lane group (p>>1)&3, column half p&1): its
           // lane 0 publishes row 8 (p&1) of every quarter, units 32 (p>>3) + 8 ((p>>1)&3) of the k-block; quarters are
           // published in order, so the probe sits in the last quarter of the slot that has this row
+          // (with two epilogue groups the quarters of a lock-step pair are published concurrently; probing BOTH quarters --
+          // 32 probing lanes -- measured slower, 6.3 against 5.6 us at 384 words: the fetch validates every value anyway)
           const int prow = (lane & 1) * 8;
           const int pq = prow < rows ? min(QS - 1, (rows - 1 - prow) / kWq) : 0;
           const uint32_t probe_off = (uint32_t)(((pq * kWq + prow) * 64 + ((lane >> 3) & 1) * 32 + ((lane >> 1) & 3) * 8) * 2);
@@ -252,7 +264,9 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     if (blockIdx.x == 0 && kb == 3 && lane == 0) TRACE_DUMP(0)
   } else {
     // ===================== epilogue: the LSTM cell =====================
-    const int lg = warp & 3, ch = warp >> 2;        // TMEM lane group (32 gate rows = 8 units), column half (8 words)
+    const int eg = warp >> 3;                       // epilogue group: owns the slots s with s % EG == eg
+    const int lg = warp & 3, ch = (warp >> 2) & 1;  // TMEM lane group (32 gate rows = 8 units), column half (8 words)
+    const bool tl0 = (warp & 7) == 0 && lane == 0 && eg == 0;   // timeline / trace thread
     const int gq = lane & 3, ul = lane >> 2;        // position in the quad = gate row held after the load; unit in the warp
     const int u = ug * 32 + lg * 8 + ul;
     const bool uvalid = u < kH;
@@ -270,13 +284,16 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     if (FUSED && uvalid)
       for (int g = 0; g < 4; ++g) bias4[g] = __ldg(bias + g * kH + u);
 
+    auto own = [&](int q) { return kByQ ? (q % QS == eg) : ((q / QS) % EG == eg); };   // quarters of this epilogue group
 #pragma unroll
-    for (int q = 0; q < NS * QS; ++q) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
+    for (int q = 0; q < NS * QS; ++q)
+      if (own(q)) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
     tmem_st_wait();
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int s = 0; s < NS; ++s) mbar_arrive(&S.acc_free[s]);
+      for (int s = 0; s < NS; ++s)
+        if (kByQ || s % EG == eg) mbar_arrive(&S.acc_free[s]);
 
     TRACE_DECL
     for (int t = 0; t < T; ++t) {
@@ -298,20 +315,22 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           for (int g = 0; g < 4; ++g) xp[g][k] = ok ? __ldg(grow + g * kH) : 0.f;
         }
       };
-      load_xp(0);
+      load_xp(kByQ ? eg : eg * QS);                // this group's first quarter
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
+        if (EG > 1 && !kByQ && s % EG != eg) continue;   // the other epilogue group's slot
         if (grp * kGW + s * kSW >= Bv) continue;   // empty slot (uniform over the CTA)
         const bool has_acc = FUSED || t > 0;
-        if (tid == 0) TL(10, s, t)   // epilogue: starts waiting for the slot's accumulator
+        if (tl0) TL(10, s, t)   // epilogue: starts waiting for the slot's accumulator
         if (has_acc) {
           mbar_wait(&S.mma_done[s], (uint32_t)((FUSED ? t : t - 1) & 1), err);
-          if (tid == 0) TL(11, s, t)   // epilogue: accumulator complete
+          if (tl0) TL(11, s, t)   // epilogue: accumulator complete
           TRACE(0)
           tcgen05_fence_after();
         }
 #pragma unroll
         for (int j = 0; j < QS; ++j) {
+          if (kByQ && j != eg) continue;                // the other epilogue group's quarter
           const int q = s * QS + j;                     // quarter inside the CTA
           const int wq = grp * kGW + q * kWq;           // first word of this quarter inside the launch
           float pre[4][2];
@@ -320,7 +339,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             tmem_ld_x8(taddr + (uint32_t)(q * kWq), acc);
             TRACE(1)
             if (t + 1 < T) tmem_zero_x8(taddr + (uint32_t)(q * kWq));   // re-arm: every MMA of the next step adds into it
-            if (j == QS - 1) {
+            if (kByQ || j == QS - 1) {                  // this group's last read of the slot's accumulator
               tmem_st_wait();
               tcgen05_fence_before();
               __syncwarp();
@@ -367,7 +386,10 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             hv[k] = go[k] * fast_tanh(fminf(fmaxf(cn[k], -15.f), 15.f));
             c_prev[q][k] = cn[k];
           }
-          if (q + 1 < NS * QS) load_xp(q + 1);   // next quarter's input projection while this one's results go out
+          // next quarter's input projection (this group's next one) while this one's results go out
+          if (kByQ) { if (s + 1 < NS) load_xp(q + QS); }
+          else if (j + 1 < QS) load_xp(q + 1);
+          else if (s + EG < NS) load_xp((s + EG) * QS);
           // pair neighbouring units (lane ^ 4) so that one thread owns {h[u], h[u+1]} of one word
           const float other = __shfl_xor_sync(0xffffffffu, e ? hv[0] : hv[1], 4);
           const __nv_bfloat162 pr = e ? __floats2bfloat162_rn(other, hv[1]) : __floats2bfloat162_rn(hv[0], other);
@@ -376,7 +398,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           if (t + 1 < T && pvalid)                      // critical path: the next step's operand
             xchg_store(ll + (size_t)(s * 2 + (t & 1)) * kBlk + ((size_t)((ug >> 1) * kSW + j * kWq + prow) * 64) * 2 + ll_unit,
                        payload | phase_bits(t));
-          if (tid == 0) TL(12, q, t)   // epilogue: quarter published
+          if (tl0) TL(12, q, t)   // epilogue: quarter published
           TRACE(3)
           // everything below is off the critical path: the next step is already fed
           if (img_seq != nullptr && uvalid && pvalid) {
@@ -398,16 +420,16 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
               if (h_out != nullptr) h_out[o] = hv[k];   // NULL: the caller only consumes the bf16 images of h
             }
           }
-          if (tid == 0) TL(13, q, t)   // epilogue: quarter's stash stores issued
+          if (tl0) TL(13, q, t)   // epilogue: quarter's stash stores issued
           TRACE(4)
         }
       }
     }
-    if (blockIdx.x == 0 && tid == 0) TRACE_DUMP(8)
+    if (blockIdx.x == 0 && tl0) TRACE_DUMP(8)
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kF2EpiWarps) tmem_dealloc<512>(tmem);
+  if (warp == kEpiW) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace tc
@@ -431,14 +453,14 @@ int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cu
   return PAULE_OK;
 }
 
-template <int NS, int QS, bool FUSED>
+template <int NS, int QS, bool FUSED, int EG>
 int launch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                 void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
   static bool attr_set = false;
   constexpr int NQ = NS * QS;
   const int smem = (int)sizeof(Fwd2Smem<NS, QS>) + 1024;
   if (!attr_set) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NS, QS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NS, QS, FUSED, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQ, NQ);
@@ -459,30 +481,41 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
     const uint8_t* pkx = reinterpret_cast<const uint8_t*>(packed) + kPackedXOff;
     const uint8_t* xi = reinterpret_cast<const uint8_t*>(x_img);
     void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bvi, &Bsi, &w0, &pkx, &xi, &bias, &Qtot};
-    PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NS, QS, FUSED>, dim3(kFwd2Groups * ng), dim3(kF2Threads),
-                                           args, (size_t)smem, s));
+    PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NS, QS, FUSED, EG>, dim3(kFwd2Groups * ng),
+                                           dim3(f2_threads(EG)), args, (size_t)smem, s));
   }
   return PAULE_OK;
 }
 
+// multi-slot layouts run two epilogue groups (PAULE_RNN_EG=1 restores one group: A/B timing).  Measured per step at
+// 128 / 192 / 256 / 384 / 1024 words: 3.19 / 3.51 / 4.65 / 6.13 / 18.4 us against 3.46 / 3.83 / 4.59 / 6.48 / 19.1 us with one
+// group; four independent slots (4,1) instead of two lock-step pairs (2,2): 6.42 us at 384 words, one lock-step pair (1,2)
+// instead of two slots (2,1): 4.40 against 3.23 us at 128 words -- no gain, not built.  Also measured and dropped: reading the
+// exchange block once before probing (the loader usually returns to a slot after its data has landed): +20-30 % per step.
+template <bool FUSED>
+int dispatch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
+                  void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+  static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
+  const int nq = choose_nq(B, kMaxQ);
+  if (nq == 1) return launch_fwd2<1, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  if (one_group) {
+    if (nq == 2) return launch_fwd2<2, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    if (nq == 3) return launch_fwd2<3, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+    return launch_fwd2<2, 2, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  }
+  if (nq == 2) return launch_fwd2<2, 1, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  if (nq == 3) return launch_fwd2<3, 1, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  return launch_fwd2<2, 2, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+}
+
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
                   cudaStream_t s) {
-  switch (choose_nq(B, kMaxQ)) {
-    case 1: return launch_fwd2<1, 1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-    case 2: return launch_fwd2<2, 1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-    case 3: return launch_fwd2<3, 1, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-    default: return launch_fwd2<2, 2, false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
-  }
+  return dispatch_fwd2<false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
 }
 
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                    void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
-  switch (choose_nq(B, kMaxQ)) {
-    case 1: return launch_fwd2<1, 1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    case 2: return launch_fwd2<2, 1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    case 3: return launch_fwd2<3, 1, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    default: return launch_fwd2<2, 2, true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-  }
+  return dispatch_fwd2<true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
 }
 
 int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s) {
