@@ -116,6 +116,9 @@ inline int64_t pass_words(int64_t B, int max_groups, int nq) {
 
 // Probe polling variants, measured at 64 words (forward step 2.42 us with the defaults): two probe loads in flight 2.75 us
 // (more polling traffic slows every exchange), a 40 / 120 ns back-off between failed probes 2.39 / 2.41 us (neutral).
+// Later A/B (same box, two builds each): 300 ns -> forward 2.27 -> 2.19 us at 64 words, but 1.74 -> 1.83 us at one word and
+// nothing in the backward or the multi-slot layouts; 600 ns is worse everywhere.  The forward kernel therefore backs off
+// 300 ns only when the launch has at least four word quarters polling (run-time argument of xchg_fetch_kblock).
 #ifndef PAULE_PROBE_PIPELINE
 #define PAULE_PROBE_PIPELINE 0
 #endif
@@ -147,7 +150,8 @@ __device__ __forceinline__ void load_weights_to_tmem(const uint8_t* __restrict__
 template <int NQ>
 __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int kb,
                                                   uint32_t phase, int lane, uint32_t probe_off, bool prober,
-                                                  int rows, volatile int* err, uint64_t* trace = nullptr) {
+                                                  int rows, volatile int* err, uint64_t* trace = nullptr,
+                                                  unsigned int backoff_ns = 0u) {
   // k-block 11 holds units 704..767: only 704..735 have a writer (chunks 0..3), the rest stays zero in shared memory
   const int c = lane & 7;
   const bool active = (kb < kNumKB - 1) || (c < 4);
@@ -172,6 +176,8 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
       if (__all_sync(0xffffffffu, ok)) break;
 #if PAULE_PROBE_BACKOFF_NS > 0
       __nanosleep(PAULE_PROBE_BACKOFF_NS);   // fewer polls in flight -> shorter L2 queues for the loads that matter
+#else
+      if (backoff_ns) __nanosleep(backoff_ns);   // caller's choice (see tc_lstm_fwd2.cu)
 #endif
 #endif
       if ((spin & 1023u) == 1023u) {

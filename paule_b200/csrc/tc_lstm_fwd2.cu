@@ -178,6 +178,8 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     const uint32_t idesc = make_idesc_bf16(kV2M, kSW);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);   // A operand: 32 columns per k-block, 8 per K = 16
     const bool xwarp = FUSED && kb == kNumKB - 1;   // this warp also feeds the fused input projection
+    // four or more single-slot word quarters polling at once: 300 ns between failed probes (tc_lstm.cuh)
+    const unsigned int backoff = (NS == 1 && gridDim.x >= 4 * kFwd2Groups) ? 300u : 0u;
     const int nk = (kb == kNumKB - 1) ? 1 : 4;       // k-block 11 holds 16 real units: one K = 16 step, the rest is padding
     const int q_first = w0 / kWq + grp * NS * QS;    // first global word quarter of this CTA (x image addressing)
     int nvq = 0;                                     // quarters of this CTA that hold words (a prefix)
@@ -217,11 +219,11 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           while ((xchg_load(src) & kPhaseMask) != phase_bits(t - 1)) {}   // split the fetch: until the first value is visible
           TRACE(0)
           uint64_t ftr[2] = {0, 0};
-          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr)) break;
+          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr, backoff)) break;
           tr_acc[6] += ftr[0] - tr_last;   // probe phase
           tr_acc[7] += ftr[1] * 1000;      // bulk passes (x1000 so that the printout shows passes per step)
 #else
-          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err)) break;
+          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, nullptr, backoff)) break;
 #endif
           TRACE(1)
           fence_proxy_async_shared();   // generic-proxy shared-memory writes -> async-proxy (tensor core) reads
@@ -406,6 +408,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             *reinterpret_cast<uint32_t*>(img_seq + ((size_t)(wg / kRows) * (size_t)T + t) * kXchgImageBytes +
                                          umma_offset(kRows, wg % kRows, u & ~1)) = payload;
           }
+#ifndef PAULE_EXPERIMENT_NO_STASH   // timing experiment only (results are then useless to the backward pass)
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int wp = wq + wl0 + k;
@@ -420,6 +423,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
               if (h_out != nullptr) h_out[o] = hv[k];   // NULL: the caller only consumes the bf16 images of h
             }
           }
+#endif
           if (tl0) TL(13, q, t)   // epilogue: quarter's stash stores issued
           TRACE(4)
         }
@@ -504,7 +508,7 @@ int dispatch_fwd2(float* gates, const void* packed, const float* bias, const voi
     return launch_fwd2<2, 2, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
   }
   if (nq == 2) return launch_fwd2<2, 1, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-  if (nq == 3) return launch_fwd2<3, 1, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  if (nq == 3) return launch_fwd2<3, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);   // 4.52 vs 4.61 us
   return launch_fwd2<2, 2, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
 }
 
