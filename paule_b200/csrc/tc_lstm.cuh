@@ -119,6 +119,8 @@ inline int64_t pass_words(int64_t B, int max_groups, int nq) {
 // Later A/B (same box, two builds each): 300 ns -> forward 2.27 -> 2.19 us at 64 words, but 1.74 -> 1.83 us at one word and
 // nothing in the backward or the multi-slot layouts; 600 ns is worse everywhere.  The forward kernel therefore backs off
 // 300 ns only when the launch has at least four word quarters polling (run-time argument of xchg_fetch_kblock).
+// Not polling at all for the first 400 / 700 / 1000 ns after the warp's own MMA issue (nothing can arrive sooner) changed
+// neither kernel (2.16-2.20 / 2.82-2.87 us): the polls that matter are the ones in flight when the data lands.
 #ifndef PAULE_PROBE_PIPELINE
 #define PAULE_PROBE_PIPELINE 0
 #endif
