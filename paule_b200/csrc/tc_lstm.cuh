@@ -119,6 +119,10 @@ inline int64_t pass_words(int64_t B, int max_groups, int nq) {
 // Later A/B (same box, two builds each): 300 ns -> forward 2.27 -> 2.19 us at 64 words, but 1.74 -> 1.83 us at one word and
 // nothing in the backward or the multi-slot layouts; 600 ns is worse everywhere.  The forward kernel therefore backs off
 // 300 ns only when the launch has at least four word quarters polling (run-time argument of xchg_fetch_kblock).
+// Forward launches of at most four words (one quarter, 23 CTAs, one 16-byte load per lane per k-block) poll with the block
+// read itself (prober = false for every lane, 300 ns between incomplete reads): the probe round trip disappears from the
+// chain -- 1.74 -> 1.63 us per step at one word.  With a full quarter (16 words) the same is 4 % slower (2.14 -> 2.22 us), at
+// 64 words 2.19 -> 2.55-2.74 us; in the backward kernel it is within noise (2.03 -> 2.00 us) and not used.
 // Not polling at all for the first 400 / 700 / 1000 ns after the warp's own MMA issue (nothing can arrive sooner) changed
 // neither kernel (2.16-2.20 / 2.82-2.87 us): the polls that matter are the ones in flight when the data lands.
 #ifndef PAULE_PROBE_PIPELINE
@@ -153,7 +157,7 @@ template <int NQ>
 __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int kb,
                                                   uint32_t phase, int lane, uint32_t probe_off, bool prober,
                                                   int rows, volatile int* err, uint64_t* trace = nullptr,
-                                                  unsigned int backoff_ns = 0u) {
+                                                  unsigned int backoff_ns = 0u, unsigned int reread_ns = 0u) {
   // k-block 11 holds units 704..767: only 704..735 have a writer (chunks 0..3), the rest stays zero in shared memory
   const int c = lane & 7;
   const bool active = (kb < kNumKB - 1) || (c < 4);
@@ -239,6 +243,7 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
       }
     }
 #endif
+    if (reread_ns && pending != 0u) __nanosleep(reread_ns);   // probe-less polling (single-quarter launches): pace the re-reads
     if ((spin & 255u) == 255u) {
       if (t0 == 0) t0 = globaltimer_ns();
       if (*err != 0) return false;

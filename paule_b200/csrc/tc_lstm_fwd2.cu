@@ -180,6 +180,10 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     const bool xwarp = FUSED && kb == kNumKB - 1;   // this warp also feeds the fused input projection
     // four or more single-slot word quarters polling at once: 300 ns between failed probes (tc_lstm.cuh)
     const unsigned int backoff = (NS == 1 && gridDim.x >= 4 * kFwd2Groups) ? 300u : 0u;
+    // a single word quarter with at most four words (one 16-byte load per lane covers the k-block): no probes, the block read
+    // itself is the poll (tc_lstm.cuh)
+    const bool solo = NS == 1 && gridDim.x == kFwd2Groups && Bv <= 4;
+    const unsigned int reread = solo ? 300u : 0u;
     const int nk = (kb == kNumKB - 1) ? 1 : 4;       // k-block 11 holds 16 real units: one K = 16 step, the rest is padding
     const int q_first = w0 / kWq + grp * NS * QS;    // first global word quarter of this CTA (x image addressing)
     int nvq = 0;                                     // quarters of this CTA that hold words (a prefix)
@@ -213,17 +217,17 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           const int prow = (lane & 1) * 8;
           const int pq = prow < rows ? min(QS - 1, (rows - 1 - prow) / kWq) : 0;
           const uint32_t probe_off = (uint32_t)(((pq * kWq + prow) * 64 + ((lane >> 3) & 1) * 32 + ((lane >> 1) & 3) * 8) * 2);
-          const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && (prow < rows);
+          const bool prober = !solo && lane < 16 && (kb < kNumKB - 1 || lane < 8) && (prow < rows);
           const uint8_t* src = ll + (size_t)(s * 2 + ((t - 1) & 1)) * kBlk + (size_t)kb * (kSW * 128);
 #ifdef PAULE_TC_TRACE
           while ((xchg_load(src) & kPhaseMask) != phase_bits(t - 1)) {}   // split the fetch: until the first value is visible
           TRACE(0)
           uint64_t ftr[2] = {0, 0};
-          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr, backoff)) break;
+          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, ftr, backoff, reread)) break;
           tr_acc[6] += ftr[0] - tr_last;   // probe phase
           tr_acc[7] += ftr[1] * 1000;      // bulk passes (x1000 so that the printout shows passes per step)
 #else
-          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, nullptr, backoff)) break;
+          if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(t - 1), lane, probe_off, prober, rows, err, nullptr, backoff, reread)) break;
 #endif
           TRACE(1)
           fence_proxy_async_shared();   // generic-proxy shared-memory writes -> async-proxy (tensor core) reads
