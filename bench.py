@@ -161,6 +161,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's own messages (e.g. the "NCCL version" banner of NCCL_DEBUG=VERSION) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     tc_ok = _lib.load().paule_tc_packed_lstm_bytes(HIDDEN, 30) > 0
