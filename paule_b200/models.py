@@ -36,16 +36,17 @@ class _PackedLSTM:
         self._key = None
         self.layers: List[ops.LstmWeights] = []
 
-    def get(self) -> List[ops.LstmWeights]:
+    def get(self, tc: bool = False) -> List[ops.LstmWeights]:
+        """tc: also hold the tcgen05 weight images (persistent-RNN kernels; hidden size 720 only)."""
         params = list(self.lstm.parameters())
-        key = _versions(params)
+        key = (_versions(params), bool(tc))
         if key != self._key:
             self.layers = []
             for k in range(self.lstm.num_layers):
                 self.layers.append(ops.LstmWeights(getattr(self.lstm, f"weight_ih_l{k}"),
                                                    getattr(self.lstm, f"weight_hh_l{k}"),
                                                    getattr(self.lstm, f"bias_ih_l{k}"),
-                                                   getattr(self.lstm, f"bias_hh_l{k}")))
+                                                   getattr(self.lstm, f"bias_hh_l{k}"), tc=tc))
             self._key = key
         return self.layers
 
@@ -80,10 +81,19 @@ def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights], lstm: nn.LSTM = N
         if learn:
             w_ih, w_hh = _param(getattr(lstm, f"weight_ih_l{k}")), _param(getattr(lstm, f"weight_hh_l{k}"))
             bias = _param(getattr(lstm, f"bias_ih_l{k}")) + _param(getattr(lstm, f"bias_hh_l{k}"))
-            h, _, _ = ops.lstm_layer_fwd(h, k == 0, w_ih, w_hh, bias)
         else:
-            h, _, _ = ops.lstm_layer_fwd(h, k == 0, L.w_ih, L.w_hh, L.bias)
+            w_ih, w_hh, bias = L.w_ih, L.w_hh, L.bias
+        if L.packed is not None:      # module.math = MATH_BF16: the persistent tcgen05 kernels (bf16 operands, fp32 state)
+            h, _, _ = ops.lstm_layer_fwd_tc(h, k == 0, w_ih, w_hh, bias, L.packed)
+        else:
+            h, _, _ = ops.lstm_layer_fwd(h, k == 0, w_ih, w_hh, bias)
     return h
+
+
+def _use_tc(module) -> bool:
+    """``module.math = ops.MATH_BF16`` selects the tensor-core recurrences for the module's own forward / backward (the fused
+    planner has its own ``math`` argument).  Only the hidden size the kernels are built for; fp32 otherwise."""
+    return getattr(module, "math", ops.MATH_FP32) != ops.MATH_FP32 and module.lstm.hidden_size == 720
 
 
 class ForwardModel(nn.Module):
@@ -100,7 +110,7 @@ class ForwardModel(nn.Module):
 
     def forward(self, x, *args):
         x = _check_input(x, "ForwardModel.forward(x)")
-        h = lstm_stack(x, self._pack.get(), self.lstm)
+        h = lstm_stack(x, self._pack.get(_use_tc(self)), self.lstm)
         if _learning(self.post_linear.parameters()):
             return ops.linear_tm(h, _param(self.post_linear.weight), _param(self.post_linear.bias),
                                  bool(self.apply_half_sequence), True)
@@ -129,7 +139,7 @@ class EmbeddingModel(nn.Module):
         if self.training and self.lstm.dropout > 0 and self.lstm.num_layers > 1:
             raise _lib.PauleB200Error("inter-layer LSTM dropout in training mode is not implemented on the CUDA path "
                                       "(Paule's embedder uses dropout=0: paule/paule.py:167)")
-        h = lstm_stack(x, self._pack.get())                                  # [T,B,H]
+        h = lstm_stack(x, self._pack.get(_use_tc(self)))                      # [T,B,H]
         B = x.shape[0]
         idx = torch.as_tensor([int(l) - 1 for l in lens], device=x.device, dtype=torch.long)
         if idx.numel() != B:
@@ -215,7 +225,7 @@ class InverseModelMelTimeSmoothResidual(nn.Module):
             cur = nxt
         feat = torch.empty((B, Tm, 3 * Cm), device=x.device, dtype=torch.float32)
         _lib.check(lib.paule_vel_acc_f32(cur.data_ptr(), feat.data_ptr(), B, Tm, Cm, st), "paule_vel_acc_f32")
-        h = lstm_stack(feat, self._pack.get())                                         # [Tm,B,H]
+        h = lstm_stack(feat, self._pack.get(_use_tc(self)))                                         # [Tm,B,H]
         y = ops.linear_tm(h, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias), False, True)  # [B,Tm,30]
         Cc = y.shape[2]
         nb = len(self.ResidualConvBlocks)
@@ -272,7 +282,7 @@ class MelEmbeddingModelMelSmoothResidualUpsampling(nn.Module):
             _lib.check(lib.paule_melconv_res_f32(cur.data_ptr(), w.data_ptr(), b.data_ptr(), nxt.data_ptr(), B, Tm, Cm,
                                                  st), "paule_melconv_res_f32")
             cur = nxt
-        h = lstm_stack(cur, self._pack.get())                                  # [T,B,H]
+        h = lstm_stack(cur, self._pack.get(_use_tc(self)))                                # [T,B,H]
         idx = torch.as_tensor([int(l) - 1 for l in lens], device=x.device, dtype=torch.long)
         if idx.numel() != B:
             raise ValueError(f"lens has {idx.numel()} entries for a batch of {B}")

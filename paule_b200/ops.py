@@ -202,6 +202,122 @@ def _lstm_layer_backward(ctx, dh, dgates, dc):
 lstm_layer_fwd.register_autograd(_lstm_layer_backward, setup_context=_lstm_layer_setup)
 
 
+# ---- the same layer on the persistent tcgen05 kernels (H = 720, bf16 operands / fp32 state): what ``module.math = MATH_BF16``
+# selects in paule_b200.models.  ``packed`` is LstmWeights(tc=True).packed.
+def _tc_scratch(lib, B: int, device) -> torch.Tensor:
+    """exchange scratch of one launch: zero-filled (its status word is sticky and starts at 0)"""
+    return torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=device)
+
+
+def _tc_check(xchg: torch.Tensor) -> None:
+    code = int(xchg[2048:2052].view(torch.int32).item())     # kXchgErrOff; one 4-byte read per model call
+    if code != 0:
+        raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")
+
+
+@torch.library.custom_op("paule_b200::lstm_layer_fwd_tc", mutates_args=())
+def lstm_layer_fwd_tc(x: torch.Tensor, batch_first_in: bool, w_ih: torch.Tensor, w_hh: torch.Tensor, bias: torch.Tensor,
+                      packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """lstm_layer_fwd on the tensor-core path: inputs of at most 64 channels (cps, mel, tube) go through the fused input
+    projection (paule_tc_x_image + paule_tc_lstm_seq_fwd_x), wider ones through the fp32 projection + paule_tc_lstm_seq_fwd."""
+    _chk(x, "x"); _chk(w_ih, "w_ih"); _chk(w_hh, "w_hh"); _chk(bias, "bias")
+    lib = _lib.load()
+    H = w_hh.shape[1]
+    if batch_first_in:
+        B, T, I = x.shape
+    else:
+        T, B, I = x.shape
+    gates = torch.empty((T, B, 4 * H), device=x.device, dtype=torch.float32)
+    h = torch.empty((T, B, H), device=x.device, dtype=torch.float32)
+    c = torch.empty((T, B, H), device=x.device, dtype=torch.float32)
+    if T * B == 0:
+        return h, gates, c
+    xchg = _tc_scratch(lib, B, x.device)
+    st = _stream()
+    if I <= 64:
+        x_tm = transpose_btc(x) if batch_first_in else x
+        ximg = torch.zeros(lib.paule_tc_x_image_bytes(T, B), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.paule_tc_x_image(x_tm.data_ptr(), ximg.data_ptr(), T, B, I, st), "paule_tc_x_image")
+        _lib.check(lib.paule_tc_lstm_seq_fwd_x(gates.data_ptr(), packed.data_ptr(), bias.data_ptr(), ximg.data_ptr(), h.data_ptr(),
+                                               c.data_ptr(), xchg.data_ptr(), None, T, B, MATH_BF16, st),
+                   "paule_tc_lstm_seq_fwd_x")
+    else:
+        a_map = (B, I, T * I) if batch_first_in else (1, I, 0)
+        linear_rows_(gates, x, w_ih, bias, T * B, a_map, (1, 4 * H, 0))
+        _lib.check(lib.paule_tc_lstm_seq_fwd(gates.data_ptr(), packed.data_ptr(), h.data_ptr(), c.data_ptr(), xchg.data_ptr(),
+                                             None, T, B, MATH_BF16, st), "paule_tc_lstm_seq_fwd")
+    _tc_check(xchg)
+    return h, gates, c
+
+
+@lstm_layer_fwd_tc.register_fake
+def _(x, batch_first_in, w_ih, w_hh, bias, packed):
+    if batch_first_in:
+        B, T, _ = x.shape
+    else:
+        T, B, _ = x.shape
+    H = w_hh.shape[1]
+    return x.new_empty((T, B, H)), x.new_empty((T, B, 4 * H)), x.new_empty((T, B, H))
+
+
+@torch.library.custom_op("paule_b200::lstm_layer_bwd_tc", mutates_args=())
+def lstm_layer_bwd_tc(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, w_ih_t: torch.Tensor, packed: torch.Tensor,
+                      batch_first_out: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """lstm_layer_bwd with the recurrence on the persistent tcgen05 BPTT kernel (paule_tc_lstm_seq_bwd)."""
+    _chk(dh, "dh"); _chk(gates, "gates"); _chk(c, "c")
+    lib = _lib.load()
+    T, B, H = dh.shape
+    I = w_ih_t.shape[0]
+    da = gates.clone()
+    dx = torch.empty((B, T, I) if batch_first_out else (T, B, I), device=dh.device, dtype=torch.float32)
+    if T * B == 0:
+        return dx, da
+    xchg = _tc_scratch(lib, B, dh.device)
+    _lib.check(lib.paule_tc_lstm_seq_bwd(da.data_ptr(), c.data_ptr(), packed.data_ptr(), dh.data_ptr(), 1, None, xchg.data_ptr(),
+                                         None, T, B, MATH_BF16, _stream()), "paule_tc_lstm_seq_bwd")
+    c_map = (B, I, T * I) if batch_first_out else (1, I, 0)
+    linear_rows_(dx, da, w_ih_t, None, T * B, (1, 4 * H, 0), c_map)
+    _tc_check(xchg)
+    return dx, da
+
+
+@lstm_layer_bwd_tc.register_fake
+def _(dh, gates, c, w_ih_t, packed, batch_first_out):
+    T, B, _ = dh.shape
+    I = w_ih_t.shape[0]
+    return dh.new_empty((B, T, I) if batch_first_out else (T, B, I)), torch.empty_like(gates)
+
+
+def _lstm_layer_tc_setup(ctx, inputs, output):
+    x, batch_first_in, w_ih, w_hh, bias, packed = inputs
+    h, gates, c = output
+    ctx.weight_grads = any(ctx.needs_input_grad[2:5])
+    if ctx.weight_grads:
+        ctx.save_for_backward(gates, c, w_ih, packed, x, h)
+    else:
+        ctx.save_for_backward(gates, c, w_ih, packed)
+    ctx.batch_first_in = batch_first_in
+
+
+def _lstm_layer_tc_backward(ctx, dh, dgates, dc):
+    gates, c, w_ih, packed = ctx.saved_tensors[:4]
+    if dh is None:
+        return None, None, None, None, None, None
+    dx, da = lstm_layer_bwd_tc(dh.contiguous(), gates, c, w_ih.t().contiguous(), packed, ctx.batch_first_in)
+    if not ctx.weight_grads:
+        return dx, None, None, None, None, None
+    x, h = ctx.saved_tensors[4:6]      # weight gradients as in _lstm_layer_backward (library GEMMs, outer-loop work)
+    T, B, G = da.shape
+    x_tm = x.transpose(0, 1) if ctx.batch_first_in else x
+    da2 = da.reshape(T * B, G)
+    d_w_ih = da2.t() @ x_tm.reshape(T * B, -1)
+    d_w_hh = da[1:].reshape((T - 1) * B, G).t() @ h[:-1].reshape((T - 1) * B, -1) if T > 1 else torch.zeros((G, h.shape[-1]), device=da.device)
+    return dx, None, d_w_ih, d_w_hh, da2.sum(0), None
+
+
+lstm_layer_fwd_tc.register_autograd(_lstm_layer_tc_backward, setup_context=_lstm_layer_tc_setup)
+
+
 @torch.library.custom_op("paule_b200::linear_tm", mutates_args=())
 def linear_tm(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, pool_pairs: bool, batch_first_out: bool
               ) -> torch.Tensor:

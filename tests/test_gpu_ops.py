@@ -249,3 +249,50 @@ def test_mel_embedding_model_matches_reference_golden(dev):
     y = m(torch.from_numpy(g["x"]).to(dev), [int(l) for l in g["lens"]])
     np.testing.assert_allclose(_np(y), g["y64"], atol=2e-5)
     np.testing.assert_allclose(_np(y), g["y32"].astype(np.float64), atol=2e-5)
+
+
+@pytest.mark.parametrize("B,T", [(2, 17), (70, 9)])
+def test_module_math_bf16_runs_the_tensor_core_recurrences(dev, B, T):
+    """``module.math = MATH_BF16``: ForwardModel / EmbeddingModel / InverseModel forward (and the input gradient) on the
+    persistent tcgen05 kernels against the same modules on the fp32 kernels.  Bounds as in test_gpu_tc.py (bf16 operands)."""
+    import paule_b200 as P
+    from paule_b200 import ops
+    torch.manual_seed(0)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=720).to(dev)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=720).to(dev)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=720).to(dev)
+    g = torch.Generator().manual_seed(B + T)
+    x = (torch.rand(B, T, 30, generator=g) - 0.5).to(dev)
+    mel = torch.rand(B, T // 2, 60, generator=g).to(dev)
+    lens = [T // 2] * B
+    out = {}
+    for math in (ops.MATH_FP32, ops.MATH_BF16):
+        for m in (pred, emb, inv):
+            m.math = math
+        xr = x.clone().requires_grad_()
+        y = pred(xr)                                         # [B,T//2,60]
+        sv = emb(y, lens)                                    # [B,300]: ForwardModel -> EmbeddingModel, as in the planner
+        (sv.square().sum() + y.square().sum()).backward()
+        with torch.no_grad():
+            cp = inv(mel)
+        out[math] = (y.detach(), sv.detach(), xr.grad.detach(), cp)
+    (y0, s0, g0, c0), (y1, s1, g1, c1) = out[ops.MATH_FP32], out[ops.MATH_BF16]
+    assert not torch.equal(y0, y1), "bf16 mode produced bit-identical results: the tensor-core path did not run"
+    np.testing.assert_allclose(y1.cpu().numpy(), y0.cpu().numpy(), atol=2e-3)
+    np.testing.assert_allclose(s1.cpu().numpy(), s0.cpu().numpy(), atol=2e-3)
+    np.testing.assert_allclose(c1.cpu().numpy(), c0.cpu().numpy(), atol=3e-3)
+    np.testing.assert_allclose(g1.cpu().numpy(), g0.cpu().numpy(), atol=2e-2 * g0.abs().max().item())
+    # weight gradients (continue-learning) flow through the tensor-core op as well
+    pred.math = ops.MATH_BF16
+    for p_ in pred.parameters():
+        p_.requires_grad_(True)
+        p_.grad = None            # (the loop above already accumulated into .grad: parameters require grad by default)
+    pred(x).square().sum().backward()
+    gw = pred.lstm.weight_hh_l0.grad
+    assert gw is not None and torch.isfinite(gw).all() and gw.abs().max() > 0
+    pred.math = ops.MATH_FP32
+    for p_ in pred.parameters():
+        p_.grad = None
+    pred(x).square().sum().backward()
+    gw0 = pred.lstm.weight_hh_l0.grad
+    np.testing.assert_allclose(gw.cpu().numpy(), gw0.cpu().numpy(), atol=3e-2 * gw0.abs().max().item())
