@@ -143,7 +143,7 @@ def run_reference(args):
                                        "(nn.LSTM/oneDNN + autograd + optim.Adam), batched with per-word losses"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -161,8 +161,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own messages (e.g. the "NCCL version" banner of NCCL_DEBUG=VERSION) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     tc_ok = _lib.load().paule_tc_packed_lstm_bytes(HIDDEN, 30) > 0
@@ -302,7 +300,7 @@ def run_ours(args):
             "loss_first_last": [loss_curve[0], loss_curve[-1]],
             "other": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -382,6 +380,19 @@ def dominant_kernel_roofline(planner, math, dev):
             "launches_timed": launches, "flops_per_launch": flops_seq / launches}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line) -> None:
+    """the one JSON line, on the process's original stdout"""
+    sys.stdout.flush()
+    text = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(text); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,6 +404,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # stdout carries exactly ONE JSON line: while the run is in progress file descriptor 1 points at stderr, so that anything
+    # a library writes there (e.g. NCCL's "NCCL version ..." banner, which ignores NCCL_DEBUG_FILE) cannot get in front of it
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
