@@ -29,9 +29,11 @@ constexpr int kSegPad = kKPad;       // padded columns per K segment (12 k-block
 // largest tile width <= 256 that is a multiple of 16 and divides the padded N -- except N = 720 (dX of embedder layer 1):
 // three 240-wide column tiles x 50 row tiles (cfg 2) are 150 tiles on 148 CTAs, i.e. two rounds for two tiles; five 144-wide
 // ones are 250 tiles = two rounds of a 40 % cheaper tile.  At large M the narrower tile re-reads A more often (+13 % on
-// that one GEMM at 256 words x 400 frames, 0.2 % of the step): the small-batch case wins.
+// that one GEMM at 256 words x 400 frames, 0.2 % of the step): the small-batch case wins.  N = 2880 (input projection of
+// embedder layer 1): 160-wide tiles measured fastest at both ends.
 __host__ __device__ inline int pick_bn(int n_pad) {
   if (n_pad == 720) return 144;
+  if (n_pad == 2880) return 160;   // measured (tools/gemm_time.py, 64 / 256 words): 240: 56.3 / 172 us, 192: 51.9 / 161, 160: 50.3 / 159, 144: 52.1 / 172
   for (int bn = 256; bn >= 16; bn -= 16)
     if (n_pad % bn == 0) return bn;
   return 16;
