@@ -263,3 +263,36 @@ def test_generator_prologue_modes(dev, models, golden):
         want_mel = pm.mel_gen_model(noise, Tm, tsv)
     np.testing.assert_allclose(res2.target_mel, _np(want_mel), atol=1e-6)
     assert np.isfinite(np.asarray(res2.planned_loss_steps)).all()
+
+
+@pytest.mark.parametrize("math", [0, 1])
+def test_classifier_with_ragged_batch_equals_words_planned_alone(dev, models, branch_models, math):
+    """The fused classifier term averages over each word's OWN mel frames: every word of a ragged batch (padded, with
+    non-zero padding content) equals the same word planned alone, classifier term and cps included."""
+    from paule_b200 import BatchPlanner
+    pred, emb, _ = models
+    cls = branch_models[3]
+    lengths = [40, 64, 51, 26]
+    g = torch.Generator().manual_seed(17)
+    T = max(lengths)
+    cps = [torch.rand((L, 30), generator=g) - 0.5 for L in lengths]
+    mels = [torch.rand((L // 2, 60), generator=g) for L in lengths]
+    cp0, tmel = torch.full((len(lengths), T, 30), 0.21), torch.full((len(lengths), T // 2, 60), 3.0)
+    for b, (c, m) in enumerate(zip(cps, mels)):
+        cp0[b, :c.shape[0]] = c
+        tmel[b, :m.shape[0]] = m
+    n = 4
+    pl = BatchPlanner(pred, emb, cp0.to(dev), tmel.to(dev), None, max_log_steps=n, math=math, lengths=lengths,
+                      speech_classifier=cls)
+    pl.step(n)
+    cp_b, L_b = _np(pl.planned_cp()), {k: _np(v) for k, v in pl.losses().items()}
+    assert np.isfinite(cp_b).all() and np.isfinite(L_b["total"]).all()
+    cp_tol, loss_tol = (5e-6, 1e-5) if math == 0 else (3e-5, 2e-4)
+    for b, L in enumerate(lengths):
+        solo = BatchPlanner(pred, emb, cps[b][None].to(dev), mels[b][None].to(dev), None, max_log_steps=n, math=math,
+                            speech_classifier=cls)
+        solo.step(n)
+        np.testing.assert_allclose(cp_b[b, :L], _np(solo.planned_cp())[0], atol=cp_tol, err_msg=f"word {b} (T={L})")
+        for k in ("total", "mel", "semvec", "speech_classifier"):
+            np.testing.assert_allclose(L_b[k][:, b], _np(solo.losses()[k])[:, 0], rtol=loss_tol, atol=1e-6, err_msg=f"{k} word {b}")
+        solo.close()
