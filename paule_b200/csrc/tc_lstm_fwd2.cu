@@ -178,8 +178,12 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
     const uint32_t idesc = make_idesc_bf16(kV2M, kSW);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);   // A operand: 32 columns per k-block, 8 per K = 16
     const bool xwarp = FUSED && kb == kNumKB - 1;   // this warp also feeds the fused input projection
-    // four or more single-slot word quarters polling at once: 300 ns between failed probes (tc_lstm.cuh)
-    const unsigned int backoff = (NS == 1 && gridDim.x >= 4 * kFwd2Groups) ? 300u : 0u;
+    // four or more single-slot word quarters polling at once: 300 ns between failed probes (tc_lstm.cuh); sweep at 64 words:
+    // 0 / 200 ns 2.27 / 2.30 us per step, 300 / 400 / 500 ns 2.20, 600 ns 2.37
+#ifndef PAULE_FWD_BACKOFF_NS
+#define PAULE_FWD_BACKOFF_NS 300
+#endif
+    const unsigned int backoff = (NS == 1 && gridDim.x >= 4 * kFwd2Groups) ? (unsigned int)PAULE_FWD_BACKOFF_NS : 0u;
     // a single word quarter with at most four words (one 16-byte load per lane covers the k-block): no probes, the block read
     // itself is the poll (tc_lstm.cuh)
     const bool solo = NS == 1 && gridDim.x == kFwd2Groups && Bv <= 4;
