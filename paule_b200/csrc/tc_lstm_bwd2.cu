@@ -135,6 +135,12 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);
     // probes: lane p < 16 watches cell warp p&7 (rows 2(p&7), 2(p&7)+1) of writer CTA p>>3 of the k-block's two
     const uint32_t probe_off = (uint32_t)(((lane & 7) * 2 * 64 + ((lane >> 3) & 1) * 32) * 2);
+    // back-off between failed probes (as in the forward kernel): 400 / 500 ns measured within noise of none (2.81-2.86 us per
+    // step at 64 words), 800 ns 3.16 us -- off by default
+#ifndef PAULE_BWD_BACKOFF_NS
+#define PAULE_BWD_BACKOFF_NS 0
+#endif
+    const unsigned int bwd_backoff = (NQ == 1 && gridDim.x >= 4 * 4 * kBwd2Groups) ? (unsigned int)PAULE_BWD_BACKOFF_NS : 0u;
     TRACE_DECL
     for (int it = 1; it < T; ++it) {
 #pragma unroll
@@ -148,12 +154,12 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         if (kb == 3 && lane == 0) TL(1, q, it)   // loader: quarter visit starts
 #ifdef PAULE_TC_TRACE
         uint64_t ftr[2] = {0, 0};
-        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr)) break;
+        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr, bwd_backoff)) break;
         tr_acc[0] += ftr[0] - tr_last;   // until the probes pass
         tr_last = ftr[0];
         TRACE(1)
 #else
-        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err)) break;
+        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, nullptr, bwd_backoff)) break;
 #endif
         fence_proxy_async_shared();
         __syncwarp();
