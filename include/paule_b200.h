@@ -292,6 +292,11 @@ PAULE_API size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, int
  * (an inter-CTA wait exceeded 4 s) and the results are invalid -- the library never hangs the GPU, the caller must check
  * this word before trusting results.  (size_t)-1 when the configuration has no such word (fp32 math). */
 PAULE_API size_t paule_plan_status_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);
+/* Byte offset inside the workspace of d(mel + semvec terms)/d(cp), [T,B,C] fp32 time-major, as the last paule_plan_step left
+ * it: the BPTT result alone (xx_new.grad of paule.py:1052 minus the smoothness terms' gradient, which the Adam kernel adds). */
+PAULE_API size_t paule_plan_grad_lstm_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);
+/* EmbeddingModel forward on a time-major mel [Tm,B,Cm] -> sv [B,S] (target semvec, paule.py:533-535), in the plan's math. */
+PAULE_API int paule_plan_embed(const paule_plan* p, const float* mel, float* sv, paule_stream_t stream);
 /* forward only (no_grad predictions: paule.py:822-824, :1460-1464): fills pred_mel, pred_sv. */
 PAULE_API int paule_plan_forward(const paule_plan* p, paule_stream_t stream);
 /* one full inner step. */

@@ -343,6 +343,37 @@ def plan_inner_loop(pred: nn.Module, emb: nn.Module, cp0: torch.Tensor, target_m
     return out
 
 
+def model_path_grad(pred: nn.Module, emb: nn.Module, cp: torch.Tensor, target_mel: torch.Tensor,
+                    target_sv: Optional[torch.Tensor] = None, objective: str = "acoustic_semvec",
+                    lens: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """d(mel term + semvec term)/d(cp) [B,T,30] by autograd: ``xx_new.grad`` of paule/paule.py:1052 WITHOUT the velocity /
+    jerk / local-linear terms, i.e. exactly what the LSTM BPTT kernels have to produce.  On the synthetic inputs this part is
+    10^4..10^6 times smaller than the smoothness gradient, so a parity test on the total gradient cannot see it.
+
+    ``lens`` (cp frames per word, ragged batches): word b is evaluated alone on its own ``lens[b]`` frames, as the reference
+    does (one word per call); its gradient is zero on the padding."""
+    B, T, _ = cp.shape
+    g = torch.zeros_like(cp)
+    words = range(B)
+    for b in words:
+        L = T if lens is None else int(lens[b])
+        x = cp[b:b + 1, :L].clone().requires_grad_()
+        tm = target_mel[b:b + 1, :L // 2]
+        ln = (torch.tensor(L // 2),)
+        with torch.no_grad():
+            tsv = emb(tm, ln) if target_sv is None else target_sv[b:b + 1]
+        mel = pred(x)
+        loss = x.new_zeros(())
+        if objective in ("acoustic_semvec", "acoustic"):
+            loss = loss + MEL_WEIGHT * ((mel - tm) ** 2).mean().sqrt()
+        if objective in ("acoustic_semvec", "semvec"):
+            sv = emb(mel, ln)
+            loss = loss + SEMANTIC_WEIGHT * ((sv - tsv) ** 2).mean().sqrt()
+        loss.backward()
+        g[b, :L] = x.grad
+    return g
+
+
 # ----------------------------------------------------------------------------------------------
 # optional loss branches (SURVEY 8f N4): speech classifier and somatosensory feedback
 # ----------------------------------------------------------------------------------------------

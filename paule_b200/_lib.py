@@ -73,6 +73,8 @@ SIGNATURES = {
     "paule_tc_lstm_seq_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, i64, i64, C.c_int, vp]),
     "paule_plan_status_offset": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
     "paule_plan_workspace_bytes": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
+    "paule_plan_grad_lstm_offset": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
+    "paule_plan_embed": (C.c_int, [C.POINTER(Plan), vp, vp, vp]),
     "paule_plan_forward": (C.c_int, [C.POINTER(Plan), vp]),
     "paule_plan_step": (C.c_int, [C.POINTER(Plan), vp]),
 }

@@ -55,4 +55,14 @@ constexpr float kClassifierWeight = 0.1f;   // SPEECH_CLASSIFIER_WEIGHT, paule/p
 
 int sm_count();
 
+// true the first time it is called on the current device with this mask (per-kernel cudaFuncSetAttribute calls are
+// per device: a process that drives several GPUs must repeat them on each)
+inline bool once_per_device(unsigned long long& mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 63) return true;
+  if ((mask >> d) & 1ull) return false;
+  mask |= 1ull << d;
+  return true;
+}
+
 }  // namespace paule

@@ -252,20 +252,18 @@ extern "C" int paule_linear_f32(const float* A, const float* W, const float* bia
                      (c_inner == 1 ? c_outer_stride == N : (c_inner_stride == N && c_outer_stride == c_inner * N));
   if (plain && M <= 64 && N >= 64 && K <= 2048) {
     const size_t smem = (size_t)8 * K * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0ull;
+    if (once_per_device(attr_set)) {
       PAULE_CUDA(cudaFuncSetAttribute(linear_fewrows_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4));
-      attr_set = true;
     }
     linear_fewrows_f32_kernel<<<dim3((unsigned)ceil_div(N, 8), (unsigned)ceil_div(M, 8)), 256, smem, as_stream(stream)>>>(
         A, W, bias, C, (int)M, N, (int)K, accumulate);
   } else if (plain && K <= 64 && M >= 256 && N >= 64) {
     const size_t smem = (size_t)K * (kSkM + kSkPad + kSkN + kSkPad) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0ull;
+    if (once_per_device(attr_set)) {
       PAULE_CUDA(cudaFuncSetAttribute(linear_skinny_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       64 * (kSkM + kSkPad + kSkN + kSkPad) * 4));
-      attr_set = true;
     }
     dim3 grid((unsigned)ceil_div(N, kSkN), (unsigned)ceil_div(M, kSkM));
     linear_skinny_f32_kernel<<<grid, 256, smem, as_stream(stream)>>>(A, W, bias, C, M, N, (int)K, accumulate);

@@ -125,8 +125,27 @@ int project_and_recur(const paule_plan* p, const paule_lstm_layer& L, const floa
   return recur_forward(p, L, steps, gates, h, c, w, h_img, s);
 }
 
+// EmbeddingModel (models.py:440-448) on a time-major mel [Tm,B,Cm] -> sv [B,S]; lens = Tm for every word (paule.py:922-924)
+// or the word's own last frame (ragged batches)
+int embed_models(const paule_plan* p, const Workspace& w, const float* mel, float* sv, paule_stream_t s) {
+  const int64_t B = p->B, H = p->H, Tm = p->T / 2, S = p->S;
+  PAULE_TRY(project_and_recur(p, p->emb0, mel, Tm, w.gates_0, w.h_0, w.c_0, w, w.x_img_0, w.h_img, s));
+  if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
+    PAULE_TRY(paule_tc_gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, s));
+  } else {
+    PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
+  }
+  PAULE_TRY(recur_forward(p, p->emb1, Tm, w.gates_1, w.h_1, w.c_1, w, nullptr, s));
+  const float* h_last = w.h_1 + (Tm - 1) * B * H;
+  if (p->word_frames) {   // ragged: every word's own last mel frame (models.py:442); dh1_last is free until the backward
+    PAULE_TRY(gather_last(w.h_1, p->word_frames, w.dh1_last, B, H, s));
+    h_last = w.dh1_last;
+  }
+  return paule_linear_f32(h_last, p->head_w, p->head_b, sv, B, S, H, 1, H, 0, 0, 1, S, 0, 0, s);
+}
+
 int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s) {
-  const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, C = p->C, Cm = p->Cm, S = p->S;
+  const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, Cm = p->Cm;
   // ForwardModel (models.py:348-356): K = 30 input projection + recurrence
   const bool tc_post = tc(p) && p->post_packed != nullptr && (T % 2 == 0);
   PAULE_TRY(project_and_recur(p, p->fwd, p->cp, T, w.gates_f, w.h_f, w.c_f, w, w.x_img_f, tc_post ? w.hf_img : nullptr, s));
@@ -139,21 +158,7 @@ int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, pa
                                0, 0, s));
   }
   if (!need_semvec) return PAULE_OK;
-  // EmbeddingModel (models.py:440-448), lens = Tm for every word (paule.py:922-924)
-  PAULE_TRY(project_and_recur(p, p->emb0, p->pred_mel, Tm, w.gates_0, w.h_0, w.c_0, w, w.x_img_0, w.h_img, s));
-  if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
-    PAULE_TRY(paule_tc_gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, s));
-  } else {
-    PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
-  }
-  PAULE_TRY(recur_forward(p, p->emb1, Tm, w.gates_1, w.h_1, w.c_1, w, nullptr, s));
-  const float* h_last = w.h_1 + (Tm - 1) * B * H;
-  if (p->word_frames) {   // ragged: every word's own last mel frame (models.py:442); dh1_last is free until the backward
-    PAULE_TRY(gather_last(w.h_1, p->word_frames, w.dh1_last, B, H, s));
-    h_last = w.dh1_last;
-  }
-  PAULE_TRY(paule_linear_f32(h_last, p->head_w, p->head_b, p->pred_sv, B, S, H, 1, H, 0, 0, 1, S, 0, 0, s));
-  return PAULE_OK;
+  return embed_models(p, w, p->pred_mel, p->pred_sv, s);
 }
 
 }  // namespace
@@ -170,6 +175,22 @@ extern "C" size_t paule_plan_status_offset(int64_t B, int64_t T, int64_t H, int6
   if (B <= 0 || T <= 0 || H <= 0 || math == PAULE_MATH_FP32) return (size_t)-1;
   const Workspace w = carve(reinterpret_cast<void*>(uintptr_t(256)), B, T, H, C, Cm, S, math);
   return (size_t)(reinterpret_cast<uintptr_t>(w.xchg) - 256) + 2048;   // kXchgErrOff
+}
+
+// Byte offset inside the workspace of the model-path gradient d(mel + semvec terms)/d(cp) [T,B,C] fp32 of the last
+// paule_plan_step (the BPTT result before the smoothness gradients are added in the Adam kernel).
+extern "C" size_t paule_plan_grad_lstm_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math) {
+  if (B <= 0 || T <= 0 || H <= 0) return (size_t)-1;
+  const Workspace w = carve(reinterpret_cast<void*>(uintptr_t(256)), B, T, H, C, Cm, S, math);
+  return (size_t)(reinterpret_cast<uintptr_t>(w.dcp_lstm) - 256);
+}
+
+// semvec of a time-major mel [Tm,B,Cm] through the plan's embedder (target semvec, paule.py:533-535; produced mels, :1139)
+extern "C" int paule_plan_embed(const paule_plan* p, const float* mel, float* sv, paule_stream_t stream) {
+  PAULE_TRY(check_plan(p));
+  PAULE_REQUIRE(mel && sv);
+  const Workspace w = carve(p->workspace, p->B, p->T, p->H, p->C, p->Cm, p->S, p->math);
+  return embed_models(p, w, mel, sv, stream);
 }
 
 extern "C" int paule_plan_forward(const paule_plan* p, paule_stream_t stream) {

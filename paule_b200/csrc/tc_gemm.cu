@@ -245,10 +245,10 @@ extern "C" int paule_tc_gemm_img(const void* a_img, const void* packed_b, const 
   const int n_groups = (int)((B + kRows - 1) / kRows), n_pairs = (int)((steps + 1) / 2);
   const int64_t total = (int64_t)n_groups * n_pairs * (np / bn);
   const int smem = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
+  static unsigned long long attr_set = 0ull;
+  if (once_per_device(attr_set)) {   // the widest tile (BN = 256) bounds every launch
+    const int smem_max = kGemmStages * (16384 + 256 * 128) + (int)sizeof(GemmBars) + 1024 + 16;
+    PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   }
   const int grid = (int)((total < (int64_t)sm_count()) ? total : (int64_t)sm_count());
   tc_gemm_img_kernel<<<grid, kGemmThreads, (size_t)smem, as_stream(stream)>>>(

@@ -1,4 +1,4 @@
-// Shapes of the H=720 persistent-RNN kernels (forward: tc_lstm_fwd.cu, backward: tc_lstm_bwd.cu).
+// Shapes of the H=720 persistent-RNN kernels (forward: tc_lstm_fwd2.cu, backward: tc_lstm_bwd2.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,26 +40,14 @@ constexpr unsigned int kTlMax = 62;
 constexpr int kH = 720;                 // hidden size the tensor-core path is built for (paule/paule.py:124,167)
 constexpr int kKPad = 768;              // K padded to 12 k-blocks of 64
 constexpr int kNumKB = kKPad / 64;      // 12
-constexpr int kRows = 64;               // batch rows per launch (UMMA M)
+constexpr int kRows = 64;               // words per image group (rows of a bf16 UMMA image, the batched GEMMs' half M tile)
 
-// forward: 90 CTAs x 8 hidden units, B operand [N=32 (4 gates x 8 units), K=768]
-constexpr int kFwdUnits = 8;
-constexpr int kFwdCtas = kH / kFwdUnits;            // 90
-constexpr int kFwdN = 4 * kFwdUnits;                // 32
-constexpr int kFwdSliceBytes = kNumKB * kFwdN * 128;  // 49152
-
-// backward: 23 unit groups x 4 gates = 92 CTAs in clusters of 4 (split-K over the gates),
-// B operand [N=32 units, K=768 (the units k of gate g)]
-constexpr int kBwdN = 32;
-constexpr int kBwdGroups = (kH + kBwdN - 1) / kBwdN;  // 23
-constexpr int kBwdCtas = kBwdGroups * 4;              // 92
-constexpr int kBwdSliceBytes = kNumKB * kBwdN * 128;  // 49152
-
-// exchange buffer: header + UMMA images [12][64 rows][128 B]
-constexpr int kXchgHeader = 4096;   // 12 barrier counters (one 128-byte line per k-block), error flag, trace words
-constexpr int kXchgErrOff = 2048;    // int: 0 ok, 1 grid-barrier watchdog fired, 2 mbarrier watchdog fired
+// exchange buffer: header + exchange blocks
+constexpr int kXchgHeader = 4096;   // status word, trace / timeline words
+constexpr int kXchgErrOff = 2048;    // int: 0 ok, 1 exchange watchdog fired, 2 mbarrier watchdog fired, 3 (sticky, informational:
+                                     // results stay valid up to the stated bound) a recurrent gradient was clamped / non-finite
 constexpr int kXchgTraceOff = 3072;  // PAULE_TC_TRACE builds only
-constexpr int kXchgImageBytes = kNumKB * kRows * 128;  // 98304
+constexpr int kXchgImageBytes = kNumKB * kRows * 128;  // 98304: one bf16 image [12 kb][64 rows][128 B]
 
 // ---- v2 persistent kernels (tc_lstm_fwd2.cu / tc_lstm_bwd2.cu): weights are the resident A operand (M = 128 rows),
 // 16 words are the N dimension, and the recurrent state travels between CTAs as 8-byte {bf16x2, step tag} elements
@@ -80,8 +68,7 @@ constexpr int kLLBlockBytes = kNumKB * kWq * 128;     // 24576
 constexpr size_t kLLBytes = (size_t)kMaxQ * 4 * 2 * 4 * kLLBlockBytes;   // up to 6 groups x 4 quarters; backward: 4 gate images per parity
 
 // offsets of the v2 weight images inside the packed buffer of one layer
-constexpr size_t kPackedV1Bytes = (size_t)kFwdCtas * kFwdSliceBytes + (size_t)kBwdCtas * kBwdSliceBytes;
-constexpr size_t kPackedFwd2Off = kPackedV1Bytes;
+constexpr size_t kPackedFwd2Off = 0;
 constexpr size_t kPackedBwd2Off = kPackedFwd2Off + (size_t)kFwd2Groups * kV2SliceBytes;
 // fused input projection (K = input_size <= 64 padded to 64): per forward CTA a [128 gate rows, 64] bf16 slice = 32 more
 // TMEM columns behind the W_hh slice, stored in the same tcgen05.st order [4 column octets][128 rows][8 x u32]
@@ -257,7 +244,7 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
 // ones put 2 or 4 quarters on a CTA (the grid is limited to 6 / 5 groups, so this is what scales the throughput)
 #endif  // __CUDACC__
 
-// host entry points of the v2 kernels (dispatched from paule_tc_lstm_seq_fwd / _bwd; PAULE_RNN_V1=1 keeps the v1 kernels)
+// host entry points of the kernels (called from the C ABI in tc_lstm_api.cu)
 int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cudaStream_t s);
 int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s);
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
@@ -267,8 +254,6 @@ int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const vo
                    void* h_img_seq, int64_t T, int64_t B, cudaStream_t s);
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s);
-inline bool use_v1_fwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_FWD_V1") != nullptr; return v; }
-inline bool use_v1_bwd() { static const bool v = getenv("PAULE_RNN_V1") != nullptr || getenv("PAULE_RNN_BWD_V1") != nullptr; return v; }
 
 }  // namespace tc
 }  // namespace paule

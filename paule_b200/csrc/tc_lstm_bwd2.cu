@@ -304,6 +304,13 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           xchg_store(dst + 1 * (size_t)kLLBlockBytes, xchg_clamped(d_f) | ph);
           xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
           xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
+          // off the critical path: a gradient beyond the +-1.5 exchange bound (or NaN / Inf) was clamped above -- record it
+          // (sticky status 3; the watchdog codes 1 / 2 take priority) so that the caller learns its results deviate
+          const float mx = fmaxf(fmaxf(fmaxf(fabsf(d_i.x), fabsf(d_i.y)), fmaxf(fabsf(d_f.x), fabsf(d_f.y))),
+                                 fmaxf(fmaxf(fabsf(d_g.x), fabsf(d_g.y)), fmaxf(fabsf(d_o.x), fabsf(d_o.y))));
+          const bool nan = (d_i.x != d_i.x) || (d_i.y != d_i.y) || (d_f.x != d_f.x) || (d_f.y != d_f.y) || (d_g.x != d_g.x) ||
+                           (d_g.y != d_g.y) || (d_o.x != d_o.x) || (d_o.y != d_o.y);
+          if (!(mx < 1.5f) || nan) atomicCAS(reinterpret_cast<int*>(xchg + kXchgErrOff), 0, 3);
         }
         if (tl0) TL(12, q, it)   // epilogue: quarter published
         TRACE(5)
@@ -352,15 +359,14 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 template <int NQ, int EG>
 int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                 void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
-  static bool attr_set = false;
+  static unsigned long long attr_set = 0ull;
   const int smem = (int)sizeof(Bwd2Smem<NQ>) + 1024;
-  if (!attr_set) {
+  if (once_per_device(attr_set)) {
     PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
-  // cooperative + cluster launch accepted by this driver?  (Nsight Compute rejects the combination with LaunchFailed;
-  // PAULE_NO_COOP_CLUSTER=1 launches with the cluster attribute only -- at most 120 CTAs always fit the 148 SMs.)
-  static int coop_ok = getenv("PAULE_NO_COOP_CLUSTER") ? 0 : 1;
+  // Cluster launch WITHOUT the cooperative attribute: at most 120 CTAs (30 clusters of 4, one CTA per SM by shared memory and
+  // TMEM) always fit the 132 cluster-schedulable SMs, so every CTA is co-resident without the co-residency check -- and
+  // Nsight Compute rejects the cooperative + cluster combination (round 1: the driver's ncu pass over smoke() died here).
   const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQBwd, NQ);
   for (int64_t r0 = 0; r0 < B; r0 += pw) {
     const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
@@ -376,27 +382,18 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
     cfg.blockDim = dim3(b2_threads(EG));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = s;
-    cudaLaunchAttribute attrs[2];
+    cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = 4;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
-    attrs[1].id = cudaLaunchAttributeCooperative;
-    attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = coop_ok ? 2 : 1;
+    cfg.numAttrs = 1;
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
     uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
-                                       (int)r0, keep_da);
-    if (e != cudaSuccess && coop_ok) {
-      cudaGetLastError();
-      coop_ok = 0;
-      cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B, (int)r0, keep_da);
-    }
-    PAULE_CUDA(e);
+    PAULE_CUDA(cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
+                                  (int)r0, keep_da));
   }
   return PAULE_OK;
 }

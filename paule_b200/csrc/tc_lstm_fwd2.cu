@@ -468,12 +468,11 @@ int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cu
 template <int NS, int QS, bool FUSED, int EG>
 int launch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                 void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
-  static bool attr_set = false;
+  static unsigned long long attr_set = 0ull;
   constexpr int NQ = NS * QS;
   const int smem = (int)sizeof(Fwd2Smem<NS, QS>) + 1024;
-  if (!attr_set) {
+  if (once_per_device(attr_set)) {
     PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NS, QS, FUSED, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQ, NQ);
   // words are independent: batches larger than one launch run as consecutive, balanced passes

@@ -11,6 +11,10 @@ Operator surface:
 """
 from __future__ import annotations
 
+import contextlib
+import functools
+import warnings
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -23,6 +27,35 @@ OBJECTIVES = {"acoustic_semvec": 0, "acoustic": 1, "semvec": 2}
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Device guard: the C side launches on the CURRENT CUDA device and stream, so every op body runs with its tensor's
+    device current (a module on cuda:1 while cuda:0 is current must not launch on device 0 with device-1 pointers)."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+        return torch.cuda.device(t.device)
+    return contextlib.nullcontext()
+
+
+def _guard(fn):
+    """Run an op body with its first tensor argument's device current (see _on)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        with _on(t):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def tc_available() -> bool:
+    """True when the tcgen05 recurrent kernels are in the library (hidden size 720)."""
+    return _lib.load().paule_tc_packed_lstm_bytes(720, 30) > 0
+
+
+def default_math(hidden_size: int) -> int:
+    """The arithmetic a planner / module uses when none is given: the tensor-core path (bf16 operands, fp32 accumulate and
+    state) for the hidden size it is built for (Paule's models, paule/paule.py:124,167), the fp32 kernels otherwise."""
+    return MATH_BF16 if (int(hidden_size) == 720 and tc_available()) else MATH_FP32
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -49,9 +82,10 @@ def linear_rows_(out: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: Opti
     """out[cmap(r), :] (+)= a'[amap(r), :] @ w.T + bias; see paule_linear_f32 in include/paule_b200.h."""
     lib = _lib.load()
     N, K = w.shape
-    _lib.check(lib.paule_linear_f32(a.data_ptr() + 4 * a_offset, w.data_ptr(), _p(bias), out.data_ptr(), M, N, K,
-                                    a_map[0], a_map[1], a_map[2], a_pair, c_map[0], c_map[1], c_map[2],
-                                    1 if accumulate else 0, _stream()), "paule_linear_f32")
+    with _on(out):
+        _lib.check(lib.paule_linear_f32(a.data_ptr() + 4 * a_offset, w.data_ptr(), _p(bias), out.data_ptr(), M, N, K,
+                                        a_map[0], a_map[1], a_map[2], a_pair, c_map[0], c_map[1], c_map[2],
+                                        1 if accumulate else 0, _stream()), "paule_linear_f32")
 
 
 def transpose_btc(x: torch.Tensor) -> torch.Tensor:
@@ -59,7 +93,8 @@ def transpose_btc(x: torch.Tensor) -> torch.Tensor:
     _chk(x, "x")
     n0, n1, c = x.shape
     out = torch.empty((n1, n0, c), device=x.device, dtype=x.dtype)
-    _lib.check(_lib.load().paule_transpose_btc(x.data_ptr(), out.data_ptr(), n0, n1, c, _stream()), "paule_transpose_btc")
+    with _on(x):
+        _lib.check(_lib.load().paule_transpose_btc(x.data_ptr(), out.data_ptr(), n0, n1, c, _stream()), "paule_transpose_btc")
     return out
 
 
@@ -112,6 +147,7 @@ class LstmWeights:
 # custom ops
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("paule_b200::lstm_layer_fwd", mutates_args=())
+@_guard
 def lstm_layer_fwd(x: torch.Tensor, batch_first_in: bool, w_ih: torch.Tensor, w_hh: torch.Tensor,
                    bias: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """x [B,T,I] (batch_first_in) or [T,B,I] -> (h [T,B,H], gates [T,B,4H] activated, c [T,B,H])."""
@@ -145,6 +181,7 @@ def _(x, batch_first_in, w_ih, w_hh, bias):
 
 
 @torch.library.custom_op("paule_b200::lstm_layer_bwd", mutates_args=())
+@_guard
 def lstm_layer_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, w_ih_t: torch.Tensor,
                    w_hh_t: torch.Tensor, batch_first_out: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     """Input-gradient BPTT: dh [T,B,H] -> (dx [T,B,I] (or [B,T,I] if batch_first_out), da [T,B,4H] = d loss / d pre-activations)."""
@@ -209,13 +246,20 @@ def _tc_scratch(lib, B: int, device) -> torch.Tensor:
     return torch.zeros(lib.paule_tc_rnn_xchg_bytes(B), dtype=torch.uint8, device=device)
 
 
+CLAMPED_MSG = ("a recurrent-path gradient of the bf16 BPTT kernel reached the +-1.5 bound of the in-band exchange (or was "
+               "NaN / Inf) and was clamped: gradients deviate from the reference's; use math=MATH_FP32 for this loss scale")
+
+
 def _tc_check(xchg: torch.Tensor) -> None:
     code = int(xchg[2048:2052].view(torch.int32).item())     # kXchgErrOff; one 4-byte read per model call
+    if code == 3:      # module-level autograd (continue-learning, user losses): a silently clamped gradient is an error
+        raise _lib.PauleB200Error(CLAMPED_MSG)
     if code != 0:
         raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")
 
 
 @torch.library.custom_op("paule_b200::lstm_layer_fwd_tc", mutates_args=())
+@_guard
 def lstm_layer_fwd_tc(x: torch.Tensor, batch_first_in: bool, w_ih: torch.Tensor, w_hh: torch.Tensor, bias: torch.Tensor,
                       packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """lstm_layer_fwd on the tensor-core path: inputs of at most 64 channels (cps, mel, tube) go through the fused input
@@ -261,6 +305,7 @@ def _(x, batch_first_in, w_ih, w_hh, bias, packed):
 
 
 @torch.library.custom_op("paule_b200::lstm_layer_bwd_tc", mutates_args=())
+@_guard
 def lstm_layer_bwd_tc(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, w_ih_t: torch.Tensor, packed: torch.Tensor,
                       batch_first_out: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     """lstm_layer_bwd with the recurrence on the persistent tcgen05 BPTT kernel (paule_tc_lstm_seq_bwd)."""
@@ -319,6 +364,7 @@ lstm_layer_fwd_tc.register_autograd(_lstm_layer_tc_backward, setup_context=_lstm
 
 
 @torch.library.custom_op("paule_b200::linear_tm", mutates_args=())
+@_guard
 def linear_tm(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, pool_pairs: bool, batch_first_out: bool
               ) -> torch.Tensor:
     """x [T,B,K] time-major -> y = pool?(x) W^T + b as [T',B,N] or batch-first [B,T',N]; T' = T//2 if pool_pairs."""
@@ -343,6 +389,7 @@ def _(x, w, bias, pool_pairs, batch_first_out):
 
 
 @torch.library.custom_op("paule_b200::linear_tm_bwd", mutates_args=())
+@_guard
 def linear_tm_bwd(dy: torch.Tensor, w_t: torch.Tensor, T: int, pool_pairs: bool, batch_first_out: bool
                   ) -> torch.Tensor:
     """Adjoint of linear_tm wrt x: dy ([T',B,N] or [B,T',N]) -> dx [T,B,K]."""
@@ -405,6 +452,7 @@ linear_tm.register_autograd(_linear_tm_backward, setup_context=_linear_tm_setup)
 
 
 @torch.library.custom_op("paule_b200::plan_loss", mutates_args=())
+@_guard
 def plan_loss(mel: torch.Tensor, tmel: torch.Tensor, sv: torch.Tensor, tsv: torch.Tensor, cp: torch.Tensor,
               objective: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Time-major inputs (mel/tmel [Tm,B,60], sv/tsv [B,300], cp [T,B,30]) ->
@@ -431,6 +479,7 @@ def _(mel, tmel, sv, tsv, cp, objective):
 
 
 @torch.library.custom_op("paule_b200::adam_clamp_", mutates_args=("cp", "m", "v", "step_count"))
+@_guard
 def adam_clamp_(cp: torch.Tensor, g_a: torch.Tensor, g_b: Optional[torch.Tensor], m: torch.Tensor, v: torch.Tensor,
                 step_count: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float, clamp: float,
                 smiling: bool, past_cp: Optional[torch.Tensor]) -> None:
@@ -450,7 +499,8 @@ def adam_clamp_(cp: torch.Tensor, g_a: torch.Tensor, g_b: Optional[torch.Tensor]
 # ------------------------------------------------------------------------------------------------
 # the fused planner step
 # ------------------------------------------------------------------------------------------------
-_PLAN_REGISTRY: Dict[int, "object"] = {}
+# weak references: a planner that goes out of scope releases its workspace, Adam state, loss log and CUDA graph
+_PLAN_REGISTRY: "weakref.WeakValueDictionary[int, object]" = weakref.WeakValueDictionary()
 
 
 def register_plan(ctx_obj) -> int:
@@ -466,6 +516,7 @@ def unregister_plan(key: int) -> None:
 @torch.library.custom_op("paule_b200::plan_step",
                          mutates_args=("cp", "adam_m", "adam_v", "step_count", "loss_log", "pred_mel", "pred_sv",
                                        "workspace"))
+@_guard
 def plan_step(cp: torch.Tensor, adam_m: torch.Tensor, adam_v: torch.Tensor, step_count: torch.Tensor,
               loss_log: torch.Tensor, pred_mel: torch.Tensor, pred_sv: torch.Tensor, workspace: torch.Tensor,
               plan_key: int) -> None:
@@ -474,7 +525,18 @@ def plan_step(cp: torch.Tensor, adam_m: torch.Tensor, adam_v: torch.Tensor, step
     _lib.check(_lib.load().paule_plan_step(ctx_obj.struct_ref(), _stream()), "paule_plan_step")
 
 
+@torch.library.custom_op("paule_b200::plan_embed", mutates_args=("sv", "workspace"))
+@_guard
+def plan_embed(mel: torch.Tensor, sv: torch.Tensor, workspace: torch.Tensor, plan_key: int) -> None:
+    """EmbeddingModel forward of the registered plan on a time-major mel [Tm,B,Cm] -> sv [B,S] (paule/paule.py:533-535)."""
+    _chk(mel, "mel"); _chk(sv, "sv")
+    ctx_obj = _PLAN_REGISTRY[plan_key]
+    _lib.check(_lib.load().paule_plan_embed(ctx_obj.struct_ref(), mel.data_ptr(), sv.data_ptr(), _stream()),
+               "paule_plan_embed")
+
+
 @torch.library.custom_op("paule_b200::plan_forward", mutates_args=("pred_mel", "pred_sv", "workspace"))
+@_guard
 def plan_forward(cp: torch.Tensor, pred_mel: torch.Tensor, pred_sv: torch.Tensor, workspace: torch.Tensor,
                  plan_key: int) -> None:
     """no_grad forward of both models on the registered PlanContext (paule/paule.py:822-824, :1460-1464)."""

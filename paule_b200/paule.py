@@ -71,11 +71,13 @@ class Paule():
                  tube_mel_model=None, tube_mel_optimizer=None, tube_embedder=None,
                  continue_data=None, device=torch.device('cuda'), smiling=False,
                  use_speech_classifier=False, speech_classifier=None, speech_classifier_optimizer=None,
-                 math=ops.MATH_FP32, synthesizer=None):
+                 math=None, synthesizer=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.PauleB200Error("paule_b200.Paule runs on a B200 (device='cuda'); there is no CPU fallback")
         self.smiling = smiling
+        # arithmetic of the planning loop: None = the tensor-core path (bf16 operands, fp32 accumulate / state / loss / Adam)
+        # for 720-unit models, fp32 kernels otherwise (ops.default_math); ops.MATH_FP32 forces the fp32 parity anchor
         self.math = math
         # host-side stand-in for speak() + librosa_melspec() + normalize_mel_librosa() (paule/util.py:115-146,175-249):
         # callable(cp [T,30] float ndarray) -> normalised log-mel [T//2,60] ndarray.  Only called at outer-loop boundaries.
@@ -134,6 +136,7 @@ class Paule():
         self.best_synthesis_acoustic = None
         self.best_synthesis_semantic = None
         self.last_planner: Optional[BatchPlanner] = None
+        self._planner_key = None      # plan_resynth in a loop re-arms the planner of the previous call (same shapes / options)
 
     # ---- host-side synthesis pipeline (reference: speak() + librosa_melspec() + normalize, paule.py:1097-1113)
     def _submit_synthesis(self, cps_np):
@@ -380,15 +383,49 @@ class Paule():
         initial_cp_np = cp0.detach().cpu().numpy().copy()
 
         n_steps = int(n_outer) * int(n_inner)
+        with torch.cuda.device(self.device):
+            planner = self._get_planner(cp0, target_mel, target_semvec, learning_rate_planning, objective, past_t,
+                                        log_semantics, log_gradients, n_steps, lengths)
+            return self._plan(planner, cp0, target_mel, initial_cp_np, lengths, batched, B, n_outer, n_inner, n_steps, log_ii,
+                              log_cps, log_gradients, log_signals, log_semantics, objective, continue_learning,
+                              add_training_data_pred, n_epochs, batch_size)
+
+    def _get_planner(self, cp0, target_mel, target_semvec, lr, objective, past_t, log_semantics, log_gradients, n_steps,
+                     lengths) -> BatchPlanner:
+        """The planner of this call: the previous call's one re-armed (workspace, packed weights and CUDA graph kept) when
+        shapes, options and weights are unchanged -- ``plan_resynth`` is normally called in a loop over words -- else a new
+        one (the old one's device memory is released first)."""
+        from .models import _versions
+        soma = self.use_somatosensory_feedback
+        weights = _versions(list(self.pred_model.parameters()) + list(self.embedder.parameters())
+                            + (list(self.speech_classifier.parameters()) if self.use_speech_classifier else []))
+        key = (tuple(cp0.shape), tuple(target_mel.shape), float(lr), objective, bool(self.smiling),
+               None if past_t is None else tuple(past_t.shape), bool(log_semantics), bool(log_gradients),
+               lengths is not None, self.math, self.use_speech_classifier, weights)
+        old = self.last_planner
+        if (old is not None and not soma and self._planner_key == key and old.workspace is not None
+                and old.max_log_steps >= max(n_steps, 1)):
+            old.reset(cp0, target_mel, target_semvec, past_cp=past_t, lengths=lengths)
+            return old
+        if old is not None:
+            old.close()
+            self.last_planner = None
         planner = BatchPlanner(self.pred_model, self.embedder, cp0, target_mel, target_semvec,
-                               lr=learning_rate_planning, objective=objective, smiling=self.smiling, past_cp=past_t,
+                               lr=lr, objective=objective, smiling=self.smiling, past_cp=past_t,
                                log_semantics=log_semantics, log_gradients=log_gradients,
                                max_log_steps=max(n_steps, 1), math=self.math,
                                use_cuda_graph=True, lengths=lengths,
                                speech_classifier=self.speech_classifier if self.use_speech_classifier else None,
                                somatosensory=(self.cp_tube_model, self.tube_mel_model, self.tube_embedder)
-                               if self.use_somatosensory_feedback else None)
+                               if soma else None)
         self.last_planner = planner
+        self._planner_key = key
+        return planner
+
+    def _plan(self, planner, cp0, target_mel, initial_cp_np, lengths, batched, B, n_outer, n_inner, n_steps, log_ii, log_cps,
+              log_gradients, log_signals, log_semantics, objective, continue_learning, add_training_data_pred, n_epochs,
+              batch_size):
+        """Outer / inner loops, final predictions and result packing (paule/paule.py:822-1550) on an armed planner."""
         soma = planner.soma
 
         def tube_predictions():       # no_grad cp -> tube -> (mel, semvec) of the current cps (paule.py:1472-1487)

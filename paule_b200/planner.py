@@ -10,6 +10,7 @@ every step go to a device ring buffer that is copied out once at the end.
 from __future__ import annotations
 
 import ctypes
+import warnings
 from typing import Dict, Optional
 
 import torch
@@ -33,13 +34,23 @@ class BatchPlanner:
     Optional loss branches (mutually exclusive as in paule/paule.py:117-118): ``speech_classifier`` -- a
     ``LinearClassifier`` whose term 0.1 BCEWithLogits(classifier(pred_mel), 0) is fused into the criterion kernel;
     ``somatosensory`` -- ``(cp_tube_model, tube_mel_model, tube_embedder)``, see ``branches.SomatosensoryBranch``.
-    """
+
+    ``math``: ``ops.MATH_FP32`` (FFMA kernels, the parity anchor) or ``ops.MATH_BF16`` (persistent tcgen05 recurrences + tcgen05
+    GEMMs: bf16 operands, fp32 accumulation, state, loss and Adam); ``None`` = ``ops.default_math(hidden_size)``, i.e. the
+    tensor-core path for Paule's 720-unit models.
+
+    The embedder is evaluated deterministically (eval-mode semantics): the reference switches it to ``train()`` inside the
+    loop (paule/paule.py:923), which only matters for an embedder with LSTM dropout > 0 -- such an embedder is rejected here
+    (Paule's embedder has dropout = 0, paule/paule.py:167).
+
+    A planner can be re-armed for another job of the same shape with ``reset()``: workspace, packed weights and the captured
+    CUDA graph are kept (this is what ``Paule.plan_resynth`` does when it is called in a loop)."""
 
     def __init__(self, pred_model: ForwardModel, embedder: EmbeddingModel, initial_cp: torch.Tensor,
                  target_mel: torch.Tensor, target_semvec: Optional[torch.Tensor] = None, *, lr: float = 0.01,
                  objective: str = "acoustic_semvec", smiling: bool = False, past_cp: Optional[torch.Tensor] = None,
                  log_semantics: bool = True, log_gradients: bool = False, max_log_steps: int = 1024,
-                 math: int = ops.MATH_FP32, use_cuda_graph: bool = True, lengths=None,
+                 math: Optional[int] = None, use_cuda_graph: bool = True, lengths=None,
                  speech_classifier=None, somatosensory=None):
         _lib.require_device()
         if objective not in ops.OBJECTIVES:
@@ -49,10 +60,26 @@ class BatchPlanner:
                                       "2-layer EmbeddingModel without post-upsampling (paule/paule.py:124,167)")
         if not pred_model.apply_half_sequence:
             raise NotImplementedError("the fused planner expects apply_half_sequence=True")
+        if getattr(embedder.lstm, "dropout", 0) > 0:
+            raise NotImplementedError("the fused planner evaluates the embedder without inter-layer dropout; the reference plans "
+                                      "with embedder.train() (paule/paule.py:923), so an embedder with LSTM dropout > 0 would "
+                                      "be planned differently -- Paule's embedder has dropout=0 (paule/paule.py:167)")
         dev = initial_cp.device
         if dev.type != "cuda":
             raise _lib.PauleB200Error("BatchPlanner needs CUDA tensors: there is no CPU fallback")
         self.device = dev
+        self._guard = torch.cuda.device(dev)      # the C side launches on the current device (ops._on)
+        self._guard.__enter__()
+        try:
+            self._init(pred_model, embedder, initial_cp, target_mel, target_semvec, lr, objective, smiling, past_cp,
+                       log_semantics, log_gradients, max_log_steps, math, use_cuda_graph, lengths, speech_classifier,
+                       somatosensory)
+        finally:
+            self._guard.__exit__(None, None, None)
+
+    def _init(self, pred_model, embedder, initial_cp, target_mel, target_semvec, lr, objective, smiling, past_cp,
+              log_semantics, log_gradients, max_log_steps, math, use_cuda_graph, lengths, speech_classifier, somatosensory):
+        dev = self.device
         B, T, C = initial_cp.shape
         Tm = T // 2
         if target_mel.shape[0] != B or target_mel.shape[1] != Tm:
@@ -64,6 +91,8 @@ class BatchPlanner:
             raise NotImplementedError("pred_model and embedder must share the hidden size")
         Cm, S = target_mel.shape[2], embedder.linear_mapping.out_features
         self.B, self.T, self.Tm, self.H, self.C, self.Cm, self.S = B, T, Tm, H, C, Cm, S
+        if math is None:
+            math = ops.default_math(H)
         self.objective, self.math = objective, math
         self.lengths, self.word_frames = None, None
         if lengths is not None:
@@ -124,6 +153,8 @@ class BatchPlanner:
         self.workspace = torch.zeros(ws_bytes, device=dev, dtype=torch.uint8)
         off = lib.paule_plan_status_offset(B, T, H, C, Cm, S, math)
         self._status_off = None if off >= ws_bytes else int(off)
+        self._grad_lstm_off = int(lib.paule_plan_grad_lstm_offset(B, T, H, C, Cm, S, math))
+        self._warned_clamp = False
         self.target_sv = torch.zeros((B, S), **f32)
         self.hp = dict(lr=float(lr), beta1=0.9, beta2=0.999, eps=1e-8, clamp=1.05)
         self.smiling, self.log_semantics = bool(smiling), bool(log_semantics)
@@ -200,22 +231,57 @@ class BatchPlanner:
 
     # ------------------------------------------------------------------------------------------
     def embed(self, mel_tm: torch.Tensor) -> torch.Tensor:
-        """semvec of a time-major mel [Tm,B,Cm] through the planner's own embedder kernels (no grad)."""
-        with torch.no_grad():
-            h = mel_tm
-            for L in (self.w_e0, self.w_e1):
-                h, _, _ = ops.lstm_layer_fwd(h, False, L.w_ih, L.w_hh, L.bias)
-            if self.word_frames is None:
-                last = h[-1:]
-            else:   # every word's own last mel frame (paule/models.py:442)
-                idx = (self.word_frames // 2 - 1).long()
-                last = h[idx, torch.arange(self.B, device=h.device)].unsqueeze(0)
-            return ops.linear_tm(last.contiguous(), self.head_w, self.head_b, False, False)[0]
+        """semvec [B,S] of a time-major mel [Tm,B,Cm] through the planner's own embedder kernels, in the planner's math
+        (no grad; ragged batches read every word's own last frame)."""
+        mel_tm = mel_tm.float().contiguous()
+        if tuple(mel_tm.shape) != (self.Tm, self.B, self.Cm):
+            raise ValueError(f"embed expects a time-major mel {(self.Tm, self.B, self.Cm)}, got {tuple(mel_tm.shape)}")
+        sv = torch.empty((self.B, self.S), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            ops.plan_embed(mel_tm, sv, self.workspace, self._key)
+        return sv
+
+    def reset(self, initial_cp: torch.Tensor, target_mel: torch.Tensor, target_semvec: Optional[torch.Tensor] = None,
+              past_cp: Optional[torch.Tensor] = None, lengths=None) -> None:
+        """Re-arm the planner for another job of the SAME shape and options: new cps / targets, zeroed Adam state and loss
+        log.  Every buffer keeps its address, so the captured CUDA graph, the workspace and the packed weights are reused."""
+        B, T, C = initial_cp.shape
+        if (B, T, C) != (self.B, self.T, self.C) or tuple(target_mel.shape) != (self.B, self.Tm, self.Cm):
+            raise ValueError("reset() needs the shapes the planner was built for")
+        if (past_cp is None) != (self.past_cp is None) or (lengths is not None and self.word_frames is None) or \
+                (lengths is None and self.word_frames is not None):
+            raise ValueError("reset() cannot add or remove past_cp / ragged lengths")
+        with torch.cuda.device(self.device):
+            self.cp.copy_(ops.transpose_btc(initial_cp.to(self.device).float().contiguous()))
+            self.target_mel.copy_(ops.transpose_btc(target_mel.to(self.device).float().contiguous()))
+            if past_cp is not None:
+                pc = past_cp.to(self.device).float().contiguous()
+                if pc.dim() == 2:
+                    pc = pc.unsqueeze(0).expand(B, -1, -1).contiguous()
+                pc = ops.transpose_btc(pc)
+                if pc.shape != self.past_cp.shape:
+                    raise ValueError("reset() needs a past_cp of the same length")
+                self.past_cp.copy_(pc)
+            if lengths is not None:
+                ln = [int(v) for v in lengths]
+                if len(ln) != B or min(ln) < 13 or max(ln) > T:
+                    raise ValueError("every word needs 13 <= lengths[b] <= initial_cp.shape[1] cp frames")
+                self.lengths = ln
+                self.word_frames.copy_(torch.tensor(ln, dtype=torch.int32))
+            self.adam_m.zero_(); self.adam_v.zero_(); self.step_count.zero_(); self.loss_log.zero_()
+            if self.aux_log is not None:
+                self.aux_log.zero_()
+            self.steps_done = 0
+            if target_semvec is None:
+                self.target_sv.copy_(self.embed(self.target_mel))
+            else:
+                self.target_sv.copy_(target_semvec.to(self.device).float().reshape(self.B, self.S))
 
     def forward(self):
         """no_grad predictions for the current cps -> (pred_mel [B,Tm,Cm], pred_semvec [B,S])."""
-        ops.plan_forward(self.cp, self.pred_mel, self.pred_sv, self.workspace, self._key)
-        return ops.transpose_btc(self.pred_mel), self.pred_sv.clone()
+        with torch.cuda.device(self.device):
+            ops.plan_forward(self.cp, self.pred_mel, self.pred_sv, self.workspace, self._key)
+            return ops.transpose_btc(self.pred_mel), self.pred_sv.clone()
 
     def _one_step(self) -> None:
         if self.soma is not None:   # tube terms + their d/d(cp) for the CURRENT cps, consumed by the fused step below
@@ -229,6 +295,10 @@ class BatchPlanner:
             return
         if self.steps_done + n > self.max_log_steps:
             raise ValueError(f"loss log holds {self.max_log_steps} steps; construct with a larger max_log_steps")
+        with torch.cuda.device(self.device):
+            self._step(n)
+
+    def _step(self, n: int) -> None:
         if self._use_graph and self._graph is None and not (self.soma is not None and self.soma.stochastic):
             # warm up on a side stream, then capture one step; Adam's step counter and the log slot live on the
             # device, so a replay is a full, correct step.
@@ -262,7 +332,11 @@ class BatchPlanner:
         device->host read; called whenever results leave the planner, never inside the inner loop."""
         if self._status_off is not None:
             code = int(self.workspace[self._status_off:self._status_off + 4].view(torch.int32).item())
-            if code != 0:
+            if code == 3:     # sticky, informational: a recurrent gradient hit the exchange bound of the bf16 BPTT kernel
+                if not self._warned_clamp:
+                    warnings.warn(ops.CLAMPED_MSG, RuntimeWarning, stacklevel=2)
+                    self._warned_clamp = True
+            elif code != 0:
                 raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")
 
     def planned_cp(self) -> torch.Tensor:
@@ -287,9 +361,20 @@ class BatchPlanner:
     def last_grad(self) -> Optional[torch.Tensor]:
         return None if self.grad_out is None else ops.transpose_btc(self.grad_out)
 
+    def last_grad_lstm(self) -> torch.Tensor:
+        """d(mel + semvec terms)/d(cp) of the last step, batch-first [B,T,C]: the BPTT result alone, i.e. ``xx_new.grad``
+        (paule/paule.py:1052) minus the gradient of the velocity / jerk / local-linear terms (which the Adam kernel adds).
+        This is what pins the model path: on iid cps the smoothness gradient is 10^5 times larger and hides it."""
+        n = self.T * self.B * self.C
+        view = self.workspace[self._grad_lstm_off:self._grad_lstm_off + 4 * n].view(torch.float32).view(self.T, self.B, self.C)
+        return ops.transpose_btc(view.contiguous())
+
     def close(self) -> None:
-        ops.unregister_plan(self._key)
+        """Release the device buffers (workspace, Adam state, loss log, CUDA graph); the planner is unusable afterwards."""
+        ops.unregister_plan(getattr(self, "_key", 0))
         self._graph = None
+        self.workspace = None
+        self.soma = None
 
     def __del__(self):
         try:

@@ -25,3 +25,11 @@ def golden_branches():
     import numpy as np
     path = os.path.join(REPO, "tests", "golden", "branches_golden.npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def golden_grad():
+    """fp64 d(loss)/d(cp) of the real reference's plan_resynth, total and model-path part (make_grad_golden.py)"""
+    import numpy as np
+    path = os.path.join(REPO, "tests", "golden", "grad_golden.npz")
+    return dict(np.load(path, allow_pickle=False))

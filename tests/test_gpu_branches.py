@@ -63,7 +63,7 @@ def test_classifier_plan_resynth_matches_the_real_reference(dev, models, branch_
     g = golden_branches
     pred, emb, inv = models
     pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, use_speech_classifier=True,
-                 speech_classifier=branch_models[3])
+                 speech_classifier=branch_models[3], math=0)
     tag = f"cls_{objective}"
     n = len(g[f"{tag}_loss"])
     res = pm.plan_resynth(target_acoustic=g["tmel"][0].astype(np.float32), initial_cp=g["cp0"][0].astype(np.float32),
@@ -127,7 +127,7 @@ def test_somatosensory_plan_resynth_matches_the_real_reference(dev, models, bran
     pred, emb, inv = models
     cp_tube, tube_mel, tube_emb, _ = branch_models
     pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, use_somatosensory_feedback=True,
-                 cp_tube_model=cp_tube, tube_mel_model=tube_mel, tube_embedder=tube_emb)
+                 cp_tube_model=cp_tube, tube_mel_model=tube_mel, tube_embedder=tube_emb, math=0)
     n = len(g["soma_loss"])
     res = pm.plan_resynth(target_acoustic=g["tmel"][0].astype(np.float32), initial_cp=g["cp0"][0].astype(np.float32),
                           initialize_from=None, objective="acoustic_semvec", n_outer=1, n_inner=n, log_ii=1,
@@ -200,7 +200,7 @@ def test_branches_are_exclusive_and_objective_checked(dev, models, branch_models
                 tube_embedder=tube_emb)
     cp0, tmel = torch.from_numpy(golden["b3_cp0"]).to(dev), torch.from_numpy(golden["b3_tmel"]).to(dev)
     with pytest.raises(NotImplementedError):
-        BatchPlanner(pred, emb, cp0, tmel, None, objective="acoustic", somatosensory=(cp_tube, tube_mel, tube_emb))
+        BatchPlanner(pred, emb, cp0, tmel, None, objective="acoustic", somatosensory=(cp_tube, tube_mel, tube_emb), math=0)
 
 
 def test_linear_classifier_module_forward(dev, branch_models):
@@ -225,7 +225,7 @@ def test_dropout_tube_embedder_plans_without_graph(dev, models, branch_models, g
     torch.manual_seed(7)
     te = P.EmbeddingModel(input_size=10, num_lstm_layers=2, hidden_size=720, dropout=0.7, post_upsampling_size=0).to(dev)
     cp0, tmel = torch.from_numpy(golden["b3_cp0"]).to(dev), torch.from_numpy(golden["b3_tmel"]).to(dev)
-    pl = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=4, somatosensory=(cp_tube, tube_mel, te))
+    pl = BatchPlanner(pred, emb, cp0, tmel, None, max_log_steps=4, somatosensory=(cp_tube, tube_mel, te), math=0)
     pl.step(4)
     assert pl._graph is None
     tot = _np(pl.losses()["total"])
@@ -239,7 +239,7 @@ def test_generator_prologue_modes(dev, models, golden):
     pred, emb, inv = models
     torch.manual_seed(4)
     cp_gen, mel_gen = P.Generator(output_size=30), P.Generator(output_size=60)
-    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, cp_gen_model=cp_gen, mel_gen_model=mel_gen, device=dev)
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, cp_gen_model=cp_gen, mel_gen_model=mel_gen, device=dev, math=0)
     tmel = torch.from_numpy(golden["b3_tmel"]).to(dev)                  # [3,20,60]
     B, Tm = tmel.shape[0], tmel.shape[1]
     res = pm.plan_resynth(target_acoustic=tmel, initialize_from="semvec", objective="acoustic_semvec", n_outer=1, n_inner=3,

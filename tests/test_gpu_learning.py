@@ -149,7 +149,7 @@ def test_host_synthesis_pipeline_fills_the_produced_fields(dev):
         pooled = 0.5 * (cp[0::2][: cp.shape[0] // 2] + cp[1::2][: cp.shape[0] // 2])
         return (np.zeros(8, dtype=np.float32), 44100, np.tanh(pooled @ proj) + 0.5)     # (sig, sr, mel)
 
-    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, synthesizer=synth)
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, synthesizer=synth, math=0)
     _, tmel = O.synthetic_inputs(5, 40, seed=8)
     cp0, _ = O.synthetic_inputs(5, 40, seed=9)
     res = pm.plan_resynth(target_acoustic=tmel.numpy(), initial_cp=cp0.numpy(), initialize_from=None, objective="acoustic_semvec",

@@ -158,3 +158,44 @@ def test_somatosensory_branch_matches_real_plan_resynth_fp64(golden_branches, mo
     np.testing.assert_allclose(r["aux"][:, 0, 1].numpy(), g["soma_tube_mel"], rtol=1e-12)
     np.testing.assert_allclose(r["aux"][:, 0, 2].numpy(), g["soma_tube_sem"], rtol=1e-12)
     np.testing.assert_allclose(r["planned_cp"][0].numpy(), g["soma_planned_cp"], atol=1e-14)
+
+
+# ---- the model-path gradient: what the LSTM BPTT kernels produce, isolated from the 10^5 x larger
+# smoothness gradient, pinned against the REAL reference's xx_new.grad (tests/golden/make_grad_golden.py, fp64)
+@pytest.mark.parametrize("init", ["iid", "smooth"])
+@pytest.mark.parametrize("objective", ["acoustic_semvec", "acoustic", "semvec"])
+def test_model_path_gradient_matches_the_real_reference(golden_grad, models64, init, objective):
+    pred, emb, _ = models64
+    g = golden_grad
+    assert [O.state_dict_digest(m) for m in models64] == list(g["digest64"])
+    tmel = torch.from_numpy(g[f"{init}_tmel"])
+    tag = f"{init}_{objective}"
+    for k in range(g[f"{tag}_cps"].shape[0]):
+        cp = torch.from_numpy(g[f"{tag}_cps"][k])[None]
+        want_total, want_model = g[f"{tag}_grad"][k], g[f"{tag}_grad_model"][k]
+        got_model = O.model_path_grad(pred, emb, cp, tmel, objective=objective)[0].numpy()
+        scale = np.abs(want_model).max()
+        assert scale > 1e-6     # the signal exists
+        # the golden model part is (total - smoothness) in fp64: its absolute accuracy is ~1e-16 x |total| <= 1e-13
+        np.testing.assert_allclose(got_model, want_model, atol=2e-9 * scale + 1e-13)
+        got_total = got_model + O.manual_smooth_grad(cp)[0].numpy()
+        np.testing.assert_allclose(got_total, want_total, rtol=1e-10, atol=1e-12)
+        # the hand-derived BPTT (the formulas of the CUDA kernels) gives the same model part
+        pw = {k_: v.double() for k_, v in pred.state_dict().items()}
+        ew = {k_: v.double() for k_, v in emb.state_dict().items()}
+        lens = (torch.tensor(tmel.shape[1]),)
+        with torch.no_grad():
+            tsv = emb(tmel, lens)
+        _, _, dcp, _, _ = O.manual_step(pw, ew, cp, tmel, tsv, objective)
+        np.testing.assert_allclose(dcp[0].numpy() - O.manual_smooth_grad(cp)[0].numpy(), want_model, atol=1e-7 * scale)
+
+
+def test_model_path_gradient_ragged_words_are_planned_alone(models64):
+    pred, emb, _ = models64
+    gen = torch.Generator().manual_seed(3)
+    cp = torch.rand(2, 30, 30, generator=gen, dtype=torch.float64) - 0.5
+    tmel = torch.rand(2, 15, 60, generator=gen, dtype=torch.float64)
+    g = O.model_path_grad(pred, emb, cp, tmel, lens=[30, 21])
+    solo = O.model_path_grad(pred, emb, cp[1:2, :21], tmel[1:2, :10])
+    np.testing.assert_allclose(g[1, :21].numpy(), solo[0].numpy(), atol=1e-15)
+    assert torch.all(g[1, 21:] == 0)
