@@ -6,10 +6,15 @@ Backend: ``torch.distributed`` -- NCCL over NVLink on the GPU box, gloo in the C
 """
 from __future__ import annotations
 
+from collections import namedtuple
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
+
+# what plan_resynth_sharded returns: this rank's PlanningResults plus the gathered job
+ShardedPlanningResults = namedtuple("ShardedPlanningResults", "local, planned_cp, planned_loss_steps, word_range")
 
 
 def shard_bounds(n_words: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -73,6 +78,39 @@ def plan_sharded(make_planner, initial_cp: torch.Tensor, target_mel: torch.Tenso
     cps = gather_words(planner.planned_cp(), n_words, gather_dst, group)
     loss = gather_words(planner.losses()["total"].transpose(0, 1).contiguous(), n_words, gather_dst, group)
     return cps, (None if loss is None else loss.transpose(0, 1))
+
+
+def _host(t: torch.Tensor) -> np.ndarray:
+    if not t.is_cuda:
+        return t.numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)      # pinned staging: the gathered job is ~100 MB
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
+def plan_resynth_sharded(paule, *, target_acoustic, initial_cp=None, target_semvec=None, gather_dst: Optional[int] = None,
+                         group: Optional[dist.ProcessGroup] = None, **kwargs) -> ShardedPlanningResults:
+    """``Paule.plan_resynth`` for a batch of words over all ranks of ``group`` (one process per GPU): every rank passes the
+    WHOLE job (host arrays ``target_acoustic`` [B,Tm,60], ``initial_cp`` [B,T,30], ``target_semvec`` [B,300]), plans its
+    contiguous shard of the word axis through ``paule.plan_resynth(**kwargs)`` and one final NCCL ``all_gather`` (``gather``
+    with ``gather_dst``) returns the planned cps [B,T,30] and the per-step total loss [steps,B] of the whole job as host
+    arrays.  No collective runs inside the planning loop.  ``local`` is this rank's full ``PlanningResults``."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_words = len(target_acoustic)
+    lo, hi = shard_bounds(n_words, ws, rank)
+    if hi <= lo:
+        raise ValueError(f"rank {rank} of {ws} has no words: plan at least one word per GPU")
+    res = paule.plan_resynth(target_acoustic=target_acoustic[lo:hi],
+                             initial_cp=None if initial_cp is None else initial_cp[lo:hi],
+                             target_semvec=None if target_semvec is None else target_semvec[lo:hi], **kwargs)
+    pl = paule.last_planner
+    cps = gather_words(pl.planned_cp(), n_words, gather_dst, group)
+    loss = gather_words(pl.losses()["total"].transpose(0, 1).contiguous(), n_words, gather_dst, group)
+    if cps is None:
+        return ShardedPlanningResults(res, None, None, (lo, hi))
+    return ShardedPlanningResults(res, _host(cps), np.ascontiguousarray(_host(loss).T), (lo, hi))
 
 
 # ---- ragged jobs (SURVEY.md section 8f, N1): length-bucketed sharding ----------------------------------------------

@@ -16,6 +16,8 @@ parameters receive no gradient.  CPU tensors raise: there is no fallback.
 """
 from __future__ import annotations
 
+import contextlib
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -90,10 +92,31 @@ def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights], lstm: nn.LSTM = N
     return h
 
 
+_SCOPE = threading.local()
+
+
+@contextlib.contextmanager
+def math_scope(math: int):
+    """Arithmetic of module forwards inside the ``with`` block for modules WITHOUT their own ``math`` attribute (used by
+    ``Paule.plan_resynth`` to run the inverse model's recurrence in the planner's arithmetic without touching the module)."""
+    old = getattr(_SCOPE, "math", None)
+    _SCOPE.math = math
+    try:
+        yield
+    finally:
+        _SCOPE.math = old
+
+
 def _use_tc(module) -> bool:
     """``module.math = ops.MATH_BF16`` selects the tensor-core recurrences for the module's own forward / backward (the fused
-    planner has its own ``math`` argument).  Only the hidden size the kernels are built for; fp32 otherwise."""
-    return getattr(module, "math", ops.MATH_FP32) != ops.MATH_FP32 and module.lstm.hidden_size == 720
+    planner has its own ``math`` argument); without the attribute an enclosing ``math_scope`` decides, else fp32.  Only the
+    hidden size the kernels are built for; fp32 otherwise."""
+    math = getattr(module, "math", None)
+    if math is None:
+        math = getattr(_SCOPE, "math", None)
+    if math is None:
+        math = ops.MATH_FP32
+    return math != ops.MATH_FP32 and module.lstm.hidden_size == 720
 
 
 class ForwardModel(nn.Module):

@@ -25,6 +25,7 @@ import torch
 
 from . import _lib, ops
 from .models import EmbeddingModel, ForwardModel, Generator, InverseModelMelTimeSmoothResidual, LinearClassifier
+from .models import math_scope as models_math_scope
 from .planner import BatchPlanner
 
 DIR = os.path.dirname(__file__)
@@ -60,6 +61,20 @@ def _load_pretrained(module, key, device):
                                 f"pretrained_models/ directory next to {__file__}")
     module.load_state_dict(torch.load(path, map_location=device, weights_only=True))
     return module
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """device tensor -> host numpy array through a pinned staging buffer (PCIe at DMA speed instead of the pageable path: a
+    1024-word job returns ~250 MB of trajectories and predictions per call)."""
+    t = t.detach()
+    if not t.is_cuda:
+        return t.numpy().copy()
+    if t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
 
 
 class Paule():
@@ -338,7 +353,10 @@ class Paule():
         # ---- 1.1 initial cp (paule.py:550-573)
         if initial_cp is None:
             if initialize_from == "acoustic":
-                with torch.no_grad():
+                # the inverse model's recurrence runs in the planner's arithmetic (tensor-core path for 720 units) unless the
+                # module carries its own `math` attribute
+                inv_math = self.math if self.math is not None else ops.default_math(self.inv_model.lstm.hidden_size)
+                with torch.no_grad(), models_math_scope(inv_math):
                     cp0 = self.inv_model(target_mel).clamp(min=-1, max=1)
             elif initialize_from == "semvec":
                 if self.cp_gen_model is None:
@@ -380,7 +398,7 @@ class Paule():
             with torch.no_grad():
                 past_mel = self.pred_model(past_t.contiguous())
             target_mel = torch.cat((past_mel, target_mel), dim=1).contiguous()
-        initial_cp_np = cp0.detach().cpu().numpy().copy()
+        initial_cp_np = _to_host(cp0)
 
         n_steps = int(n_outer) * int(n_inner)
         with torch.cuda.device(self.device):
@@ -436,17 +454,25 @@ class Paule():
             initial_pred_tube, initial_pred_tube_mel, initial_pred_tube_semvec = tube_predictions()
 
         def out(t):
-            a = t.detach().cpu().numpy()
+            a = _to_host(t)
             if lengths is not None and a.ndim == 3:   # ragged: per-word arrays without the padding frames
                 per = 1 if a.shape[1] == cp0.shape[1] else 2
                 return [a[b, :L // per] for b, L in enumerate(lengths)]
             return a if batched else a[0]
 
-        # initial predictions (paule.py:822-824)
-        initial_pred_mel, initial_pred_semvec = planner.forward()
+        # initial predictions (paule.py:822-824).  The forward pass of the FIRST inner step is exactly this prediction (the
+        # step logs before it updates), so it is taken from there instead of running the models once more
+        sem_in_step = objective != "acoustic" or log_semantics
+        first_from_step = (soma is None and sem_in_step and n_steps >= 1 and not (log_cps or log_gradients)
+                           and self.synthesizer is None and planner.steps_done == 0)
+        if first_from_step:
+            planner.step(1)
+            initial_pred_mel, initial_pred_semvec = ops.transpose_btc(planner.pred_mel), planner.pred_sv.clone()
+        else:
+            initial_pred_mel, initial_pred_semvec = planner.forward()
 
         def word_cps():
-            cur = planner.planned_cp().detach().cpu().numpy()
+            cur = _to_host(planner.planned_cp())
             return [cur[b, :L] for b, L in enumerate(lengths)] if lengths is not None else [cur[b] for b in range(cur.shape[0])]
 
         # produced side (paule.py:826-870, :1097-1164): synthesised on the host at the outer-loop boundaries, overlapped with
@@ -463,7 +489,8 @@ class Paule():
         for ii_outer in range(n_outer):
             cp_steps_ii, pred_semvec_steps_ii, pred_mel_steps_ii = [], [], []
             if not need_per_step:
-                planner.step(n_inner)                      # no host round trip inside the inner loop
+                # no host round trip inside the inner loop (the first step may already have run, see above)
+                planner.step(n_inner - (1 if (first_from_step and ii_outer == 0) else 0))
             else:
                 for ii in range(n_inner):
                     if log_cps and (ii + 1) % log_ii == 0:
@@ -526,7 +553,7 @@ class Paule():
                         self.best_synthesis_acoustic[b] = BestSynthesisAcoustic(float(mel_loss[b]), cps_k[b], res[b][0], mels_k[b], None)
                     if bs is None or bs.semvec_loss > float(sem_loss[b]):
                         self.best_synthesis_semantic[b] = BestSynthesisSemantic(float(sem_loss[b]), cps_k[b], res[b][0], sv[b], None)
-        logs = {k: v.detach().cpu().numpy() for k, v in planner.losses().items()}   # ONE device->host copy
+        logs = {k: _to_host(v.contiguous()) for k, v in planner.losses().items()}   # the device-resident loss log, read once
 
         def per_step(name):
             rows = [logs[name][k] for k in range(n_steps) if (k % n_inner + 1) % log_ii == 0]

@@ -301,7 +301,8 @@ def test_full_size_properties_cfg3_inverse_init(dev, models):
     _, _, iv = O.build_reference_models(0, 720, torch.float32)
     with torch.no_grad():
         init = iv(tmel[100:103]).clamp(-1, 1)
-    np.testing.assert_allclose(res.initial_cp[100:103], init.numpy(), atol=1e-4)
+    # the inverse model's recurrence runs on the bf16 tensor-core kernel in this mode (fp32 mode: 5e-5, test_inverse_init_batched_plan)
+    np.testing.assert_allclose(res.initial_cp[100:103], init.numpy(), atol=5e-3)
     solo = pm.plan_resynth(target_acoustic=tmel[101].numpy(), initial_cp=res.initial_cp[101], initialize_from=None,
                            objective="acoustic_semvec", n_outer=1, n_inner=3, continue_learning=False, verbose=False)
     np.testing.assert_allclose(np.array(solo.planned_loss_steps), np.stack(res.planned_loss_steps)[:, 101], rtol=2e-3)

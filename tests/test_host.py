@@ -137,6 +137,57 @@ def test_sharded_plan_equals_single_rank_gloo_world2(n_words):
             np.testing.assert_array_equal(cps0, ref.planned_cp().numpy())
 
 
+class _FakePaule:
+    """Stands in for paule_b200.Paule in the CPU test of plan_resynth_sharded: plan_resynth on host arrays -> results object,
+    and a `last_planner` with planned_cp() / losses() (device tensors on the GPU box, CPU tensors here)."""
+
+    def plan_resynth(self, *, target_acoustic, initial_cp, target_semvec=None, n_inner=3, **kw):
+        self.last_planner = _FakePlanner(torch.as_tensor(initial_cp), torch.as_tensor(target_acoustic), None)
+        self.last_planner.step(n_inner)
+        return {"planned_cp": self.last_planner.planned_cp().numpy(), "n_words": len(target_acoustic)}
+
+
+def _resynth_worker(rank, ws, port, n_words, out_q):
+    sys.path.insert(0, REPO)
+    from paule_b200 import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    g = torch.Generator().manual_seed(0)
+    cp = torch.rand(n_words, 20, 30, generator=g).numpy()
+    mel = torch.rand(n_words, 10, 60, generator=g).numpy()
+    r = D.plan_resynth_sharded(_FakePaule(), target_acoustic=mel, initial_cp=cp, n_inner=3)
+    r0 = D.plan_resynth_sharded(_FakePaule(), target_acoustic=mel, initial_cp=cp, n_inner=3, gather_dst=0)
+    assert (r0.planned_cp is None) == (rank != 0)
+    out_q.put((rank, r.planned_cp, r.planned_loss_steps, r.word_range, r.local["n_words"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_plan_resynth_sharded_gathers_the_whole_job_gloo_world2():
+    """distributed.plan_resynth_sharded (what bench.py times at N > 1): every rank plans its shard through the Paule API, one
+    final all_gather returns the whole job -- equal to the job planned on one rank."""
+    n_words = 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_resynth_worker, args=(r, 2, port, n_words, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    cp = torch.rand(n_words, 20, 30, generator=g)
+    mel = torch.rand(n_words, 10, 60, generator=g)
+    ref = _FakePlanner(cp, mel, None)
+    ref.step(3)
+    for rank, cps, loss, rng, n_local in res:
+        np.testing.assert_array_equal(cps, ref.planned_cp().numpy())
+        np.testing.assert_array_equal(loss, ref.losses()["total"].numpy())
+        assert rng == ((0, 4) if rank == 0 else (4, 7)) and n_local == rng[1] - rng[0]
+
+
 # ---- ragged jobs: length-bucketed sharding --------------------------------------------------------------------------
 def test_length_buckets_balance_cost_and_cover_every_word():
     from paule_b200.distributed import length_buckets
