@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpaule_b200.so")
+# PAULE_B200_LIB selects another build of the same library (A/B timing of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("PAULE_B200_LIB") or os.path.join(_HERE, "lib", "libpaule_b200.so")
 
 i64, i32, f32, vp, sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
 

@@ -507,16 +507,30 @@ template <bool FUSED>
 int dispatch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
   static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
-  const int nq = choose_nq(B, kMaxQ);
-  if (nq == 1) return launch_fwd2<1, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-  if (one_group) {
-    if (nq == 2) return launch_fwd2<2, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    if (nq == 3) return launch_fwd2<3, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-    return launch_fwd2<2, 2, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  // PAULE_FWD_LAYOUT=<NS><QS><EG> (e.g. 222) forces a layout (A/B timing, tools/ab_groups.sh)
+  static const int forced = getenv("PAULE_FWD_LAYOUT") ? atoi(getenv("PAULE_FWD_LAYOUT")) : 0;
+#define PAULE_FWD_CASE(NS_, QS_, EG_) \
+  return launch_fwd2<NS_, QS_, FUSED, EG_>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s)
+  switch (forced) {
+    case 111: PAULE_FWD_CASE(1, 1, 1);
+    case 211: PAULE_FWD_CASE(2, 1, 1);
+    case 212: PAULE_FWD_CASE(2, 1, 2);
+    case 311: PAULE_FWD_CASE(3, 1, 1);
+    case 221: PAULE_FWD_CASE(2, 2, 1);
+    case 222: PAULE_FWD_CASE(2, 2, 2);
+    default: break;
   }
-  if (nq == 2) return launch_fwd2<2, 1, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
-  if (nq == 3) return launch_fwd2<3, 1, FUSED, 1>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);   // 4.52 vs 4.61 us
-  return launch_fwd2<2, 2, FUSED, 2>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+  const int nq = choose_nq(B, kMaxQ);
+  if (nq == 1) PAULE_FWD_CASE(1, 1, 1);
+  if (one_group) {
+    if (nq == 2) PAULE_FWD_CASE(2, 1, 1);
+    if (nq == 3) PAULE_FWD_CASE(3, 1, 1);
+    PAULE_FWD_CASE(2, 2, 1);
+  }
+  if (nq == 2) PAULE_FWD_CASE(2, 1, 2);
+  if (nq == 3) PAULE_FWD_CASE(3, 1, 1);   // 4.52 vs 4.61 us with two groups
+  PAULE_FWD_CASE(2, 2, 2);
+#undef PAULE_FWD_CASE
 }
 
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
