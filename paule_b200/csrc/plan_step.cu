@@ -18,6 +18,8 @@
 
 #include "common.cuh"
 #include "plan_internal.cuh"
+#include "tc_common.cuh"
+#include "tc_lstm.cuh"
 
 using namespace paule;
 
@@ -30,6 +32,10 @@ struct Workspace {
   float *dmel, *dsv, *dh1_last, *dh0, *dhp, *dcp_lstm, *dcp_smooth, *dc, *partial;
   void *xchg, *h_img, *hf_img, *da_img;   // tensor-core path only; the image buffers must have been zero-filled once
   void *x_img_f, *x_img_0;                // operand blocks of the fused input projections (cps, mel)
+  // layer wavefront (forward model || pooled post_linear || embedder layer 0 as one pipeline): a second exchange buffer for
+  // the co-resident recurrence and the per-step arrival counters
+  void* xchg2;
+  unsigned int *wf_img_flags, *wf_x_flags, *wf_target;
   size_t floats;
 };
 
@@ -60,6 +66,11 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
     w.da_img = take_bytes(paule_tc_img_seq_bytes(T, B, 4));    // dA of the layer being back-propagated (reused by all three)
     w.x_img_f = take_bytes(paule_tc_x_image_bytes(T, B));      // cps as hi/lo bf16 operand blocks
     w.x_img_0 = take_bytes(paule_tc_x_image_bytes(Tm, B));     // predicted mel as bf16 operand blocks
+    const int64_t n_groups = (B + 63) / 64;
+    w.xchg2 = take_bytes(paule_tc_rnn_xchg_bytes(B));
+    w.wf_img_flags = reinterpret_cast<unsigned int*>(take(n_groups * T));
+    w.wf_x_flags = reinterpret_cast<unsigned int*>(take(n_groups * ((Tm + 1) / 2)));
+    w.wf_target = reinterpret_cast<unsigned int*>(take(n_groups));
   }
   w.floats = off;
   return w;
@@ -103,7 +114,8 @@ int layer_backward(const paule_plan* p, const paule_lstm_layer& L, float* gates,
   if (tc(p)) {
     // only the bf16 dA images are consumed (dX GEMM on tcgen05): the fp32 copy over the stash is not written
     PAULE_TRY(paule_tc_lstm_seq_bwd_img(gates, c, L.packed, dh_seq, dh_mode, dh_last, w.xchg, w.da_img, steps, B, p->math, s));
-    return paule_tc_gemm_img(w.da_img, L.packed_ih_t, nullptr, dx, steps, B, I, 4, accumulate, s);
+    return tc::gemm_img(w.da_img, L.packed_ih_t, nullptr, dx, steps, B, I, 4, accumulate,
+                        reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg) + tc::kXchgErrOff), as_stream(s));
   }
   PAULE_TRY(paule_lstm_seq_bwd_f32(gates, c, L.w_hh_t, dh_seq, dh_mode, dh_last, w.dc, steps, B, H, s));
   return paule_linear_f32(gates, L.w_ih_t, nullptr, dx, steps * B, I, 4 * H, 1, 4 * H, 0, 0, 1, I, 0, accumulate, s);
@@ -125,13 +137,105 @@ int project_and_recur(const paule_plan* p, const paule_lstm_layer& L, const floa
   return recur_forward(p, L, steps, gates, h, c, w, h_img, s);
 }
 
-// EmbeddingModel (models.py:440-448) on a time-major mel [Tm,B,Cm] -> sv [B,S]; lens = Tm for every word (paule.py:922-924)
-// or the word's own last frame (ragged batches)
-int embed_models(const paule_plan* p, const Workspace& w, const float* mel, float* sv, paule_stream_t s) {
+// ---- layer wavefront of the forward pass ------------------------------------------------------------------
+// Three kernels run CONCURRENTLY on three streams (fork / join with events, capturable in a CUDA graph):
+//   stream s   forward-model recurrence (T steps); every epilogue warp release-increments wf_img_flags[group][t] once its
+//              h_t image stores are out
+//   side 1     pooled post_linear as a STREAMING tcgen05 GEMM: waits for the four h images of a pair of mel frames, writes
+//              pred_mel (fp32) and the bf16 operand blocks of embedder layer 0, release-increments wf_x_flags[group][pair]
+//   side 2     embedder layer-0 recurrence with the fused input projection: its x-fetching warp waits for wf_x_flags
+// The dependency chain is acyclic (s -> side 1 -> side 2), so partial residency of a later kernel can only delay, never
+// deadlock; all three fit the device together by construction (CTA budget below).  Critical path: T steps + a short tail
+// instead of T + T/2 steps + a GEMM.
+struct SideStreams {
+  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+};
+
+int side_streams(SideStreams** out) {
+  static SideStreams per_device[64];
+  int d = 0;
+  PAULE_CUDA(cudaGetDevice(&d));
+  PAULE_REQUIRE(d >= 0 && d < 64);
+  SideStreams& ss = per_device[d];
+  if (ss.s1 == nullptr) {   // first use on this device (BatchPlanner warms up outside graph capture)
+    PAULE_CUDA(cudaStreamCreateWithFlags(&ss.s1, cudaStreamNonBlocking));
+    PAULE_CUDA(cudaStreamCreateWithFlags(&ss.s2, cudaStreamNonBlocking));
+    PAULE_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    PAULE_CUDA(cudaEventCreateWithFlags(&ss.join1, cudaEventDisableTiming));
+    PAULE_CUDA(cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming));
+  }
+  *out = &ss;
+  return PAULE_OK;
+}
+
+// arrivals that complete one step of 64-word group g: 23 unit groups x 8 epilogue warps per non-empty word quarter
+__global__ void wave_targets_kernel(unsigned int* target, int B, int n_groups) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_groups) {
+    const int words = min(64, B - 64 * g);
+    target[g] = (unsigned int)(tc::kWaveArrivalsPerQuarter * ((words + tc::kWq - 1) / tc::kWq));
+  }
+}
+// the co-resident recurrence used its own exchange buffer: fold its status word into the plan's (sticky) one
+__global__ void merge_status_kernel(int* dst, const int* src) {
+  const int v = *src;
+  if (v != 0) atomicCAS(dst, 0, v);
+}
+
+// CTA budget of the wavefront: forward model in its usual layout + streaming GEMM + embedder layer 0 in the smallest layout
+// that still fits the remaining SMs.  Returns 0 when the three do not fit together (large batches: no wavefront).
+int wavefront_emb0_ctas(const paule_plan* p) {
+  static const bool off = getenv("PAULE_NO_WAVEFRONT") != nullptr;
+  if (off || !tc(p) || p->post_packed == nullptr || (p->T % 2) != 0 || p->T < 8) return 0;
+  const int n_f = tc::fwd2_ctas(p->B, 0);
+  if (n_f == 0) return 0;
+  // the forward model keeps its latency-optimal layout: fewest quarters per CTA that fit one launch
+  const int n_m = tc::gemm_stream_ctas(p->B, p->Cm, 2);
+  const int left = sm_count() - n_f - n_m - 2;
+  return left > 0 ? tc::fwd2_ctas(p->B, left) : 0;
+}
+
+int forward_wavefront(const paule_plan* p, const Workspace& w, int emb0_ctas, paule_stream_t stream) {
+  const int64_t B = p->B, T = p->T, Tm = T / 2, Cm = p->Cm;
+  const int n_groups = (int)((B + 63) / 64), x_pairs = (int)((Tm + 1) / 2);
+  cudaStream_t s = as_stream(stream);
+  SideStreams* ss = nullptr;
+  PAULE_TRY(side_streams(&ss));
+  int* status = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg) + tc::kXchgErrOff);
+  int* status2 = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg2) + tc::kXchgErrOff);
+  PAULE_CUDA(cudaMemsetAsync(w.wf_img_flags, 0, sizeof(unsigned int) * (size_t)n_groups * T, s));
+  PAULE_CUDA(cudaMemsetAsync(w.wf_x_flags, 0, sizeof(unsigned int) * (size_t)n_groups * x_pairs, s));
+  wave_targets_kernel<<<(n_groups + 63) / 64, 64, 0, s>>>(w.wf_target, (int)B, n_groups);
+  PAULE_LAUNCH_CHECK("wave_targets_kernel");
+  PAULE_TRY(paule_tc_x_image(p->cp, w.x_img_f, T, B, p->C, stream));
+  PAULE_CUDA(cudaEventRecord(ss->fork, s));
+  PAULE_CUDA(cudaStreamWaitEvent(ss->s1, ss->fork, 0));
+  PAULE_CUDA(cudaStreamWaitEvent(ss->s2, ss->fork, 0));
+  // (1) forward-model recurrence, T steps, announces every h_t image
+  PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_f, p->fwd.packed, p->fwd.bias, w.x_img_f, nullptr, w.c_f, w.xchg, w.hf_img, T, B, s,
+                               tc::WaveFlags{w.wf_img_flags, nullptr, 0}, 0));
+  // (2) pooled post_linear, streaming: pred_mel + operand blocks of embedder layer 0
+  PAULE_TRY(tc::gemm_img_stream(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, w.wf_img_flags, w.wf_target, 2,
+                                w.wf_x_flags, w.x_img_0, 2, status, ss->s1));
+  // (3) embedder layer 0, fed step by step
+  PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_0, p->emb0.packed, p->emb0.bias, w.x_img_0, nullptr, w.c_0, w.xchg2, w.h_img, Tm, B,
+                               ss->s2, tc::WaveFlags{nullptr, w.wf_x_flags, x_pairs}, emb0_ctas));
+  PAULE_CUDA(cudaEventRecord(ss->join1, ss->s1));
+  PAULE_CUDA(cudaEventRecord(ss->join2, ss->s2));
+  PAULE_CUDA(cudaStreamWaitEvent(s, ss->join1, 0));
+  PAULE_CUDA(cudaStreamWaitEvent(s, ss->join2, 0));
+  merge_status_kernel<<<1, 1, 0, s>>>(status, status2);
+  PAULE_LAUNCH_CHECK("merge_status_kernel");
+  return PAULE_OK;
+}
+
+// embedder layer 1 + head on the images / stash layer 0 left behind
+int embed_top(const paule_plan* p, const Workspace& w, float* sv, paule_stream_t s) {
   const int64_t B = p->B, H = p->H, Tm = p->T / 2, S = p->S;
-  PAULE_TRY(project_and_recur(p, p->emb0, mel, Tm, w.gates_0, w.h_0, w.c_0, w, w.x_img_0, w.h_img, s));
   if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
-    PAULE_TRY(paule_tc_gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, s));
+    PAULE_TRY(tc::gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0,
+                           reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg) + tc::kXchgErrOff), as_stream(s)));
   } else {
     PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
   }
@@ -144,15 +248,32 @@ int embed_models(const paule_plan* p, const Workspace& w, const float* mel, floa
   return paule_linear_f32(h_last, p->head_w, p->head_b, sv, B, S, H, 1, H, 0, 0, 1, S, 0, 0, s);
 }
 
+// EmbeddingModel (models.py:440-448) on a time-major mel [Tm,B,Cm] -> sv [B,S]; lens = Tm for every word (paule.py:922-924)
+// or the word's own last frame (ragged batches)
+int embed_models(const paule_plan* p, const Workspace& w, const float* mel, float* sv, paule_stream_t s) {
+  const int64_t Tm = p->T / 2;
+  PAULE_TRY(project_and_recur(p, p->emb0, mel, Tm, w.gates_0, w.h_0, w.c_0, w, w.x_img_0, w.h_img, s));
+  return embed_top(p, w, sv, s);
+}
+
 int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s) {
   const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, Cm = p->Cm;
+  if (need_semvec) {
+    // batches that leave room for it: forward model, pooled post_linear and embedder layer 0 as ONE pipeline
+    const int emb0_ctas = wavefront_emb0_ctas(p);
+    if (emb0_ctas > 0) {
+      PAULE_TRY(forward_wavefront(p, w, emb0_ctas, s));
+      return embed_top(p, w, p->pred_sv, s);
+    }
+  }
   // ForwardModel (models.py:348-356): K = 30 input projection + recurrence
   const bool tc_post = tc(p) && p->post_packed != nullptr && (T % 2 == 0);
   PAULE_TRY(project_and_recur(p, p->fwd, p->cp, T, w.gates_f, w.h_f, w.c_f, w, w.x_img_f, tc_post ? w.hf_img : nullptr, s));
   // post_linear + AvgPool1d(2,2) (the pool commutes with the Linear)
   if (tc_post) {
     // on tcgen05: frames 2k and 2k+1 are consecutive images = two K segments of row (k, b); weights [0.5 W | 0.5 W]
-    PAULE_TRY(paule_tc_gemm_img(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, 0, s));
+    PAULE_TRY(tc::gemm_img(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, 0,
+                           reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg) + tc::kXchgErrOff), as_stream(s)));
   } else {   // pool the pair of frames on load
     PAULE_TRY(paule_linear_f32(w.h_f, p->post_w, p->post_b, p->pred_mel, Tm * B, Cm, H, B, 2 * B * H, H, B * H, 1, Cm,
                                0, 0, s));
@@ -174,7 +295,7 @@ extern "C" size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, in
 extern "C" size_t paule_plan_status_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math) {
   if (B <= 0 || T <= 0 || H <= 0 || math == PAULE_MATH_FP32) return (size_t)-1;
   const Workspace w = carve(reinterpret_cast<void*>(uintptr_t(256)), B, T, H, C, Cm, S, math);
-  return (size_t)(reinterpret_cast<uintptr_t>(w.xchg) - 256) + 2048;   // kXchgErrOff
+  return (size_t)(reinterpret_cast<uintptr_t>(w.xchg) - 256) + tc::kXchgErrOff;
 }
 
 // Byte offset inside the workspace of the model-path gradient d(mel + semvec terms)/d(cp) [T,B,C] fp32 of the last

@@ -262,6 +262,16 @@ __device__ __forceinline__ bool grid_wait(const unsigned int* counter, unsigned 
   }
 }
 
+// ---- flag-based hand-over between concurrently running kernels (layer wavefront): release-increment / acquire-poll
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---- self-validating exchange of bf16 operands between CTAs.  Every exchanged value satisfies |x| < 2 (h is a product of
 // a sigmoid and a tanh; gradients are clamped), so bit 14 of its bf16 encoding -- the top exponent bit -- is always 0
 // and is free to carry a phase bit.  Consecutive occupants of a ping-pong buffer are steps t-2 and t, which differ in

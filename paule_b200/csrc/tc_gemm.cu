@@ -67,21 +67,53 @@ struct GemmBars {
   alignas(16) float stage[4][32][kStageLd];
 };
 
+// Streaming mode (layer wavefront): the GEMM runs CONCURRENTLY with the recurrent kernel that produces its A
+// operand and with the recurrent kernel that consumes its output.
+//   * a CTA owns one (64-word group, column tile) and every `n_par`-th pair of output steps, in time order;
+//   * before the first TMA of a tile the producer warp polls the arrival counter of the LAST source step the tile reads
+//     (`src_flags[grp * src_steps + step]`, incremented with release semantics by every epilogue warp of the producing kernel
+//     once its image stores of that step are out; steps complete in order) until it reaches `src_target[grp]`;
+//   * the epilogue also emits the tile as bf16 operand blocks of the consumer's fused input projection
+//     (`x_out`: [steps][ceil(B/16)][16 rows][128 B], SWIZZLE_128B, N <= 64 columns) and then increments `dst_flags[grp * n_pairs +
+//     pair]` (release; 4 arrivals = the 4 epilogue warps).
+struct GemmStream {
+  const unsigned int* src_flags;   // [n_groups][src_steps]
+  const unsigned int* src_target;  // [n_groups] arrivals that complete a source step
+  unsigned int* dst_flags;         // [n_groups][n_pairs], or nullptr
+  uint8_t* x_out;                  // consumer operand blocks, or nullptr
+  int* status;                     // sticky status word (watchdog), or nullptr
+  int src_per_step;                // source steps per output step (2: pooled post_linear over frame pairs)
+  int n_par;                       // CTAs that alternate over the step pairs of one (group, column tile)
+};
+
+template <bool STREAM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, const float* __restrict__ bias,
-                   float* __restrict__ C, int steps, int B, int N, int KB, int BN, int accumulate) {
+                   float* __restrict__ C, int steps, int B, int N, int KB, int BN, int accumulate, GemmStream st) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = 16384u + (uint32_t)BN * 128u;   // A [128 x 128 B] + B [BN x 128 B]; BN % 8 == 0 keeps 1 KB alignment
   GemmBars& bars = *reinterpret_cast<GemmBars*>(base + (size_t)kGemmStages * stage_bytes);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  volatile int dummy_err = 0;
-  volatile int* err = &dummy_err;
+  // a timed-out TMA / MMA wait is recorded in the caller's sticky status word when it gave one (planner.check() reads it)
+  __shared__ int local_err;
+  volatile int* err = (st.status != nullptr) ? reinterpret_cast<volatile int*>(st.status) : reinterpret_cast<volatile int*>(&local_err);
+  if (threadIdx.x == 0) local_err = 0;
 
   const int n_groups = (B + kRows - 1) / kRows;
   const int n_pairs = (steps + 1) / 2;
   const int n_nt = pad_n(N) / BN;
-  const int total = n_groups * n_pairs * n_nt;
+  // tile walk: batch mode = all tiles strided over the grid; streaming = this CTA's (group, column tile), every n_par-th pair
+  const int total = STREAM ? (n_pairs - (int)(blockIdx.x % st.n_par) + st.n_par - 1) / st.n_par : n_groups * n_pairs * n_nt;
+  const int tile_first = STREAM ? 0 : (int)blockIdx.x, tile_stride = STREAM ? 1 : (int)gridDim.x;
+  auto coords = [&](int tile, int& nt, int& sp, int& grp) {
+    if (STREAM) {
+      const int cta = (int)blockIdx.x / st.n_par;
+      nt = cta % n_nt; grp = cta / n_nt; sp = (int)(blockIdx.x % st.n_par) + tile * st.n_par;
+    } else {
+      nt = tile % n_nt; const int rest = tile / n_nt; sp = rest % n_pairs; grp = rest / n_pairs;
+    }
+  };
 
   if (tid == 0) {
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
@@ -98,12 +130,30 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int nt = tile % n_nt, rest = tile / n_nt, sp = rest % n_pairs, grp = rest / n_pairs;
+    for (int tile = tile_first; tile < total; tile += tile_stride) {
+      int nt, sp, grp;
+      coords(tile, nt, sp, grp);
       const int t0 = 2 * sp;
       const bool two = (t0 + 1 < steps);
       const uint8_t* a0 = a_img + ((size_t)(grp * steps + t0) * KB) * (kRows * 128);
       const uint8_t* bt = b_img + (size_t)nt * KB * BN * 128;
+      if (STREAM) {
+        // the producing recurrent kernel has finished the last source step this tile reads (steps complete in order)
+        const int src_steps = steps * st.src_per_step;
+        const int last = min((t0 + 2) * st.src_per_step, src_steps) - 1;
+        const unsigned int* f = st.src_flags + (size_t)grp * src_steps + last;
+        const unsigned int want = st.src_target[grp];
+        uint64_t w0 = 0;
+        for (unsigned int spin = 0; ld_acquire_u32(f) < want; ++spin) {
+          __nanosleep(200);
+          if ((spin & 255u) == 255u) {
+            if (w0 == 0) w0 = globaltimer_ns();
+            if (*err != 0) break;
+            if (globaltimer_ns() - w0 > kWatchdogNs) { *err = 1; break; }
+          }
+        }
+        fence_proxy_async_global();   // the acquire above orders the generic proxy; the TMA reads go through the async proxy
+      }
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&bars.empty[s], ph ^ 1u, err);
         if (elect_one_sync()) {
@@ -125,7 +175,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
     int s = 0;
     uint32_t ph = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
+    for (int tile = tile_first; tile < total; tile += tile_stride, ++local) {
       const int ab = local & 1;
       mbar_wait(&bars.tmem_empty[ab], (uint32_t)(((local >> 1) & 1) ^ 1), err);   // epilogue drained this buffer
       tcgen05_fence_after();
@@ -151,8 +201,9 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
     const int lg = warp & 3;                     // TMEM lane group this warp may access
     const int r = lg * 32 + lane;                // tile row: two time steps x 64 words
     int local = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
-      const int nt = tile % n_nt, rest = tile / n_nt, sp = rest % n_pairs, grp = rest / n_pairs;
+    for (int tile = tile_first; tile < total; tile += tile_stride, ++local) {
+      int nt, sp, grp;
+      coords(tile, nt, sp, grp);
       const int ab = local & 1;
       const int t = 2 * sp + (r >> 6), b = grp * kRows + (r & 63);
       const bool valid = (t < steps) && (b < B);
@@ -172,6 +223,26 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
         }
         const int n0 = nt * BN + c0;
         const int lim = (BN - c0 >= 32) ? 32 : 16;
+        if (STREAM && st.x_out != nullptr && valid) {
+          // the consumer's operand block of (step t, word quarter b / 16): row b % 16, 16-byte chunk j ^ (row % 8) holds columns
+          // 8 j .. 8 j + 7 as bf16 (+ bias; columns >= N are zero: the packed weights' pad rows and no bias)
+          const int row = b & (kWq - 1);
+          uint8_t* blk = st.x_out + ((size_t)t * ((B + kWq - 1) / kWq) + (size_t)(b / kWq)) * kXBlockBytes + (size_t)row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const int i0 = 8 * j + 2 * e2, na = n0 + i0, nb = na + 1;
+              const float fa = (i0 < lim && na < N) ? v[i0] + (bias ? __ldg(bias + na) : 0.f) : 0.f;
+              const float fb = (i0 + 1 < lim && nb < N) ? v[i0 + 1] + (bias ? __ldg(bias + nb) : 0.f) : 0.f;
+              const __nv_bfloat162 pr = __floats2bfloat162_rn(fa, fb);
+              w[e2] = *reinterpret_cast<const uint32_t*>(&pr);
+            }
+            const int chunk = (n0 >> 3) + j;
+            if (chunk < 8) *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
         if ((N & 3) == 0) {
           // ---- coalesced path: own row -> staging, then 8 instructions x (4 rows x 128 B)
           float* srow = &bars.stage[lg][lane][0];
@@ -207,7 +278,11 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.tmem_empty[ab]);
+      if (lane == 0) {
+        mbar_arrive(&bars.tmem_empty[ab]);
+        // streaming: this warp's rows of the pair (fp32 C and operand blocks) are out -- release them to the consumer
+        if (STREAM && st.dst_flags != nullptr) red_release_add_u32(st.dst_flags + (size_t)grp * n_pairs + sp, 1u);
+      }
     }
   }
   tcgen05_fence_before();
@@ -235,25 +310,68 @@ extern "C" int paule_tc_gemm_pack(const float* W, void* packed, int64_t N, int64
   return PAULE_OK;
 }
 
+namespace paule {
+namespace tc {
+
+static int gemm_attrs() {
+  static unsigned long long attr_set = 0ull;
+  if (once_per_device(attr_set)) {   // the widest tile (BN = 256) bounds every launch
+    const int smem_max = kGemmStages * (16384 + 256 * 128) + (int)sizeof(GemmBars) + 1024 + 16;
+    PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  }
+  return PAULE_OK;
+}
+
+int gemm_stream_ctas(int64_t B, int64_t N, int n_par) {
+  const int np = pad_n((int)N), bn = pick_bn(np);
+  return (int)((B + kRows - 1) / kRows) * (np / bn) * n_par;
+}
+
+// the GEMM of paule_tc_gemm_img in streaming mode (see GemmStream); `status` may be NULL
+int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
+                    int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
+                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s) {
+  PAULE_REQUIRE(a_img && packed_b && C && steps > 0 && B > 0 && N > 0 && nseg > 0 && nseg <= 4 && src_flags && src_target);
+  PAULE_REQUIRE(n_par >= 1 && (x_out == nullptr || N <= kXK));
+  PAULE_TRY(gemm_attrs());
+  const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
+  const int smem_own = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
+  const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // never shares an SM (tensor memory)
+  GemmStream st{src_flags, src_target, dst_flags, reinterpret_cast<uint8_t*>(x_out), status, src_per_step, n_par};
+  tc_gemm_img_kernel<true><<<gemm_stream_ctas(B, N, n_par), kGemmThreads, (size_t)smem, s>>>(
+      reinterpret_cast<const uint8_t*>(a_img), reinterpret_cast<const uint8_t*>(packed_b), bias, C, (int)steps, (int)B, (int)N,
+      KB, bn, 0, st);
+  PAULE_LAUNCH_CHECK("tc_gemm_img_kernel<stream>");
+  return PAULE_OK;
+}
+
+}  // namespace tc
+}  // namespace paule
+
 extern "C" int paule_tc_gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps,
                                  int64_t B, int64_t N, int64_t nseg, int accumulate, paule_stream_t stream) {
+  return paule::tc::gemm_img(a_img, packed_b, bias, C, steps, B, N, nseg, accumulate, nullptr, as_stream(stream));
+}
+
+// paule_tc_gemm_img with the caller's sticky status word: a timed-out TMA / MMA wait is recorded there (planner.check())
+int paule::tc::gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B,
+                        int64_t N, int64_t nseg, int accumulate, int* status, cudaStream_t stream) {
   PAULE_REQUIRE(a_img && packed_b && C && steps >= 0 && B > 0 && N > 0 && nseg > 0 && nseg <= 4);
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(a_img) % 16 == 0 && reinterpret_cast<uintptr_t>(packed_b) % 16 == 0);
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(C) % 16 == 0);
   if (steps == 0) return PAULE_OK;
+  PAULE_TRY(gemm_attrs());
   const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
   const int n_groups = (int)((B + kRows - 1) / kRows), n_pairs = (int)((steps + 1) / 2);
   const int64_t total = (int64_t)n_groups * n_pairs * (np / bn);
   const int smem = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
-  static unsigned long long attr_set = 0ull;
-  if (once_per_device(attr_set)) {   // the widest tile (BN = 256) bounds every launch
-    const int smem_max = kGemmStages * (16384 + 256 * 128) + (int)sizeof(GemmBars) + 1024 + 16;
-    PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-  }
   const int grid = (int)((total < (int64_t)sm_count()) ? total : (int64_t)sm_count());
-  tc_gemm_img_kernel<<<grid, kGemmThreads, (size_t)smem, as_stream(stream)>>>(
+  GemmStream st{};
+  st.status = status;
+  tc_gemm_img_kernel<false><<<grid, kGemmThreads, (size_t)smem, stream>>>(
       reinterpret_cast<const uint8_t*>(a_img), reinterpret_cast<const uint8_t*>(packed_b), bias, C, (int)steps, (int)B,
-      (int)N, KB, bn, accumulate);
+      (int)N, KB, bn, accumulate, st);
   PAULE_LAUNCH_CHECK("tc_gemm_img_kernel");
   return PAULE_OK;
 }

@@ -244,6 +244,21 @@ __device__ __forceinline__ bool xchg_fetch_kblock(const uint8_t* __restrict__ sr
 // ones put 2 or 4 quarters on a CTA (the grid is limited to 6 / 5 groups, so this is what scales the throughput)
 #endif  // __CUDACC__
 
+// ---- layer wavefront: per-step arrival counters next to the bf16 images.  A producing recurrent kernel
+// increments `img_flags[(word group) * T + t]` (release) from every epilogue warp once its stores of step t are out; a
+// consuming kernel / streaming GEMM polls them (acquire).  A consuming recurrent kernel with a fused input projection waits
+// for `x_flags[(word group) * x_pairs + t / 2] >= 4` (the streaming GEMM's four epilogue warps) before it fetches x_t.
+struct WaveFlags {
+  unsigned int* img_flags;        // producer side, or nullptr
+  const unsigned int* x_flags;    // consumer side, or nullptr
+  int x_pairs;                    // pairs of steps per word group in x_flags
+};
+constexpr int kWaveArrivalsPerQuarter = kFwd2Groups * 8;   // 23 unit groups x 8 epilogue warps per (step, word quarter)
+// Kernels that run side by side in the wavefront all allocate the SM's whole tensor memory: two of their CTAs on one SM would
+// park the second in tcgen05.alloc until the first exits -- a deadlock when the first (transitively) waits for the second.
+// Requesting more than half of the SM's shared memory makes every such CTA the only one on its SM.
+constexpr int kExclusiveSmemBytes = 117 * 1024;
+
 // host entry points of the kernels (called from the C ABI in tc_lstm_api.cu)
 int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cudaStream_t s);
 int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s);
@@ -251,7 +266,17 @@ int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xc
                   cudaStream_t s);
 // fused input projection: gates is output only (the activated-gate stash), pre-activations = W_hh h + W_ih x_t + bias
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s);
+                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf = WaveFlags{nullptr, nullptr, 0},
+                   int max_ctas = 0);
+// CTAs lstm_seq_fwd2x launches for B words when at most max_ctas (0: no limit) may be used; 0 = does not fit one launch
+int fwd2_ctas(int64_t B, int max_ctas);
+// batched tcgen05 GEMM over image sequences (tc_gemm.cu): batch mode with a status word, streaming mode for the wavefront
+int gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
+             int64_t nseg, int accumulate, int* status, cudaStream_t s);
+int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
+                    int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
+                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s);
+int gemm_stream_ctas(int64_t B, int64_t N, int n_par);
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s);
 

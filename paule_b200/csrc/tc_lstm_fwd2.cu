@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(f2_threads(EG), 1)
 tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packed, float* __restrict__ h_out,
                     float* __restrict__ c_out, uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv,
                     int Bs, int w0, const uint8_t* __restrict__ packed_x, const uint8_t* __restrict__ x_img,
-                    const float* __restrict__ bias, int Qtot) {
+                    const float* __restrict__ bias, int Qtot, WaveFlags wf) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = Fwd2Smem<NS, QS>;
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -194,6 +194,23 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
 #pragma unroll
     for (int q = 0; q < NS * QS; ++q) nvq += (grp * kGW + q * kWq < Bv) ? 1 : 0;
     auto fetch_x = [&](int t) {   // x_t blocks of every valid quarter: one bulk copy each onto xfull[t & 1]
+      if (wf.x_flags != nullptr) {
+        // layer wavefront: x_t is produced while this kernel runs -- wait until the streaming GEMM has released the pair of
+        // steps that holds x_t for every 64-word group this CTA's quarters belong to (4 arrivals: its epilogue warps)
+        uint64_t wd0 = 0;
+        for (int g64 = q_first / 4; g64 <= (q_first + nvq - 1) / 4; ++g64) {
+          const unsigned int* f = wf.x_flags + (size_t)g64 * wf.x_pairs + (t >> 1);
+          for (unsigned int spin = 0; ld_acquire_u32(f) < 4u; ++spin) {
+            __nanosleep(100);
+            if ((spin & 255u) == 255u) {
+              if (wd0 == 0) wd0 = globaltimer_ns();
+              if (*err != 0) break;
+              if (globaltimer_ns() - wd0 > kWatchdogNs) { *err = 1; break; }
+            }
+          }
+        }
+        fence_proxy_async_global();   // acquire (generic proxy) -> TMA reads (async proxy)
+      }
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&S.xfull[t & 1], (uint32_t)(nvq * kXBlockBytes));
         for (int q = 0; q < nvq; ++q)
@@ -432,6 +449,11 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             }
           }
 #endif
+          if (wf.img_flags != nullptr && wq < Bv) {
+            // layer wavefront: this warp's image stores of step t are out -- one release-arrival per (step, quarter, warp)
+            __syncwarp();
+            if (lane == 0) red_release_add_u32(wf.img_flags + (size_t)((w0 + wq) / kRows) * (size_t)T + t, 1u);
+          }
           if (tl0) TL(13, q, t)   // epilogue: quarter's stash stores issued
           TRACE(4)
         }
@@ -467,10 +489,11 @@ int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cu
 
 template <int NS, int QS, bool FUSED, int EG>
 int launch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+                void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf) {
   static unsigned long long attr_set = 0ull;
   constexpr int NQ = NS * QS;
-  const int smem = (int)sizeof(Fwd2Smem<NS, QS>) + 1024;
+  const int smem_own = (int)sizeof(Fwd2Smem<NS, QS>) + 1024;
+  const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // one CTA per SM, whatever runs beside it
   if (once_per_device(attr_set)) {
     PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NS, QS, FUSED, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
@@ -491,7 +514,7 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedFwd2Off;
     const uint8_t* pkx = reinterpret_cast<const uint8_t*>(packed) + kPackedXOff;
     const uint8_t* xi = reinterpret_cast<const uint8_t*>(x_img);
-    void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bvi, &Bsi, &w0, &pkx, &xi, &bias, &Qtot};
+    void* args[] = {&gp, &pk, &hp, &cp, &xc, &is, &Ti, &Bvi, &Bsi, &w0, &pkx, &xi, &bias, &Qtot, &wf};
     PAULE_CUDA(cudaLaunchCooperativeKernel((void*)tc_lstm_fwd2_kernel<NS, QS, FUSED, EG>, dim3(kFwd2Groups * ng),
                                            dim3(f2_threads(EG)), args, (size_t)smem, s));
   }
@@ -505,13 +528,13 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
 // exchange block once before probing (the loader usually returns to a slot after its data has landed): +20-30 % per step.
 template <bool FUSED>
 int dispatch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                  void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
+                  void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int nq_min) {
   static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
   // PAULE_FWD_LAYOUT=<NS><QS><EG> (e.g. 222) forces a layout (A/B timing, tools/ab_groups.sh)
   static const int forced = getenv("PAULE_FWD_LAYOUT") ? atoi(getenv("PAULE_FWD_LAYOUT")) : 0;
 #define PAULE_FWD_CASE(NS_, QS_, EG_) \
-  return launch_fwd2<NS_, QS_, FUSED, EG_>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s)
-  switch (forced) {
+  return launch_fwd2<NS_, QS_, FUSED, EG_>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s, wf)
+  switch (nq_min > 1 ? 0 : forced) {
     case 111: PAULE_FWD_CASE(1, 1, 1);
     case 211: PAULE_FWD_CASE(2, 1, 1);
     case 212: PAULE_FWD_CASE(2, 1, 2);
@@ -520,7 +543,8 @@ int dispatch_fwd2(float* gates, const void* packed, const float* bias, const voi
     case 222: PAULE_FWD_CASE(2, 2, 2);
     default: break;
   }
-  const int nq = choose_nq(B, kMaxQ);
+  int nq = choose_nq(B, kMaxQ);
+  if (nq < nq_min) nq = nq_min;      // a co-resident kernel (layer wavefront) leaves this one fewer SMs: more quarters per CTA
   if (nq == 1) PAULE_FWD_CASE(1, 1, 1);
   if (one_group) {
     if (nq == 2) PAULE_FWD_CASE(2, 1, 1);
@@ -533,14 +557,36 @@ int dispatch_fwd2(float* gates, const void* packed, const float* bias, const voi
 #undef PAULE_FWD_CASE
 }
 
+// quarters per CTA (1..4) such that B words fit ONE launch of at most max_ctas CTAs (0: the device); 0 = impossible
+static int nq_for(int64_t B, int max_ctas) {
+  const int64_t quarters = (B + kWq - 1) / kWq;
+  for (int nq = 1; nq <= 4; ++nq) {
+    const int64_t groups = (quarters + nq - 1) / nq;
+    if (groups <= kMaxQ && (max_ctas <= 0 || groups * kFwd2Groups <= max_ctas)) return nq;
+  }
+  return 0;
+}
+
+int fwd2_ctas(int64_t B, int max_ctas) {
+  const int nq = nq_for(B, max_ctas);
+  if (nq == 0) return 0;
+  const int64_t quarters = (B + kWq - 1) / kWq;
+  return (int)((quarters + nq - 1) / nq) * kFwd2Groups;
+}
+
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
                   cudaStream_t s) {
-  return dispatch_fwd2<false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s);
+  return dispatch_fwd2<false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s, WaveFlags{nullptr, nullptr, 0}, 1);
 }
 
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s) {
-  return dispatch_fwd2<true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s);
+                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int max_ctas) {
+  int nq_min = 1;
+  if (max_ctas > 0) {
+    nq_min = nq_for(B, max_ctas);
+    if (nq_min == 0) return PAULE_ERR_ARG;
+  }
+  return dispatch_fwd2<true>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s, wf, nq_min);
 }
 
 int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s) {
