@@ -285,6 +285,10 @@ typedef struct paule_plan {
   const float* extra_terms;   /* [B,2]: tube_mel_loss, tube_semvec_loss, or NULL */
   const float* extra_grad;    /* [T,B,C] time-major, or NULL */
   float* aux_log;             /* [log_slot_count, B, 3]: speech_classifier, tube_mel, tube_semvec terms, or NULL */
+  /* backward layer wavefront (tensor-core math, <= 64 words): paule_tc_gemm_pack of (W_ih0 W_post)^T, i.e. of the [H, 4H] matrix
+     post_linear.weight^T x EmbeddingModel.lstm.weight_ih_l0^T, with (N = H, nseg = 4): embedder layer 0's dA goes to
+     d/d(pooled forward-model h) in ONE streaming GEMM while both BPTT kernels run.  NULL: serial backward. */
+  const void* bwd_fused_packed;
 } paule_plan;
 
 PAULE_API size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);

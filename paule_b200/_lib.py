@@ -38,6 +38,7 @@ class Plan(C.Structure):
         ("workspace", vp), ("workspace_bytes", sz),
         ("word_frames", vp),
         ("cls_w", vp), ("cls_b", vp), ("extra_terms", vp), ("extra_grad", vp), ("aux_log", vp),
+        ("bwd_fused_packed", vp),
     ]
 
 

@@ -34,8 +34,13 @@ struct Workspace {
   void *x_img_f, *x_img_0;                // operand blocks of the fused input projections (cps, mel)
   // layer wavefront (forward model || pooled post_linear || embedder layer 0 as one pipeline): a second exchange buffer for
   // the co-resident recurrence and the per-step arrival counters
-  void* xchg2;
-  unsigned int *wf_img_flags, *wf_x_flags, *wf_target;
+  void *xchg2, *xchg3;
+  void *da_img_0, *da_img_1;              // dA images of the embedder layers when the three BPTT kernels run concurrently
+  // arrival counters [word group][step or pair of steps] of every hand-over, one contiguous block (zeroed once per step)
+  unsigned int *wf_flags;                 // start of the block
+  size_t wf_flag_count;
+  unsigned int *f_hf, *f_x0, *f_h0, *f_g1, *f_da1, *f_dh0, *f_da0, *f_dhp;
+  unsigned int *wf_target, *wf_target_b;  // arrivals that complete one step: forward / backward recurrences
   size_t floats;
 };
 
@@ -66,11 +71,28 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
     w.da_img = take_bytes(paule_tc_img_seq_bytes(T, B, 4));    // dA of the layer being back-propagated (reused by all three)
     w.x_img_f = take_bytes(paule_tc_x_image_bytes(T, B));      // cps as hi/lo bf16 operand blocks
     w.x_img_0 = take_bytes(paule_tc_x_image_bytes(Tm, B));     // predicted mel as bf16 operand blocks
-    const int64_t n_groups = (B + 63) / 64;
+    const int64_t G = (B + 63) / 64, P = (Tm + 1) / 2;
     w.xchg2 = take_bytes(paule_tc_rnn_xchg_bytes(B));
-    w.wf_img_flags = reinterpret_cast<unsigned int*>(take(n_groups * T));
-    w.wf_x_flags = reinterpret_cast<unsigned int*>(take(n_groups * ((Tm + 1) / 2)));
-    w.wf_target = reinterpret_cast<unsigned int*>(take(n_groups));
+    w.xchg3 = take_bytes(paule_tc_rnn_xchg_bytes(B));
+    // the backward wavefront is only taken by batches of at most 64 words: the extra dA image buffers are sized for that
+    const int64_t Bw = B <= 64 ? B : 0;
+    w.da_img_0 = take_bytes(paule_tc_img_seq_bytes(Tm, Bw, 4));
+    w.da_img_1 = take_bytes(paule_tc_img_seq_bytes(Tm, Bw, 4));
+    w.wf_flag_count = (size_t)(G * (T + 3 * Tm + 4 * P));
+    w.wf_flags = reinterpret_cast<unsigned int*>(take((int64_t)w.wf_flag_count));
+    if (w.wf_flags) {
+      unsigned int* f = w.wf_flags;
+      w.f_hf = f;  f += G * T;
+      w.f_h0 = f;  f += G * Tm;
+      w.f_da1 = f; f += G * Tm;
+      w.f_da0 = f; f += G * Tm;
+      w.f_x0 = f;  f += G * P;
+      w.f_g1 = f;  f += G * P;
+      w.f_dh0 = f; f += G * P;
+      w.f_dhp = f;
+    }
+    w.wf_target = reinterpret_cast<unsigned int*>(take(G));
+    w.wf_target_b = reinterpret_cast<unsigned int*>(take(G));
   }
   w.floats = off;
   return w;
@@ -137,19 +159,26 @@ int project_and_recur(const paule_plan* p, const paule_lstm_layer& L, const floa
   return recur_forward(p, L, steps, gates, h, c, w, h_img, s);
 }
 
-// ---- layer wavefront of the forward pass ------------------------------------------------------------------
-// Three kernels run CONCURRENTLY on three streams (fork / join with events, capturable in a CUDA graph):
-//   stream s   forward-model recurrence (T steps); every epilogue warp release-increments wf_img_flags[group][t] once its
-//              h_t image stores are out
-//   side 1     pooled post_linear as a STREAMING tcgen05 GEMM: waits for the four h images of a pair of mel frames, writes
-//              pred_mel (fp32) and the bf16 operand blocks of embedder layer 0, release-increments wf_x_flags[group][pair]
-//   side 2     embedder layer-0 recurrence with the fused input projection: its x-fetching warp waits for wf_x_flags
-// The dependency chain is acyclic (s -> side 1 -> side 2), so partial residency of a later kernel can only delay, never
-// deadlock; all three fit the device together by construction (CTA budget below).  Critical path: T steps + a short tail
-// instead of T + T/2 steps + a GEMM.
+// ---- layer wavefront -----------------------------------------------------------------------------------------
+// The layers of a pass run CONCURRENTLY as one pipeline: every kernel on its own stream (event fork / join, capturable in a
+// CUDA graph), handing its output to the next stage step by step through release / acquire arrival counters:
+//
+//   forward   forward-model recurrence  ->  pooled post_linear (streaming tcgen05 GEMM: pred_mel + bf16 operand blocks)
+//             ->  embedder layer 0 (fused input projection)  [->  gate GEMM of layer 1 (streaming)  ->  embedder layer 1]
+//   backward  [BPTT layer 1  ->  dX GEMM (streaming, reverse time)  ->]  BPTT layer 0  ->  dX . post_linear^T GEMM (streaming,
+//             combined weights, accumulates onto the mel-loss part)  ->  BPTT forward model
+//
+// A recurrent kernel release-increments counter[group][t] from every epilogue warp once its bf16 image stores of step t are out;
+// a streaming GEMM polls the counter of the last step its tile reads, writes its tile and release-increments counter[group][pair];
+// the consuming recurrence polls that one before it fetches the step's input.  The dependency chain is acyclic, all kernels of a
+// pipeline fit the device together by construction (CTA budget below, one CTA per SM by a shared-memory floor: every kernel
+// allocates the whole tensor memory), so partial residency can only delay, never deadlock.  The critical path of a pass falls from
+// the SUM of the layers' steps (T + T/2 + T/2) to the longest layer (T) plus a short tail.  Bracketed stages join when the batch
+// leaves room for them (<= 48 words); batches beyond 64 words (128 forward) run the serial schedule.
+constexpr int kSide = 4;
 struct SideStreams {
-  cudaStream_t s1 = nullptr, s2 = nullptr;
-  cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+  cudaStream_t s[kSide] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kSide] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 int side_streams(SideStreams** out) {
@@ -158,94 +187,222 @@ int side_streams(SideStreams** out) {
   PAULE_CUDA(cudaGetDevice(&d));
   PAULE_REQUIRE(d >= 0 && d < 64);
   SideStreams& ss = per_device[d];
-  if (ss.s1 == nullptr) {   // first use on this device (BatchPlanner warms up outside graph capture)
-    PAULE_CUDA(cudaStreamCreateWithFlags(&ss.s1, cudaStreamNonBlocking));
-    PAULE_CUDA(cudaStreamCreateWithFlags(&ss.s2, cudaStreamNonBlocking));
+  if (ss.fork == nullptr) {   // first use on this device (BatchPlanner warms up outside graph capture)
+    for (int i = 0; i < kSide; ++i) {
+      PAULE_CUDA(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      PAULE_CUDA(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
+    }
     PAULE_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
-    PAULE_CUDA(cudaEventCreateWithFlags(&ss.join1, cudaEventDisableTiming));
-    PAULE_CUDA(cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming));
   }
   *out = &ss;
   return PAULE_OK;
 }
+int fork_streams(SideStreams* ss, cudaStream_t s, int n) {
+  PAULE_CUDA(cudaEventRecord(ss->fork, s));
+  for (int i = 0; i < n; ++i) PAULE_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
+  return PAULE_OK;
+}
+int join_streams(SideStreams* ss, cudaStream_t s, int n) {
+  for (int i = 0; i < n; ++i) {
+    PAULE_CUDA(cudaEventRecord(ss->join[i], ss->s[i]));
+    PAULE_CUDA(cudaStreamWaitEvent(s, ss->join[i], 0));
+  }
+  return PAULE_OK;
+}
 
-// arrivals that complete one step of 64-word group g: 23 unit groups x 8 epilogue warps per non-empty word quarter
-__global__ void wave_targets_kernel(unsigned int* target, int B, int n_groups) {
+// arrivals that complete one step of 64-word group g: (CTAs per word quarter) x 8 epilogue warps per non-empty quarter
+__global__ void wave_targets_kernel(unsigned int* target_f, unsigned int* target_b, int B, int n_groups) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < n_groups) {
-    const int words = min(64, B - 64 * g);
-    target[g] = (unsigned int)(tc::kWaveArrivalsPerQuarter * ((words + tc::kWq - 1) / tc::kWq));
+    const int words = min(64, B - 64 * g), quarters = (words + tc::kWq - 1) / tc::kWq;
+    target_f[g] = (unsigned int)(tc::kWaveArrivalsPerQuarter * quarters);
+    target_b[g] = (unsigned int)(tc::kWaveArrivalsPerQuarterBwd * quarters);
   }
 }
-// the co-resident recurrence used its own exchange buffer: fold its status word into the plan's (sticky) one
-__global__ void merge_status_kernel(int* dst, const int* src) {
-  const int v = *src;
-  if (v != 0) atomicCAS(dst, 0, v);
+// co-resident recurrences use their own exchange buffers: fold their status words into the plan's (sticky) one
+__global__ void merge_status_kernel(int* dst, const int* a, const int* b) {
+  const int va = *a, vb = *b;
+  if (va != 0) atomicCAS(dst, 0, va);
+  if (vb != 0) atomicCAS(dst, 0, vb);
+  if (a[1] != 0 || b[1] != 0) dst[1] = 1;   // the informational clamp word sits right behind the status word
 }
+inline int* status_of(void* xchg) { return reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(xchg) + tc::kXchgErrOff); }
 
-// CTA budget of the wavefront: forward model in its usual layout + streaming GEMM + embedder layer 0 in the smallest layout
-// that still fits the remaining SMs.  Returns 0 when the three do not fit together (large batches: no wavefront).
-int wavefront_emb0_ctas(const paule_plan* p) {
+struct WavePlan {
+  int fwd = 0;          // 0 serial, 1 forward model || post_linear || embedder l0, 2 + gate GEMM || embedder l1
+  int e0_ctas = 0, e1_ctas = 0;
+  int bwd = 0;          // 0 serial, 2 BPTT l0 || dX GEMM || BPTT forward model (l1 before, alone), 3 all three BPTT kernels
+  int b_nq = 0, g_par = 0;   // quarters per CTA of the co-resident BPTT kernels (one common layout), GEMM CTAs per column tile
+};
+
+// CTA budget: the longest layer (forward model) keeps its latency-optimal layout, the others take the smallest layout that
+// still fits the remaining SMs (clusters of 4: at most 132 co-resident CTAs of the BPTT kernels).
+WavePlan plan_wavefront(const paule_plan* p, bool use_sem) {
   static const bool off = getenv("PAULE_NO_WAVEFRONT") != nullptr;
-  if (off || !tc(p) || p->post_packed == nullptr || (p->T % 2) != 0 || p->T < 8) return 0;
-  const int n_f = tc::fwd2_ctas(p->B, 0);
-  if (n_f == 0) return 0;
-  // the forward model keeps its latency-optimal layout: fewest quarters per CTA that fit one launch
-  const int n_m = tc::gemm_stream_ctas(p->B, p->Cm, 2);
-  const int left = sm_count() - n_f - n_m - 2;
-  return left > 0 ? tc::fwd2_ctas(p->B, left) : 0;
+  static const int fwd_max = getenv("PAULE_WAVEFRONT_FWD") ? atoi(getenv("PAULE_WAVEFRONT_FWD")) : 2;
+  static const int bwd_max = getenv("PAULE_WAVEFRONT_BWD") ? atoi(getenv("PAULE_WAVEFRONT_BWD")) : 3;
+  WavePlan wp;
+  if (off || !tc(p) || p->post_packed == nullptr || (p->T % 2) != 0 || p->T < 8) return wp;
+  const int sm = sm_count() - 2;
+  const int64_t B = p->B;
+  const int n_f = tc::fwd2_ctas(B, 0);
+  if (n_f > 0 && fwd_max >= 1) {
+    const int n_m = tc::gemm_stream_ctas(B, p->Cm, 2), n_g1 = tc::gemm_stream_ctas(B, 4 * p->H, 1);
+    // (a budget <= 0 must not reach fwd2_ctas: 0 means "no limit" there)
+    const int left2 = (sm - n_f - n_m - n_g1) / 2, left1 = sm - n_f - n_m;
+    const int e2 = left2 > 0 ? tc::fwd2_ctas(B, left2) : 0;
+    if (fwd_max >= 2 && e2 > 0) {
+      wp.fwd = 2; wp.e0_ctas = wp.e1_ctas = e2;
+    } else {
+      const int e1 = left1 > 0 ? tc::fwd2_ctas(B, left1) : 0;
+      if (e1 > 0) { wp.fwd = 1; wp.e0_ctas = e1; }
+    }
+  }
+  if (use_sem && p->bwd_fused_packed != nullptr && p->word_frames == nullptr && B <= 64 && bwd_max >= 2) {
+    // BPTT kernels that run side by side must be ONE instantiation of the kernel template (measured: two different
+    // instantiations of the cluster kernel running concurrently fault with "unspecified launch failure", the same one runs
+    // fine) -- so the pipeline picks one common number of quarters per CTA, by estimated time of the pass.  us per step of the
+    // BPTT kernel by quarters per CTA (tools/rnn_time.py, <= 64 words per group):
+    static const float us_step[5] = {0.f, 2.85f, 3.4f, 5.5f, 8.0f};   // 3 / 4 quarters: as measured side by side with two more kernels
+    const float serial = (float)(p->T + 2 * (p->T / 2)) * us_step[tc::bwd2_default_nq(B)];
+    float best = serial * 0.97f;   // a pipeline has to be worth its fork / join
+    for (int mode = min(bwd_max, 3); mode >= 2; --mode) {
+      for (int nq = 1; nq <= 4; ++nq) {
+        const int n_b = tc::bwd2_ctas(B, nq), kernels = mode;   // mode 3: l1, l0, forward model; mode 2: l0, forward model
+        if (n_b == 0 || kernels * n_b > 132) continue;
+        int par = 0;
+        for (int c = 4; c >= 2 && par == 0; c -= 2)
+          if (kernels * n_b + (mode - 1) * tc::gemm_stream_ctas(B, p->H, c) <= sm) par = c;
+        if (par == 0) continue;
+        const float est = (float)p->T * us_step[nq] + (mode == 2 ? (float)(p->T / 2) * us_step[tc::bwd2_default_nq(B)] : 0.f);
+        if (est < best) { best = est; wp.bwd = mode; wp.b_nq = nq; wp.g_par = par; }
+      }
+    }
+  }
+  // debugging overrides of the backward pipeline's layout
+  static const int force_nq = getenv("PAULE_WAVE_BNQ") ? atoi(getenv("PAULE_WAVE_BNQ")) : 0;
+  static const int force_par = getenv("PAULE_WAVE_PAR") ? atoi(getenv("PAULE_WAVE_PAR")) : 0;
+  if (wp.bwd != 0 && force_nq > 0) wp.b_nq = force_nq;
+  if (wp.bwd != 0 && force_par > 0) wp.g_par = force_par;
+  return wp;
 }
 
-int forward_wavefront(const paule_plan* p, const Workspace& w, int emb0_ctas, paule_stream_t stream) {
-  const int64_t B = p->B, T = p->T, Tm = T / 2, Cm = p->Cm;
-  const int n_groups = (int)((B + 63) / 64), x_pairs = (int)((Tm + 1) / 2);
+int zero_wave_flags(const paule_plan* p, const Workspace& w, cudaStream_t s) {
+  const int n_groups = (int)((p->B + 63) / 64);
+  PAULE_CUDA(cudaMemsetAsync(w.wf_flags, 0, sizeof(unsigned int) * w.wf_flag_count, s));
+  wave_targets_kernel<<<(n_groups + 63) / 64, 64, 0, s>>>(w.wf_target, w.wf_target_b, (int)p->B, n_groups);
+  PAULE_LAUNCH_CHECK("wave_targets_kernel");
+  return PAULE_OK;
+}
+
+int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& wp, paule_stream_t stream) {
+  const int64_t B = p->B, T = p->T, Tm = T / 2, Cm = p->Cm, H = p->H;
+  const int P = (int)((Tm + 1) / 2);
   cudaStream_t s = as_stream(stream);
   SideStreams* ss = nullptr;
   PAULE_TRY(side_streams(&ss));
-  int* status = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg) + tc::kXchgErrOff);
-  int* status2 = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg2) + tc::kXchgErrOff);
-  PAULE_CUDA(cudaMemsetAsync(w.wf_img_flags, 0, sizeof(unsigned int) * (size_t)n_groups * T, s));
-  PAULE_CUDA(cudaMemsetAsync(w.wf_x_flags, 0, sizeof(unsigned int) * (size_t)n_groups * x_pairs, s));
-  wave_targets_kernel<<<(n_groups + 63) / 64, 64, 0, s>>>(w.wf_target, (int)B, n_groups);
-  PAULE_LAUNCH_CHECK("wave_targets_kernel");
+  const int n_side = wp.fwd == 2 ? 4 : 2;
+  PAULE_TRY(zero_wave_flags(p, w, s));
   PAULE_TRY(paule_tc_x_image(p->cp, w.x_img_f, T, B, p->C, stream));
-  PAULE_CUDA(cudaEventRecord(ss->fork, s));
-  PAULE_CUDA(cudaStreamWaitEvent(ss->s1, ss->fork, 0));
-  PAULE_CUDA(cudaStreamWaitEvent(ss->s2, ss->fork, 0));
+  PAULE_TRY(fork_streams(ss, s, n_side));
   // (1) forward-model recurrence, T steps, announces every h_t image
   PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_f, p->fwd.packed, p->fwd.bias, w.x_img_f, nullptr, w.c_f, w.xchg, w.hf_img, T, B, s,
-                               tc::WaveFlags{w.wf_img_flags, nullptr, 0}, 0));
+                               tc::WaveFlags{w.f_hf, nullptr, 0, 0u}, 0));
   // (2) pooled post_linear, streaming: pred_mel + operand blocks of embedder layer 0
-  PAULE_TRY(tc::gemm_img_stream(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, w.wf_img_flags, w.wf_target, 2,
-                                w.wf_x_flags, w.x_img_0, 2, status, ss->s1));
-  // (3) embedder layer 0, fed step by step
+  PAULE_TRY(tc::gemm_img_stream(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, w.f_hf, w.wf_target, 2, w.f_x0,
+                                w.x_img_0, 2, status_of(w.xchg), ss->s[0]));
+  // (3) embedder layer 0, fed step by step; announces its h images when layer 1 runs in the pipeline too
   PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_0, p->emb0.packed, p->emb0.bias, w.x_img_0, nullptr, w.c_0, w.xchg2, w.h_img, Tm, B,
-                               ss->s2, tc::WaveFlags{nullptr, w.wf_x_flags, x_pairs}, emb0_ctas));
-  PAULE_CUDA(cudaEventRecord(ss->join1, ss->s1));
-  PAULE_CUDA(cudaEventRecord(ss->join2, ss->s2));
-  PAULE_CUDA(cudaStreamWaitEvent(s, ss->join1, 0));
-  PAULE_CUDA(cudaStreamWaitEvent(s, ss->join2, 0));
-  merge_status_kernel<<<1, 1, 0, s>>>(status, status2);
+                               ss->s[1], tc::WaveFlags{wp.fwd == 2 ? w.f_h0 : nullptr, w.f_x0, P, tc::gemm_stream_arrivals(Cm)},
+                               wp.e0_ctas));
+  if (wp.fwd == 2) {
+    // (4) the gate GEMM over all time steps, streaming: Xp1 = h_0 W_ih1^T + b
+    PAULE_TRY(tc::gemm_img_stream(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, w.f_h0, w.wf_target, 1,
+                                  w.f_g1, nullptr, 1, status_of(w.xchg), ss->s[2]));
+    // (5) embedder layer 1: its cell warps wait for the pre-activations of the step
+    PAULE_TRY(tc::lstm_seq_fwd2(w.gates_1, p->emb1.packed, w.h_1, w.c_1, w.xchg3, nullptr, Tm, B, ss->s[3],
+                                tc::WaveFlags{nullptr, w.f_g1, P, tc::gemm_stream_arrivals(4 * H)}, wp.e1_ctas));
+  }
+  PAULE_TRY(join_streams(ss, s, n_side));
+  merge_status_kernel<<<1, 1, 0, s>>>(status_of(w.xchg), status_of(w.xchg2), status_of(w.xchg3));
   PAULE_LAUNCH_CHECK("merge_status_kernel");
   return PAULE_OK;
 }
 
-// embedder layer 1 + head on the images / stash layer 0 left behind
-int embed_top(const paule_plan* p, const Workspace& w, float* sv, paule_stream_t s) {
-  const int64_t B = p->B, H = p->H, Tm = p->T / 2, S = p->S;
-  if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
-    PAULE_TRY(tc::gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0,
-                           reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(w.xchg) + tc::kXchgErrOff), as_stream(s)));
+// BPTT of the embedder (both layers, or layer 0 only) and of the forward model as one reverse-time pipeline.  On entry dhp holds
+// the mel-loss part d(mel term)/d(pooled h) = dmel W_post; the streaming GEMM adds dA_0 (W_ih0 W_post) step by step.
+int backward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& wp, paule_stream_t stream) {
+  const int64_t B = p->B, T = p->T, Tm = T / 2, H = p->H;
+  const int P = (int)((Tm + 1) / 2);
+  cudaStream_t s = as_stream(stream);
+  SideStreams* ss = nullptr;
+  PAULE_TRY(side_streams(&ss));
+  const unsigned int g_arr = tc::gemm_stream_arrivals(H);
+  PAULE_TRY(zero_wave_flags(p, w, s));
+  if (wp.bwd == 2)   // layer 1 first, alone, in its usual layout; its dX GEMM as a batch GEMM
+    PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, stream));
+  // PAULE_WAVE_SERIALIZE=1 (debugging): the same kernels with the same flags, one after the other on one stream in dependency
+  // order -- every wait finds its counter complete
+  static const bool serialize = getenv("PAULE_WAVE_SERIALIZE") != nullptr;
+  const int n_side = wp.bwd == 3 ? 4 : 2;
+  cudaStream_t sBF = s, sB0 = serialize ? s : ss->s[0], sG0 = serialize ? s : ss->s[1], sB1 = serialize ? s : ss->s[2],
+               sG1 = serialize ? s : ss->s[3];
+  if (!serialize) PAULE_TRY(fork_streams(ss, s, n_side));
+  auto run_bf = [&]() {   // forward model (the longest layer), usual layout; waits for dhp pair by pair
+    return tc::lstm_seq_bwd2(w.gates_f, w.c_f, p->fwd.packed, w.dhp, 2, nullptr, w.xchg, w.da_img, T, B, 0, sBF,
+                             tc::WaveFlags{nullptr, w.f_dhp, P, g_arr}, wp.b_nq);
+  };
+  auto run_b0 = [&]() {   // embedder layer 0: announces its dA images; in the three-kernel pipeline it waits for dh0 pair by pair
+    return tc::lstm_seq_bwd2(w.gates_0, w.c_0, p->emb0.packed, w.dh0, 1, nullptr, w.xchg2, w.da_img_0, Tm, B, 0, sB0,
+                             tc::WaveFlags{w.f_da0, wp.bwd == 3 ? w.f_dh0 : nullptr, P, g_arr}, wp.b_nq);
+  };
+  auto run_g0 = [&]() {   // dhp += dA_0 (W_ih0 W_post): streaming, reverse time, accumulating onto the mel-loss part
+    return tc::gemm_img_stream(w.da_img_0, p->bwd_fused_packed, nullptr, w.dhp, Tm, B, H, 4, w.f_da0, w.wf_target_b, 1, w.f_dhp,
+                               nullptr, wp.g_par, status_of(w.xchg), sG0, 1, 1);
+  };
+  auto run_b1 = [&]() {
+    return tc::lstm_seq_bwd2(w.gates_1, w.c_1, p->emb1.packed, nullptr, 0, w.dh1_last, w.xchg3, w.da_img_1, Tm, B, 0, sB1,
+                             tc::WaveFlags{w.f_da1, nullptr, 0, 0u}, wp.b_nq);
+  };
+  auto run_g1 = [&]() {   // dh0 = dA_1 W_ih1: streaming, reverse time
+    return tc::gemm_img_stream(w.da_img_1, p->emb1.packed_ih_t, nullptr, w.dh0, Tm, B, H, 4, w.f_da1, w.wf_target_b, 1, w.f_dh0,
+                               nullptr, wp.g_par, status_of(w.xchg), sG1, 1, 0);
+  };
+  if (serialize) {
+    if (wp.bwd == 3) { PAULE_TRY(run_b1()); PAULE_TRY(run_g1()); }
+    PAULE_TRY(run_b0()); PAULE_TRY(run_g0()); PAULE_TRY(run_bf());
   } else {
-    PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
+    PAULE_TRY(run_bf()); PAULE_TRY(run_b0()); PAULE_TRY(run_g0());
+    if (wp.bwd == 3) { PAULE_TRY(run_b1()); PAULE_TRY(run_g1()); }
+    PAULE_TRY(join_streams(ss, s, n_side));
   }
-  PAULE_TRY(recur_forward(p, p->emb1, Tm, w.gates_1, w.h_1, w.c_1, w, nullptr, s));
+  merge_status_kernel<<<1, 1, 0, s>>>(status_of(w.xchg), status_of(w.xchg2), status_of(w.xchg3));
+  PAULE_LAUNCH_CHECK("merge_status_kernel");
+  // d(cp) = dA_f W_ih (batch GEMM over the images the forward model's BPTT left)
+  return tc::gemm_img(w.da_img, p->fwd.packed_ih_t, nullptr, w.dcp_lstm, T, B, p->fwd.input_size, 4, 0, status_of(w.xchg), s);
+}
+
+// head of the embedder: semvec from layer 1's output at the last frame (every word's own last frame in ragged batches)
+int embed_head(const paule_plan* p, const Workspace& w, float* sv, paule_stream_t s) {
+  const int64_t B = p->B, H = p->H, Tm = p->T / 2, S = p->S;
   const float* h_last = w.h_1 + (Tm - 1) * B * H;
   if (p->word_frames) {   // ragged: every word's own last mel frame (models.py:442); dh1_last is free until the backward
     PAULE_TRY(gather_last(w.h_1, p->word_frames, w.dh1_last, B, H, s));
     h_last = w.dh1_last;
   }
   return paule_linear_f32(h_last, p->head_w, p->head_b, sv, B, S, H, 1, H, 0, 0, 1, S, 0, 0, s);
+}
+
+// embedder layer 1 + head on the images / stash layer 0 left behind
+int embed_top(const paule_plan* p, const Workspace& w, float* sv, paule_stream_t s) {
+  const int64_t B = p->B, H = p->H, Tm = p->T / 2;
+  if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
+    PAULE_TRY(tc::gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, status_of(w.xchg), as_stream(s)));
+  } else {
+    PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
+  }
+  PAULE_TRY(recur_forward(p, p->emb1, Tm, w.gates_1, w.h_1, w.c_1, w, nullptr, s));
+  return embed_head(p, w, sv, s);
 }
 
 // EmbeddingModel (models.py:440-448) on a time-major mel [Tm,B,Cm] -> sv [B,S]; lens = Tm for every word (paule.py:922-924)
@@ -259,10 +416,14 @@ int embed_models(const paule_plan* p, const Workspace& w, const float* mel, floa
 int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s) {
   const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, Cm = p->Cm;
   if (need_semvec) {
-    // batches that leave room for it: forward model, pooled post_linear and embedder layer 0 as ONE pipeline
-    const int emb0_ctas = wavefront_emb0_ctas(p);
-    if (emb0_ctas > 0) {
-      PAULE_TRY(forward_wavefront(p, w, emb0_ctas, s));
+    // batches that leave room for it: the layers of the forward pass as ONE pipeline
+    const WavePlan wp = plan_wavefront(p, false);
+    if (wp.fwd == 2) {
+      PAULE_TRY(forward_wavefront(p, w, wp, s));
+      return embed_head(p, w, p->pred_sv, s);
+    }
+    if (wp.fwd == 1) {
+      PAULE_TRY(forward_wavefront(p, w, wp, s));
       return embed_top(p, w, p->pred_sv, s);
     }
   }
@@ -335,6 +496,17 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
                              need_sv ? p->target_sv : nullptr, p->cp, p->loss_log, p->step_count, p->log_slot_count,
                              w.dmel, w.dsv, w.dcp_smooth, w.partial, T, Tm, p->word_frames, B, C, Cm, S, p->objective,
                              s, p->cls_w, p->cls_b, p->extra_terms, p->aux_log));  // :986
+  const WavePlan wp = plan_wavefront(p, use_sem);
+  if (use_sem && wp.bwd != 0) {                                                    // discrepancy.backward(), :1052, as a pipeline
+    PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));   // dh1[Tm-1] = dsv W_head
+    // mel-loss part of d/d(pooled h); the un-pooling (x0.5 to both frames of a pair) is folded into the BPTT's dh load
+    PAULE_TRY(paule_linear_f32(w.dmel, p->post_w_t, nullptr, w.dhp, Tm * B, H, Cm, 1, Cm, 0, 0, 1, H, 0, 0, s));
+    PAULE_TRY(backward_wavefront(p, w, wp, s));
+    PAULE_TRY(adam_clamp_logged(p->cp, w.dcp_lstm, w.dcp_smooth, p->adam_m, p->adam_v, p->step_count, p->lr, p->beta1,
+                                p->beta2, p->eps, p->clamp, p->smiling, p->past_cp, p->past_T, p->grad_out, T, B, C, s,
+                                p->extra_grad));
+    return PAULE_OK;
+  }
   if (use_sem) {                                                                   // discrepancy.backward(), :1052
     // head: dh1[Tm-1] = dsv W_head
     PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));

@@ -84,6 +84,7 @@ struct GemmStream {
   int* status;                     // sticky status word (watchdog), or nullptr
   int src_per_step;                // source steps per output step (2: pooled post_linear over frame pairs)
   int n_par;                       // CTAs that alternate over the step pairs of one (group, column tile)
+  int reverse;                     // the producer runs backwards in time (BPTT): pairs from the last to the first
 };
 
 template <bool STREAM>
@@ -110,6 +111,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
     if (STREAM) {
       const int cta = (int)blockIdx.x / st.n_par;
       nt = cta % n_nt; grp = cta / n_nt; sp = (int)(blockIdx.x % st.n_par) + tile * st.n_par;
+      if (st.reverse) sp = n_pairs - 1 - sp;
     } else {
       nt = tile % n_nt; const int rest = tile / n_nt; sp = rest % n_pairs; grp = rest / n_pairs;
     }
@@ -140,7 +142,8 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
       if (STREAM) {
         // the producing recurrent kernel has finished the last source step this tile reads (steps complete in order)
         const int src_steps = steps * st.src_per_step;
-        const int last = min((t0 + 2) * st.src_per_step, src_steps) - 1;
+        // forward producers finish the tile's LAST source step last, reverse-time producers its FIRST one
+        const int last = st.reverse ? t0 * st.src_per_step : min((t0 + 2) * st.src_per_step, src_steps) - 1;
         const unsigned int* f = st.src_flags + (size_t)grp * src_steps + last;
         const unsigned int want = st.src_target[grp];
         uint64_t w0 = 0;
@@ -327,21 +330,26 @@ int gemm_stream_ctas(int64_t B, int64_t N, int n_par) {
   const int np = pad_n((int)N), bn = pick_bn(np);
   return (int)((B + kRows - 1) / kRows) * (np / bn) * n_par;
 }
+// arrivals that complete one pair of output steps in dst_flags: 4 epilogue warps per column tile
+unsigned int gemm_stream_arrivals(int64_t N) {
+  const int np = pad_n((int)N), bn = pick_bn(np);
+  return 4u * (unsigned int)(np / bn);
+}
 
 // the GEMM of paule_tc_gemm_img in streaming mode (see GemmStream); `status` may be NULL
 int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
                     int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
-                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s) {
+                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s, int reverse, int accumulate) {
   PAULE_REQUIRE(a_img && packed_b && C && steps > 0 && B > 0 && N > 0 && nseg > 0 && nseg <= 4 && src_flags && src_target);
   PAULE_REQUIRE(n_par >= 1 && (x_out == nullptr || N <= kXK));
   PAULE_TRY(gemm_attrs());
   const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
   const int smem_own = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
   const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // never shares an SM (tensor memory)
-  GemmStream st{src_flags, src_target, dst_flags, reinterpret_cast<uint8_t*>(x_out), status, src_per_step, n_par};
+  GemmStream st{src_flags, src_target, dst_flags, reinterpret_cast<uint8_t*>(x_out), status, src_per_step, n_par, reverse};
   tc_gemm_img_kernel<true><<<gemm_stream_ctas(B, N, n_par), kGemmThreads, (size_t)smem, s>>>(
       reinterpret_cast<const uint8_t*>(a_img), reinterpret_cast<const uint8_t*>(packed_b), bias, C, (int)steps, (int)B, (int)N,
-      KB, bn, 0, st);
+      KB, bn, accumulate, st);
   PAULE_LAUNCH_CHECK("tc_gemm_img_kernel<stream>");
   return PAULE_OK;
 }

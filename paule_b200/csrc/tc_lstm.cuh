@@ -44,8 +44,10 @@ constexpr int kRows = 64;               // words per image group (rows of a bf16
 
 // exchange buffer: header + exchange blocks
 constexpr int kXchgHeader = 4096;   // status word, trace / timeline words
-constexpr int kXchgErrOff = 2048;    // int: 0 ok, 1 exchange watchdog fired, 2 mbarrier watchdog fired, 3 (sticky, informational:
-                                     // results stay valid up to the stated bound) a recurrent gradient was clamped / non-finite
+constexpr int kXchgErrOff = 2048;    // int: 0 ok, 1 exchange watchdog fired, 2 mbarrier watchdog fired (every wait loop of the
+                                     // kernels bails out once this word is non-zero: results are invalid)
+constexpr int kXchgClampOff = 2052;  // int, sticky and informational (must NOT stop the kernels): 1 = the BPTT kernel clamped a
+                                     // recurrent gradient to the +-1.5 bound of the in-band exchange, or it was NaN / Inf
 constexpr int kXchgTraceOff = 3072;  // PAULE_TC_TRACE builds only
 constexpr int kXchgImageBytes = kNumKB * kRows * 128;  // 98304: one bf16 image [12 kb][64 rows][128 B]
 
@@ -252,7 +254,9 @@ struct WaveFlags {
   unsigned int* img_flags;        // producer side, or nullptr
   const unsigned int* x_flags;    // consumer side, or nullptr
   int x_pairs;                    // pairs of steps per word group in x_flags
+  unsigned int x_target;          // arrivals that complete a pair (4 epilogue warps x column tiles of the streaming GEMM)
 };
+constexpr WaveFlags kNoWave = {nullptr, nullptr, 0, 0u};
 constexpr int kWaveArrivalsPerQuarter = kFwd2Groups * 8;   // 23 unit groups x 8 epilogue warps per (step, word quarter)
 // Kernels that run side by side in the wavefront all allocate the SM's whole tensor memory: two of their CTAs on one SM would
 // park the second in tcgen05.alloc until the first exits -- a deadlock when the first (transitively) waits for the second.
@@ -263,11 +267,10 @@ constexpr int kExclusiveSmemBytes = 117 * 1024;
 int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cudaStream_t s);
 int x_image(const float* x, void* img, int64_t T, int64_t B, int64_t I, cudaStream_t s);
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
-                  cudaStream_t s);
+                  cudaStream_t s, WaveFlags wf = kNoWave, int max_ctas = 0);
 // fused input projection: gates is output only (the activated-gate stash), pre-activations = W_hh h + W_ih x_t + bias
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf = WaveFlags{nullptr, nullptr, 0},
-                   int max_ctas = 0);
+                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf = kNoWave, int max_ctas = 0);
 // CTAs lstm_seq_fwd2x launches for B words when at most max_ctas (0: no limit) may be used; 0 = does not fit one launch
 int fwd2_ctas(int64_t B, int max_ctas);
 // batched tcgen05 GEMM over image sequences (tc_gemm.cu): batch mode with a status word, streaming mode for the wavefront
@@ -275,10 +278,16 @@ int gemm_img(const void* a_img, const void* packed_b, const float* bias, float* 
              int64_t nseg, int accumulate, int* status, cudaStream_t s);
 int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
                     int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
-                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s);
+                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s, int reverse = 0,
+                    int accumulate = 0);
 int gemm_stream_ctas(int64_t B, int64_t N, int n_par);
+unsigned int gemm_stream_arrivals(int64_t N);
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                  void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s);
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf = kNoWave,
+                  int force_nq = 0);
+int bwd2_ctas(int64_t B, int nq);
+int bwd2_default_nq(int64_t B);
+constexpr int kWaveArrivalsPerQuarterBwd = kBwd2Groups * 4 * 8;   // 24 CTAs x 8 cell warps per (step, word quarter)
 
 }  // namespace tc
 }  // namespace paule

@@ -91,7 +91,8 @@ template <int NQ, int EG>
 __global__ void __launch_bounds__(b2_threads(EG), 1)
 tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed,
                     const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
-                    uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0, int keep_da) {
+                    uint8_t* __restrict__ xchg, uint8_t* __restrict__ img_seq, int T, int Bv, int Bs, int w0, int keep_da,
+                    WaveFlags wf) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = Bwd2Smem<NQ>;
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,6 +228,21 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           s_o = *reinterpret_cast<const float2*>(grow + 3 * kH + j);
           ct = *reinterpret_cast<const float2*>(c_seq + ((size_t)t * Bs + wp) * kH + j);
           if (t > 0) cp = *reinterpret_cast<const float2*>(c_seq + ((size_t)(t - 1) * Bs + wp) * kH + j);
+          if (wf.x_flags != nullptr && dh_mode != 0 && (dh_mode == 1 || (t >> 1) < (T >> 1))) {
+            // layer wavefront: the external gradient of this step is produced while this kernel runs (streaming dX GEMM over the
+            // dA images of the layer above, reverse time) -- wait until its pair of steps has been released for this word group
+            const int src = dh_mode == 1 ? t : (t >> 1);
+            const unsigned int* f = wf.x_flags + (size_t)((w0 + wp) / kRows) * wf.x_pairs + (src >> 1);
+            uint64_t wd0 = 0;
+            for (unsigned int spin = 0; ld_acquire_u32(f) < wf.x_target; ++spin) {
+              __nanosleep(100);
+              if ((spin & 255u) == 255u) {
+                if (wd0 == 0) wd0 = globaltimer_ns();
+                if (*err != 0) break;
+                if (globaltimer_ns() - wd0 > kWatchdogNs) { *err = 1; break; }
+              }
+            }
+          }
           if (dh_mode == 1) {
             dh = *reinterpret_cast<const float2*>(dh_seq + ((size_t)t * Bs + wp) * kH + j);
           } else if (dh_mode == 2 && (t >> 1) < (T >> 1)) {
@@ -305,12 +321,13 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
           xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
           xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
           // off the critical path: a gradient beyond the +-1.5 exchange bound (or NaN / Inf) was clamped above -- record it
-          // (sticky status 3; the watchdog codes 1 / 2 take priority) so that the caller learns its results deviate
+          // in the header's informational word (NOT the status word: the wait loops abort on that one) so that the caller learns
+          // its results deviate
           const float mx = fmaxf(fmaxf(fmaxf(fabsf(d_i.x), fabsf(d_i.y)), fmaxf(fabsf(d_f.x), fabsf(d_f.y))),
                                  fmaxf(fmaxf(fabsf(d_g.x), fabsf(d_g.y)), fmaxf(fabsf(d_o.x), fabsf(d_o.y))));
           const bool nan = (d_i.x != d_i.x) || (d_i.y != d_i.y) || (d_f.x != d_f.x) || (d_f.y != d_f.y) || (d_g.x != d_g.x) ||
                            (d_g.y != d_g.y) || (d_o.x != d_o.x) || (d_o.y != d_o.y);
-          if (!(mx < 1.5f) || nan) atomicCAS(reinterpret_cast<int*>(xchg + kXchgErrOff), 0, 3);
+          if (!(mx < 1.5f) || nan) *reinterpret_cast<volatile int*>(xchg + kXchgClampOff) = 1;
         }
         if (tl0) TL(12, q, it)   // epilogue: quarter published
         TRACE(5)
@@ -332,6 +349,11 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
             *reinterpret_cast<float2*>(grow + 2 * kH + j) = d_g;
             *reinterpret_cast<float2*>(grow + 3 * kH + j) = d_o;
           }
+        }
+        if (wf.img_flags != nullptr && (grp * NQ + q) * kWq < Bv) {
+          // layer wavefront: this warp's dA image stores of step t are out -- one release-arrival per (step, quarter, warp)
+          __syncwarp();
+          if (lane == 0) red_release_add_u32(wf.img_flags + (size_t)((w0 + (grp * NQ + q) * kWq) / kRows) * (size_t)T + t, 1u);
         }
         if (tl0) TL(13, q, it)   // epilogue: image / stash stores issued
         TRACE(6)
@@ -358,9 +380,10 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 
 template <int NQ, int EG>
 int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
+                void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf) {
   static unsigned long long attr_set = 0ull;
-  const int smem = (int)sizeof(Bwd2Smem<NQ>) + 1024;
+  const int smem_own = (int)sizeof(Bwd2Smem<NQ>) + 1024;
+  const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // one CTA per SM, whatever runs beside it
   if (once_per_device(attr_set)) {
     PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
@@ -393,23 +416,35 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
     uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
     PAULE_CUDA(cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
-                                  (int)r0, keep_da));
+                                  (int)r0, keep_da, wf));
   }
   return PAULE_OK;
 }
 
+// CTAs of one launch that holds B words with nq quarters per CTA; 0 = does not fit one launch (at most kMaxQBwd word groups)
+int bwd2_ctas(int64_t B, int nq) {
+  if (nq < 1 || nq > 4) return 0;
+  const int64_t quarters = (B + kWq - 1) / kWq, groups = (quarters + nq - 1) / nq;
+  return groups <= kMaxQBwd ? (int)groups * kBwd2Groups * 4 : 0;
+}
+int bwd2_default_nq(int64_t B) { return choose_nq(B, kMaxQBwd); }
+
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                  void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s) {
+                  void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int force_nq) {
   // two quarters per CTA: two epilogue groups, one quarter each (4.57 -> 3.62 us per step at 128 words).  With three or four
   // quarters a second group measured 4-6 % SLOWER (contiguous halves; 20 % slower interleaved) and is not used.
   // PAULE_RNN_EG=1 restores one group everywhere (A/B timing).
   static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
-  const int nq = choose_nq(B, kMaxQBwd);
-  if (nq == 1) return launch_bwd2<1, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-  if (nq == 2 && !one_group) return launch_bwd2<2, 2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-  if (nq == 2) return launch_bwd2<2, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-  if (nq == 3) return launch_bwd2<3, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
-  return launch_bwd2<4, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s);
+  int nq = choose_nq(B, kMaxQBwd);
+  if (force_nq > 0) {   // layer wavefront: BPTT kernels that run side by side must be the SAME instantiation (see plan_step.cu)
+    if (bwd2_ctas(B, force_nq) == 0) return PAULE_ERR_ARG;
+    nq = force_nq;
+  }
+  if (nq == 1) return launch_bwd2<1, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
+  if (nq == 2 && !one_group) return launch_bwd2<2, 2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
+  if (nq == 2) return launch_bwd2<2, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
+  if (nq == 3) return launch_bwd2<3, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
+  return launch_bwd2<4, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
 }
 
 }  // namespace tc

@@ -200,7 +200,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
         uint64_t wd0 = 0;
         for (int g64 = q_first / 4; g64 <= (q_first + nvq - 1) / 4; ++g64) {
           const unsigned int* f = wf.x_flags + (size_t)g64 * wf.x_pairs + (t >> 1);
-          for (unsigned int spin = 0; ld_acquire_u32(f) < 4u; ++spin) {
+          for (unsigned int spin = 0; ld_acquire_u32(f) < wf.x_target; ++spin) {
             __nanosleep(100);
             if ((spin & 255u) == 255u) {
               if (wd0 == 0) wd0 = globaltimer_ns();
@@ -333,13 +333,28 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
           for (int g = 0; g < 4; ++g) xp[g][0] = xp[g][1] = bias4[g];
           return;
         }
+        if (wf.x_flags != nullptr && grp * kGW + q * kWq < Bv) {
+          // layer wavefront: the pre-activations x_t W_ih^T + b are produced while this kernel runs (streaming gate GEMM over the
+          // images of the layer below) -- wait until the pair of steps that holds step t has been released for this quarter's
+          // 64-word group
+          const unsigned int* f = wf.x_flags + (size_t)((w0 + grp * kGW + q * kWq) / kRows) * wf.x_pairs + (t >> 1);
+          uint64_t wd0 = 0;
+          for (unsigned int spin = 0; ld_acquire_u32(f) < wf.x_target; ++spin) {
+            __nanosleep(100);
+            if ((spin & 255u) == 255u) {
+              if (wd0 == 0) wd0 = globaltimer_ns();
+              if (*err != 0) break;
+              if (globaltimer_ns() - wd0 > kWatchdogNs) { *err = 1; break; }
+            }
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int wp = grp * kGW + q * kWq + wl0 + k;
           const bool ok = uvalid && wp < Bv;
           const float* grow = gates + ((size_t)t * Bs + (ok ? wp : 0)) * (4 * kH) + (uvalid ? u : 0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) xp[g][k] = ok ? __ldg(grow + g * kH) : 0.f;
+          for (int g = 0; g < 4; ++g) xp[g][k] = ok ? __ldcg(grow + g * kH) : 0.f;   // L2-coherent: may be written by a co-resident kernel
         }
       };
       load_xp(kByQ ? eg : eg * QS);                // this group's first quarter
@@ -575,8 +590,13 @@ int fwd2_ctas(int64_t B, int max_ctas) {
 }
 
 int lstm_seq_fwd2(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq, int64_t T, int64_t B,
-                  cudaStream_t s) {
-  return dispatch_fwd2<false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s, WaveFlags{nullptr, nullptr, 0}, 1);
+                  cudaStream_t s, WaveFlags wf, int max_ctas) {
+  int nq_min = 1;
+  if (max_ctas > 0) {
+    nq_min = nq_for(B, max_ctas);
+    if (nq_min == 0) return PAULE_ERR_ARG;
+  }
+  return dispatch_fwd2<false>(gates, packed, nullptr, nullptr, h, c, xchg, h_img_seq, T, B, s, wf, nq_min);
 }
 
 int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,

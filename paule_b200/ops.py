@@ -251,8 +251,8 @@ CLAMPED_MSG = ("a recurrent-path gradient of the bf16 BPTT kernel reached the +-
 
 
 def _tc_check(xchg: torch.Tensor) -> None:
-    code = int(xchg[2048:2052].view(torch.int32).item())     # kXchgErrOff; one 4-byte read per model call
-    if code == 3:      # module-level autograd (continue-learning, user losses): a silently clamped gradient is an error
+    code, clamped = (int(v) for v in xchg[2048:2056].view(torch.int32).tolist())   # kXchgErrOff, kXchgClampOff: one 8-byte read
+    if clamped:        # module-level autograd (continue-learning, user losses): a silently clamped gradient is an error
         raise _lib.PauleB200Error(CLAMPED_MSG)
     if code != 0:
         raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")

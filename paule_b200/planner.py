@@ -192,6 +192,15 @@ class BatchPlanner:
             self.post_packed = torch.empty(lib.paule_tc_gemm_packed_bytes(n_out, 2), dtype=torch.uint8, device=w2.device)
             _lib.check(lib.paule_tc_gemm_pack(w2.data_ptr(), self.post_packed.data_ptr(), n_out, 2, ops._stream()),
                        "paule_tc_gemm_pack")
+        self.bwd_fused_packed = None
+        if self._tc:
+            # backward layer wavefront: d/d(pooled forward-model h) = dA_0 (W_ih0 W_post) in one streaming GEMM -- the weights
+            # as the GEMM wants them: [N = H, K = 4H] = post_linear.weight^T x weight_ih_l0^T
+            lib = _lib.load()
+            wc = (self.post_w.t() @ self.w_e0.w_ih.t()).contiguous()
+            self.bwd_fused_packed = torch.empty(lib.paule_tc_gemm_packed_bytes(wc.shape[0], 4), dtype=torch.uint8, device=wc.device)
+            _lib.check(lib.paule_tc_gemm_pack(wc.data_ptr(), self.bwd_fused_packed.data_ptr(), wc.shape[0], 4, ops._stream()),
+                       "paule_tc_gemm_pack")
         self.head_w, self.head_b = _f32c(e.linear_mapping.weight), _f32c(e.linear_mapping.bias)
         self.head_w_t = self.head_w.t().contiguous()
         if getattr(self, "_struct", None) is not None:
@@ -224,6 +233,7 @@ class BatchPlanner:
         s.extra_terms = None if self.soma is None else self.soma.extra_terms.data_ptr()
         s.extra_grad = None if self.soma is None else self.soma.extra_grad.data_ptr()
         s.aux_log = None if self.aux_log is None else self.aux_log.data_ptr()
+        s.bwd_fused_packed = None if self.bwd_fused_packed is None else self.bwd_fused_packed.data_ptr()
         self._struct = s
 
     def struct_ref(self):
@@ -331,12 +341,11 @@ class BatchPlanner:
         """Raise if a persistent kernel's watchdog fired (an inter-CTA wait exceeded 4 s: results are invalid).  One 4-byte
         device->host read; called whenever results leave the planner, never inside the inner loop."""
         if self._status_off is not None:
-            code = int(self.workspace[self._status_off:self._status_off + 4].view(torch.int32).item())
-            if code == 3:     # sticky, informational: a recurrent gradient hit the exchange bound of the bf16 BPTT kernel
-                if not self._warned_clamp:
-                    warnings.warn(ops.CLAMPED_MSG, RuntimeWarning, stacklevel=2)
-                    self._warned_clamp = True
-            elif code != 0:
+            code, clamped = (int(v) for v in self.workspace[self._status_off:self._status_off + 8].view(torch.int32).tolist())
+            if clamped and not self._warned_clamp:   # informational: a recurrent gradient hit the exchange bound of the bf16 BPTT
+                warnings.warn(ops.CLAMPED_MSG, RuntimeWarning, stacklevel=2)
+                self._warned_clamp = True
+            if code != 0:
                 raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")
 
     def planned_cp(self) -> torch.Tensor:
