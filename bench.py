@@ -205,15 +205,6 @@ def rnn_passes(B):
     return -(-B // (6 * 64)), -(-B // (5 * 64))
 
 
-def launches_per_step(B, T, math):
-    """Kernels of libpaule_b200.so launched by one paule_plan_step."""
-    gemms = 8                                          # post_linear, gate GEMM, head, head^T, 3 dX, post_linear^T
-    if math == 0:
-        return 1 + (gemms + 2) + 2 * (T + T // 2 + T // 2) + 2 + 1   # + 2 skinny input projections; one launch per time step
-    f, b = rnn_passes(B)
-    return 1 + 2 + gemms + 3 * f + 3 * b + 2 + 1       # tick, x images, GEMMs, recurrences, loss (2), Adam (= 20 at 64 words)
-
-
 def run_ours(args):
     import numpy as np
     import torch
@@ -282,6 +273,7 @@ def run_ours(args):
     planner.check()
     loss_curve = planner.losses()["total"].mean(1).cpu().tolist()
     ws_mb = planner.workspace.numel() / 1e6
+    n_launch = planner.launches_per_step()
     roof = dominant_kernel_roofline(planner, math, dev) if rank == 0 else None
     kernels = kernel_rooflines(planner, math, dev) if (rank == 0 and math != 0) else None
     planner.close(); del planner
@@ -421,7 +413,7 @@ def run_ours(args):
                            "n_outer=1, n_inner=K) -> PlanningResults of host arrays"
                            + ("" if world == 1 else " on every rank's shard + final NCCL all_gather of planned cps and loss log "
                                                     "(distributed.plan_resynth_sharded)")},
-            "gpu_launches": launches_per_step(B, T, math) * K * reps,
+            "gpu_launches": n_launch * K * reps,
             "final_gather": gather,
             "roofline": roof,
             "kernel_rooflines": kernels,

@@ -301,6 +301,8 @@ PAULE_API size_t paule_plan_status_offset(int64_t B, int64_t T, int64_t H, int64
 PAULE_API size_t paule_plan_grad_lstm_offset(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);
 /* EmbeddingModel forward on a time-major mel [Tm,B,Cm] -> sv [B,S] (target semvec, paule.py:533-535), in the plan's math. */
 PAULE_API int paule_plan_embed(const paule_plan* p, const float* mel, float* sv, paule_stream_t stream);
+/* Kernel launches one paule_plan_step issues for this plan (-1: invalid plan); what callers report as their launch count. */
+PAULE_API int64_t paule_plan_step_launches(const paule_plan* p);
 /* forward only (no_grad predictions: paule.py:822-824, :1460-1464): fills pred_mel, pred_sv. */
 PAULE_API int paule_plan_forward(const paule_plan* p, paule_stream_t stream);
 /* one full inner step. */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "paule_plan_workspace_bytes": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
     "paule_plan_grad_lstm_offset": (sz, [i64, i64, i64, i64, i64, i64, C.c_int]),
     "paule_plan_embed": (C.c_int, [C.POINTER(Plan), vp, vp, vp]),
+    "paule_plan_step_launches": (i64, [C.POINTER(Plan)]),
     "paule_plan_forward": (C.c_int, [C.POINTER(Plan), vp]),
     "paule_plan_step": (C.c_int, [C.POINTER(Plan), vp]),
 }

@@ -119,12 +119,12 @@ int check_plan(const paule_plan* p) {
   return PAULE_OK;
 }
 
-inline bool tc(const paule_plan* p) { return p->math != PAULE_MATH_FP32; }
+inline bool use_tc(const paule_plan* p) { return p->math != PAULE_MATH_FP32; }
 
 // recurrence of one layer on time-major data; gates already holds x W_ih^T + b
 int recur_forward(const paule_plan* p, const paule_lstm_layer& L, int64_t steps, float* gates, float* h, float* c,
                   const Workspace& w, void* h_img, paule_stream_t s) {
-  if (tc(p)) return paule_tc_lstm_seq_fwd(gates, L.packed, h, c, w.xchg, h_img, steps, p->B, p->math, s);
+  if (use_tc(p)) return paule_tc_lstm_seq_fwd(gates, L.packed, h, c, w.xchg, h_img, steps, p->B, p->math, s);
   return paule_lstm_seq_fwd_f32(gates, L.w_hh, h, c, steps, p->B, p->H, s);
 }
 
@@ -133,7 +133,7 @@ int layer_backward(const paule_plan* p, const paule_lstm_layer& L, float* gates,
                    int dh_mode, const float* dh_last, int64_t steps, float* dx, int accumulate, const Workspace& w,
                    paule_stream_t s) {
   const int64_t B = p->B, H = p->H, I = L.input_size;
-  if (tc(p)) {
+  if (use_tc(p)) {
     // only the bf16 dA images are consumed (dX GEMM on tcgen05): the fp32 copy over the stash is not written
     PAULE_TRY(paule_tc_lstm_seq_bwd_img(gates, c, L.packed, dh_seq, dh_mode, dh_last, w.xchg, w.da_img, steps, B, p->math, s));
     return tc::gemm_img(w.da_img, L.packed_ih_t, nullptr, dx, steps, B, I, 4, accumulate,
@@ -150,7 +150,7 @@ int project_and_recur(const paule_plan* p, const paule_lstm_layer& L, const floa
                       float* c, const Workspace& w, void* x_img, void* h_img, paule_stream_t s) {
   const int64_t B = p->B, H = p->H, I = L.input_size;
   static const bool no_fuse = getenv("PAULE_NO_FUSED_X") != nullptr;
-  if (tc(p) && I <= 64 && !no_fuse) {
+  if (use_tc(p) && I <= 64 && !no_fuse) {
     PAULE_TRY(paule_tc_x_image(x, x_img, steps, B, I, s));
     // nobody reads this layer's fp32 h when it leaves bf16 images (post_linear / the next layer's projection run on them)
     return paule_tc_lstm_seq_fwd_x(gates, L.packed, L.bias, x_img, h_img ? nullptr : h, c, w.xchg, h_img, steps, B, p->math, s);
@@ -242,7 +242,7 @@ WavePlan plan_wavefront(const paule_plan* p, bool use_sem) {
   static const int fwd_max = getenv("PAULE_WAVEFRONT_FWD") ? atoi(getenv("PAULE_WAVEFRONT_FWD")) : 2;
   static const int bwd_max = getenv("PAULE_WAVEFRONT_BWD") ? atoi(getenv("PAULE_WAVEFRONT_BWD")) : 3;
   WavePlan wp;
-  if (off || !tc(p) || p->post_packed == nullptr || (p->T % 2) != 0 || p->T < 8) return wp;
+  if (off || !use_tc(p) || p->post_packed == nullptr || (p->T % 2) != 0 || p->T < 8) return wp;
   const int sm = sm_count() - 2;
   const int64_t B = p->B;
   const int n_f = tc::fwd2_ctas(B, 0);
@@ -372,8 +372,10 @@ int backward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& 
     if (wp.bwd == 3) { PAULE_TRY(run_b1()); PAULE_TRY(run_g1()); }
     PAULE_TRY(run_b0()); PAULE_TRY(run_g0()); PAULE_TRY(run_bf());
   } else {
-    PAULE_TRY(run_bf()); PAULE_TRY(run_b0()); PAULE_TRY(run_g0());
+    // launched in dependency order: a tool that serialises kernels (Nsight Compute's kernel replay) then still finds every
+    // counter complete when its waiter starts
     if (wp.bwd == 3) { PAULE_TRY(run_b1()); PAULE_TRY(run_g1()); }
+    PAULE_TRY(run_b0()); PAULE_TRY(run_g0()); PAULE_TRY(run_bf());
     PAULE_TRY(join_streams(ss, s, n_side));
   }
   merge_status_kernel<<<1, 1, 0, s>>>(status_of(w.xchg), status_of(w.xchg2), status_of(w.xchg3));
@@ -396,7 +398,7 @@ int embed_head(const paule_plan* p, const Workspace& w, float* sv, paule_stream_
 // embedder layer 1 + head on the images / stash layer 0 left behind
 int embed_top(const paule_plan* p, const Workspace& w, float* sv, paule_stream_t s) {
   const int64_t B = p->B, H = p->H, Tm = p->T / 2;
-  if (tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
+  if (use_tc(p)) {   // the gate GEMM over all time steps: Xp1 = h_0 W_ih1^T + b on tcgen05, A = the images layer 0 left
     PAULE_TRY(tc::gemm_img(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, 0, status_of(w.xchg), as_stream(s)));
   } else {
     PAULE_TRY(paule_linear_f32(w.h_0, p->emb1.w_ih, p->emb1.bias, w.gates_1, Tm * B, 4 * H, H, 1, H, 0, 0, 1, 4 * H, 0, 0, s));
@@ -428,7 +430,7 @@ int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, pa
     }
   }
   // ForwardModel (models.py:348-356): K = 30 input projection + recurrence
-  const bool tc_post = tc(p) && p->post_packed != nullptr && (T % 2 == 0);
+  const bool tc_post = use_tc(p) && p->post_packed != nullptr && (T % 2 == 0);
   PAULE_TRY(project_and_recur(p, p->fwd, p->cp, T, w.gates_f, w.h_f, w.c_f, w, w.x_img_f, tc_post ? w.hf_img : nullptr, s));
   // post_linear + AvgPool1d(2,2) (the pool commutes with the Linear)
   if (tc_post) {
@@ -473,6 +475,41 @@ extern "C" int paule_plan_embed(const paule_plan* p, const float* mel, float* sv
   PAULE_REQUIRE(mel && sv);
   const Workspace w = carve(p->workspace, p->B, p->T, p->H, p->C, p->Cm, p->S, p->math);
   return embed_models(p, w, mel, sv, stream);
+}
+
+// Kernel launches of the library that one paule_plan_step issues for this plan (memsets and event nodes not counted): the
+// same branch conditions as the code below, for callers that report a launch count (bench.py's `gpu_launches`).
+extern "C" int64_t paule_plan_step_launches(const paule_plan* p) {
+  if (check_plan(p) != PAULE_OK) return -1;
+  const int64_t B = p->B, T = p->T, Tm = T / 2;
+  const bool use_sem = p->objective != PAULE_OBJ_ACOUSTIC;
+  const bool need_sv = use_sem || (p->log_semantics && p->target_sv);
+  const int64_t ragged = p->word_frames ? 1 : 0;
+  int64_t n = 1 + 2 + 1;   // step tick, criterion (2 kernels), Adam
+  if (!use_tc(p)) {
+    n += (1 + T) + 1;                                                    // forward model: projection + T steps, post_linear
+    if (need_sv) n += 2 * (1 + Tm) + ragged + 1;                         // embedder: 2 x (projection + steps), head
+    if (use_sem) n += 1 + ragged + 2 * (Tm + 1);                         // head^T, BPTT + dX of both embedder layers
+    n += 1 + (T + 1);                                                    // post_linear^T, BPTT + dX of the forward model
+    return n;
+  }
+  const int64_t fpass = (B + 6 * 64 - 1) / (6 * 64), bpass = (B + 5 * 64 - 1) / (5 * 64);   // launches per recurrent layer
+  const WavePlan wf = need_sv ? plan_wavefront(p, false) : WavePlan{};
+  if (wf.fwd != 0) {
+    n += 1 + 1 + fpass + 1 + 1 + 1;                                      // targets, x image, forward model, GEMM, embedder l0, status
+    n += (wf.fwd == 2 ? 2 : 1 + fpass) + ragged + 1;                     // gate GEMM + embedder l1, head
+  } else {
+    n += 1 + fpass + 1;                                                  // x image, forward model, post_linear
+    if (need_sv) n += 1 + fpass + 1 + fpass + ragged + 1;                // x image, l0, gate GEMM, l1, head
+  }
+  const WavePlan wb = plan_wavefront(p, use_sem);
+  if (use_sem && wb.bwd != 0) {
+    n += 2 + 1 + (wb.bwd == 2 ? bpass + 1 : 2) + 3 + 1 + 1;              // head^T, post^T, targets, l1 (+ dX), BF, l0, GEMM, status, dX
+  } else {
+    if (use_sem) n += 1 + ragged + 2 * (bpass + 1);
+    n += 1 + bpass + 1;
+  }
+  return n;
 }
 
 extern "C" int paule_plan_forward(const paule_plan* p, paule_stream_t stream) {

@@ -239,6 +239,11 @@ class BatchPlanner:
     def struct_ref(self):
         return ctypes.byref(self._struct)
 
+    def launches_per_step(self) -> int:
+        """kernel launches of libpaule_b200.so per inner step of this planner (paule_plan_step_launches)"""
+        with torch.cuda.device(self.device):
+            return int(_lib.load().paule_plan_step_launches(self.struct_ref()))
+
     # ------------------------------------------------------------------------------------------
     def embed(self, mel_tm: torch.Tensor) -> torch.Tensor:
         """semvec [B,S] of a time-major mel [Tm,B,Cm] through the planner's own embedder kernels, in the planner's math
