@@ -77,6 +77,15 @@ PAULE_API int paule_linear_f32(const float* A, const float* W, const float* bias
                      int64_t c_inner, int64_t c_outer_stride, int64_t c_inner_stride,
                      int accumulate, paule_stream_t stream);
 
+/* Weight gradients of the continue-learning step (paule/paule.py:1372-1377: autograd through aten::lstm / aten::linear):
+ *   C[m, n] (+)= sum_r A[r, m] B[r, n]     A [R, lda] (d loss / d pre-activation), B [R, ldb] (layer input or h_{t-1}), C [M, N]
+ *   out[m]  (+)= sum_r A[r, m]             (bias gradient)
+ * accumulate != 0 adds into the output. */
+PAULE_API int paule_gemm_tn_f32(const float* A, const float* B, float* C, int64_t R, int64_t M, int64_t N, int64_t lda,
+                      int64_t ldb, int accumulate, paule_stream_t stream);
+PAULE_API int paule_colsum_f32(const float* A, float* out, int64_t R, int64_t M, int64_t lda, int accumulate,
+                     paule_stream_t stream);
+
 /* [B,T,C] <-> [T,B,C]: out[t,b,:] = in[b,t,:] with (B,T) = (n_outer,n_inner) of `in`. */
 PAULE_API int paule_transpose_btc(const float* in, float* out, int64_t n_outer, int64_t n_inner, int64_t C,
                         paule_stream_t stream);

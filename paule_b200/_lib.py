@@ -49,6 +49,8 @@ SIGNATURES = {
     "paule_last_cuda_error": (C.c_char_p, []),
     "paule_device_check": (C.c_int, []),
     "paule_linear_f32": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, C.c_int, vp]),
+    "paule_gemm_tn_f32": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, i64, C.c_int, vp]),
+    "paule_colsum_f32": (C.c_int, [vp, vp, i64, i64, i64, C.c_int, vp]),
     "paule_transpose_btc": (C.c_int, [vp, vp, i64, i64, i64, vp]),
     "paule_lstm_seq_fwd_f32": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp]),
     "paule_lstm_seq_bwd_f32": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, i64, i64, i64, vp]),

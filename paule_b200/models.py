@@ -233,8 +233,59 @@ class InverseModelMelTimeSmoothResidual(nn.Module):
                                              groups=output_size)
         self._pack = _PackedLSTM(self.lstm)
 
-    @torch.no_grad()
     def forward(self, x, *args):
+        """Planning: the hand-written stencil kernels + LSTM ops, no autograd graph (the reference only ever calls the inverse
+        model under no_grad while planning, paule/paule.py:551-557).  Continue-learning of the inverse model
+        (``self.learnable = True``, grad mode on, parameters require grad; paule/paule.py:1413-1436, set by
+        ``Paule.continue_learning_inv``): the differentiable restatement ``_forward_trainable`` -- outer-loop work, a few small
+        batches between planning rounds."""
+        if getattr(self, "learnable", False) and _learning(self.parameters()):
+            return self._forward_trainable(_check_input(x, "InverseModel.forward(x)"))
+        with torch.no_grad():
+            return self._forward_kernels(x)
+
+    def _forward_trainable(self, x):
+        """models.py:221-247 with autograd: the recurrence and post_linear on the library's LSTM / Linear ops (own forward, BPTT
+        and weight-gradient kernels), the per-channel stencils -- 1 % of the FLOPs -- as grouped ``conv1d`` library calls so
+        that autograd reaches their weights."""
+        F = nn.functional
+        B, Tm, Cm = x.shape
+        z = x.transpose(1, 2)                                                   # [B, mel, seq]
+        for blk in self.MelBlocks:                                              # models.py:152-169, :224-228
+            fs = blk.filter_size_channel
+            outs = []
+            for i, conv in enumerate(blk.ConvLayers):                           # layer i sees the mel axis shifted by (fs - 2) - i rows
+                shift = (fs - 2) - i
+                if shift > 0:
+                    zi = F.pad(z, (0, 0, shift, 0))[:, :Cm, :]
+                elif shift < 0:
+                    zi = F.pad(z, (0, 0, 0, -shift))[:, -Cm:, :]
+                else:
+                    zi = z
+                outs.append(F.conv1d(zi, conv.weight.float(), conv.bias.float(), padding=2, groups=conv.groups))
+            z = torch.stack(outs, dim=2).reshape(B, Cm, Tm) + z
+        z = z.transpose(1, 2)
+        zero = z.new_zeros(B, 1, Cm)                                            # add_vel_and_acc_info, models.py:47-61
+        vel = z[:, 1:] - z[:, :-1]
+        acc = vel[:, 1:] - vel[:, :-1]
+        feat = torch.cat((z, torch.cat((vel, zero), 1), torch.cat((zero, acc, zero), 1)), dim=2).contiguous()
+        h = lstm_stack(feat, self._pack.get(_use_tc(self)), self.lstm)          # [Tm,B,H]
+        y = ops.linear_tm(h, _param(self.post_linear.weight), _param(self.post_linear.bias), False, True)   # [B,Tm,30]
+        mid = torch.cat(((y[:, :-1] + y[:, 1:]) / 2.0, y[:, -1:]), dim=1)       # double_sequence, models.py:63-81
+        out = torch.stack((y, mid), dim=2).reshape(B, 2 * Tm, y.shape[2]).transpose(1, 2)   # [B,30,2Tm]
+        raw = out
+        for r in self.ResidualConvBlocks:                                       # models.py:131-139
+            c1, c2 = r.band_conv1d_1, r.band_conv1d_2
+            out = F.conv1d(F.conv1d(out, c1.weight.float(), c1.bias.float(), padding=2, groups=c1.groups),
+                           c2.weight.float(), c2.bias.float(), padding=2, groups=c2.groups) + out
+        if len(self.ResidualConvBlocks) > 0:
+            Cc, S = out.shape[1], out.shape[2]
+            mixed = torch.stack((out, raw), dim=2).reshape(B, 2 * Cc, S)        # models.py:241-243
+            rw = self.resid_weighting
+            out = F.conv1d(mixed, rw.weight.float(), rw.bias.float(), padding=2, groups=rw.groups)
+        return out.transpose(1, 2).contiguous()
+
+    def _forward_kernels(self, x):
         x = _check_input(x, "InverseModel.forward(x)")
         lib = _lib.load()
         st = ops._stream()

@@ -98,6 +98,29 @@ def transpose_btc(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [R, M], b [R, N] (row-major, contiguous) -> a^T b [M, N]: the weight-gradient reduction over all (step, word) rows
+    (paule_gemm_tn_f32)."""
+    _chk(a, "a"); _chk(b, "b")
+    R, M = a.shape
+    N = b.shape[1]
+    out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    with _on(a):
+        _lib.check(_lib.load().paule_gemm_tn_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), R, M, N, M, N, 0, _stream()),
+                   "paule_gemm_tn_f32")
+    return out
+
+
+def colsum(a: torch.Tensor) -> torch.Tensor:
+    """a [R, M] -> column sums [M] (bias gradient; paule_colsum_f32)."""
+    _chk(a, "a")
+    R, M = a.shape
+    out = torch.empty((M,), device=a.device, dtype=torch.float32)
+    with _on(a):
+        _lib.check(_lib.load().paule_colsum_f32(a.data_ptr(), out.data_ptr(), R, M, M, 0, _stream()), "paule_colsum_f32")
+    return out
+
+
 class LstmWeights:
     """Device-side operand pack of one LSTM layer (fp32 originals, transposes, summed bias, tcgen05 image).
 
@@ -208,6 +231,20 @@ def _(dh, gates, c, w_ih_t, w_hh_t, batch_first_out):
     return dh.new_empty((B, T, I) if batch_first_out else (T, B, I)), torch.empty_like(gates)
 
 
+def _lstm_weight_grads(da: torch.Tensor, x: torch.Tensor, h: torch.Tensor, batch_first_in: bool):
+    """dW_ih = dA^T x, dW_hh = dA[1:]^T h[:-1], db = column sums of dA over all (step, word) rows -- the library's own reduction
+    kernels (the reference gets them from autograd through aten::lstm, paule/paule.py:1376)."""
+    T, B, G = da.shape
+    x_tm = (x.transpose(0, 1) if batch_first_in else x).reshape(T * B, -1).float().contiguous()
+    da2 = da.reshape(T * B, G)
+    d_w_ih = gemm_tn(da2, x_tm)
+    if T > 1:
+        d_w_hh = gemm_tn(da[1:].reshape((T - 1) * B, G), h[:-1].reshape((T - 1) * B, -1).contiguous())
+    else:
+        d_w_hh = torch.zeros((G, h.shape[-1]), device=da.device, dtype=torch.float32)
+    return d_w_ih, d_w_hh, colsum(da2)
+
+
 def _lstm_layer_setup(ctx, inputs, output):
     x, batch_first_in, w_ih, w_hh, bias = inputs
     h, gates, c = output
@@ -226,14 +263,10 @@ def _lstm_layer_backward(ctx, dh, dgates, dc):
     dx, da = lstm_layer_bwd(dh.contiguous(), gates, c, w_ih.t().contiguous(), w_hh.t().contiguous(), ctx.batch_first_in)
     if not ctx.weight_grads:
         return dx, None, None, None, None      # planning needs input gradients only
-    # weight gradients: plain GEMMs over the saved operands (library GEMMs; they are outer-loop work, not the hot path)
+    # weight gradients: reductions over all (step, word) rows of the saved operands (paule_gemm_tn_f32 / paule_colsum_f32)
     x, h = ctx.saved_tensors[4:6]
-    T, B, G = da.shape
-    x_tm = x.transpose(0, 1) if ctx.batch_first_in else x
-    da2 = da.reshape(T * B, G)
-    d_w_ih = da2.t() @ x_tm.reshape(T * B, -1)
-    d_w_hh = da[1:].reshape((T - 1) * B, G).t() @ h[:-1].reshape((T - 1) * B, -1) if T > 1 else torch.zeros_like(w_hh)
-    return dx, None, d_w_ih, d_w_hh, da2.sum(0)
+    d_w_ih, d_w_hh, d_b = _lstm_weight_grads(da, x, h, ctx.batch_first_in)
+    return dx, None, d_w_ih, d_w_hh, d_b
 
 
 lstm_layer_fwd.register_autograd(_lstm_layer_backward, setup_context=_lstm_layer_setup)
@@ -351,13 +384,9 @@ def _lstm_layer_tc_backward(ctx, dh, dgates, dc):
     dx, da = lstm_layer_bwd_tc(dh.contiguous(), gates, c, w_ih.t().contiguous(), packed, ctx.batch_first_in)
     if not ctx.weight_grads:
         return dx, None, None, None, None, None
-    x, h = ctx.saved_tensors[4:6]      # weight gradients as in _lstm_layer_backward (library GEMMs, outer-loop work)
-    T, B, G = da.shape
-    x_tm = x.transpose(0, 1) if ctx.batch_first_in else x
-    da2 = da.reshape(T * B, G)
-    d_w_ih = da2.t() @ x_tm.reshape(T * B, -1)
-    d_w_hh = da[1:].reshape((T - 1) * B, G).t() @ h[:-1].reshape((T - 1) * B, -1) if T > 1 else torch.zeros((G, h.shape[-1]), device=da.device)
-    return dx, None, d_w_ih, d_w_hh, da2.sum(0), None
+    x, h = ctx.saved_tensors[4:6]      # weight gradients as in _lstm_layer_backward
+    d_w_ih, d_w_hh, d_b = _lstm_weight_grads(da, x, h, ctx.batch_first_in)
+    return dx, None, d_w_ih, d_w_hh, d_b, None
 
 
 lstm_layer_fwd_tc.register_autograd(_lstm_layer_tc_backward, setup_context=_lstm_layer_tc_setup)
@@ -444,8 +473,9 @@ def _linear_tm_backward(ctx, dy):
         To = dy_tm.shape[0]
         x = 0.5 * (x[0:2 * To:2] + x[1:2 * To:2])
     N = dy_tm.shape[-1]
-    d_w = dy_tm.reshape(-1, N).t() @ x.reshape(-1, x.shape[-1])
-    return dx, d_w, dy_tm.reshape(-1, N).sum(0), None, None
+    dy2 = dy_tm.reshape(-1, N).float().contiguous()
+    d_w = gemm_tn(dy2, x.reshape(-1, x.shape[-1]).float().contiguous())
+    return dx, d_w, colsum(dy2), None, None
 
 
 linear_tm.register_autograd(_linear_tm_backward, setup_context=_linear_tm_setup)

@@ -228,6 +228,116 @@ class Paule():
             self.last_planner.refresh_weights()      # repack: the planner holds bf16 / transposed copies of the weights
         return epoch_losses
 
+    @staticmethod
+    def _same_size_batches(lengths, batch_size, shuffle):
+        """create_epoch_batches(same_size_batching=True) of the reference (paule/paule.py:349-369): batches of samples of one
+        length, shuffled inside a length and across batches."""
+        by_len = {}
+        for i, n in enumerate(lengths):
+            by_len.setdefault(int(n), []).append(i)
+        batches = []
+        for length in sorted(by_len):
+            idx = list(by_len[length])
+            if shuffle:
+                random.shuffle(idx)
+            batches += [idx[k:k + batch_size] for k in range(0, len(idx), batch_size)]
+        if shuffle:
+            random.shuffle(batches)
+        return batches
+
+    @staticmethod
+    def cp_trajectory_loss(y_hat, tgts):
+        """paule/util.py:640-671: RMSE of position, velocity, acceleration and jerk (five-point stencils; the deprecated ``lag``
+        argument is ignored by the reference, so every derivative term counts three times).  Returns (loss, pos, vel, acc, jerk)."""
+        def d5(v):
+            return (-v[:, 4:] + 8.0 * v[:, 3:-1] - 8.0 * v[:, 1:-3] + v[:, :-4]) / 12.0
+
+        def rmse(a, b):
+            return torch.sqrt(torch.mean((a - b) ** 2))
+        v_t = d5(tgts); a_t = d5(v_t); j_t = d5(a_t)
+        v_h = d5(y_hat); a_h = d5(v_h); j_h = d5(a_h)
+        pos = rmse(y_hat, tgts)
+        vel, acc, jerk = 3.0 * rmse(v_h, v_t), 3.0 * rmse(a_h, a_t), 3.0 * rmse(j_h, j_t)
+        return pos + vel + acc + jerk, pos, vel, acc, jerk
+
+    def continue_learning_inv(self, mels, cps, *, n_epochs=10, batch_size=8, shuffle=True):
+        """Continue-learning of the inverse model on (produced mel -> cp) pairs (paule/paule.py:1413-1436): same-size batching,
+        ``Y_hat = inv_model(batch)``, ``cp_trajectory_loss`` (:294), ``self.inv_optimizer``.  ``mels[i]`` is [Tm_i, 60],
+        ``cps[i]`` [2 Tm_i, 30].  Returns the mean loss of every epoch."""
+        if len(cps) != len(mels):
+            raise ValueError("cps and mels need the same number of samples")
+        xs = [torch.as_tensor(np.ascontiguousarray(m)).float() for m in mels]
+        ys = [torch.as_tensor(np.ascontiguousarray(c)).float() for c in cps]
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            if y.shape[0] != 2 * x.shape[0]:
+                raise ValueError(f"sample {i}: {x.shape[0]} mel frames need {2 * x.shape[0]} cp frames, got {y.shape[0]}")
+        was_training = self.inv_model.training
+        self.inv_model.train()
+        self.inv_model.learnable = True          # the differentiable forward (models.InverseModel...forward)
+        for p in self.inv_model.parameters():
+            p.requires_grad_(True)
+        epoch_losses = []
+        for _ in range(int(n_epochs)):
+            losses = []
+            for j in self._same_size_batches([x.shape[0] for x in xs], batch_size, shuffle):
+                batch_input = torch.stack([xs[i] for i in j]).to(self.device)
+                batch_output = torch.stack([ys[i] for i in j]).to(self.device)
+                y_hat = self.inv_model(batch_input)                         # :1427
+                self.inv_optimizer.zero_grad()                              # :1429
+                inv_loss = self.cp_trajectory_loss(y_hat, batch_output)[0]  # :1430-1432
+                inv_loss.backward()                                         # :1433
+                self.inv_optimizer.step()                                   # :1434
+                losses.append(float(inv_loss.item()))
+            epoch_losses.append(float(np.mean(losses)) if losses else float("nan"))
+        self.inv_model.train(was_training)
+        self.inv_model.learnable = False
+        return epoch_losses
+
+    def continue_learning_tube(self, cps, tubes, mels, *, n_epochs=10, batch_size=8, shuffle=True):
+        """Continue-learning of the somatosensory models (paule/paule.py:1381-1405): ``cp_tube_model`` on (cp -> produced tube)
+        and ``tube_mel_model`` on (produced tube -> produced mel), both with the RMSE criterion (:301-302) and their own
+        optimizers.  ``tubes[i]`` is [T_i, 10] (VocalTractLab's tube extraction, host side).  Returns (tube_losses, tube_mel_losses)."""
+        if not self.use_somatosensory_feedback:
+            raise ValueError("continue_learning_tube needs use_somatosensory_feedback=True")
+        if not (len(cps) == len(tubes) == len(mels)):
+            raise ValueError("cps, tubes and mels need the same number of samples")
+        xs = [torch.as_tensor(np.ascontiguousarray(c)).float() for c in cps]
+        ts = [torch.as_tensor(np.ascontiguousarray(t)).float() for t in tubes]
+        ms = [torch.as_tensor(np.ascontiguousarray(m)).float() for m in mels]
+        if getattr(self, "tube_optimizer", None) is None:
+            self.tube_optimizer = torch.optim.Adam(self.cp_tube_model.parameters(), lr=0.001)          # paule.py:296-298
+        if getattr(self, "tube_mel_optimizer", None) is None:
+            self.tube_mel_optimizer = torch.optim.Adam(self.tube_mel_model.parameters(), lr=0.001)
+        for m_ in (self.cp_tube_model, self.tube_mel_model):
+            m_.train()
+            for p in m_.parameters():
+                p.requires_grad_(True)
+
+        def rmse(a, b):
+            return torch.sqrt(torch.mean((a - b) ** 2))
+        tube_losses, tube_mel_losses = [], []
+        for _ in range(int(n_epochs)):
+            l1, l2 = [], []
+            for j in self._same_size_batches([x.shape[0] for x in xs], batch_size, shuffle):
+                batch_input = torch.stack([xs[i] for i in j]).to(self.device)
+                batch_tube = torch.stack([ts[i] for i in j]).to(self.device)
+                batch_mel = torch.stack([ms[i] for i in j]).to(self.device)
+                y_hat = self.cp_tube_model(batch_input)                     # :1388
+                self.tube_optimizer.zero_grad()
+                tube_loss = rmse(y_hat, batch_tube)
+                tube_loss.backward()
+                self.tube_optimizer.step()
+                l1.append(float(tube_loss.item()))
+                y_hat = self.tube_mel_model(batch_tube)                     # :1397
+                self.tube_mel_optimizer.zero_grad()
+                tube_mel_loss = rmse(y_hat, batch_mel)
+                tube_mel_loss.backward()
+                self.tube_mel_optimizer.step()
+                l2.append(float(tube_mel_loss.item()))
+            tube_losses.append(float(np.mean(l1)) if l1 else float("nan"))
+            tube_mel_losses.append(float(np.mean(l2)) if l2 else float("nan"))
+        return tube_losses, tube_mel_losses
+
     def plan_iterative(self, overlap=8):
         """Empty stub in the reference as well (paule/paule.py:383-388)."""
         pass
@@ -406,7 +516,7 @@ class Paule():
                                         log_semantics, log_gradients, n_steps, lengths)
             return self._plan(planner, cp0, target_mel, initial_cp_np, lengths, batched, B, n_outer, n_inner, n_steps, log_ii,
                               log_cps, log_gradients, log_signals, log_semantics, objective, continue_learning,
-                              add_training_data_pred, n_epochs, batch_size)
+                              add_training_data_pred, n_epochs, batch_size, continue_learning_inv)
 
     def _get_planner(self, cp0, target_mel, target_semvec, lr, objective, past_t, log_semantics, log_gradients, n_steps,
                      lengths) -> BatchPlanner:
@@ -442,7 +552,7 @@ class Paule():
 
     def _plan(self, planner, cp0, target_mel, initial_cp_np, lengths, batched, B, n_outer, n_inner, n_steps, log_ii, log_cps,
               log_gradients, log_signals, log_semantics, objective, continue_learning, add_training_data_pred, n_epochs,
-              batch_size):
+              batch_size, learn_inv=False):
         """Outer / inner loops, final predictions and result packing (paule/paule.py:822-1550) on an armed planner."""
         soma = planner.soma
 
@@ -484,7 +594,7 @@ class Paule():
             pending.append((-1, cps_init, self._submit_synthesis(cps_init)))
 
         cp_steps, grad_steps, pred_semvec_steps, pred_mel_steps = [], [], [], []
-        pred_model_loss = []
+        pred_model_loss, inv_model_loss = [], []
         need_per_step = log_cps or log_gradients
         for ii_outer in range(n_outer):
             cp_steps_ii, pred_semvec_steps_ii, pred_mel_steps_ii = [], [], []
@@ -517,6 +627,8 @@ class Paule():
                         train_cps.append(np.asarray(row["cp_norm"], dtype=np.float32))
                         train_mels.append(np.asarray(row["melspec_norm_synthesized"], dtype=np.float32))
                 pred_model_loss += self.continue_learning_pred(train_cps, train_mels, n_epochs=n_epochs, batch_size=batch_size)
+                if learn_inv:      # paule.py:1413-1436: the inverse model learns (produced mel -> cp) on the same samples
+                    inv_model_loss += self.continue_learning_inv(train_mels, train_cps, n_epochs=n_epochs, batch_size=batch_size)
 
         # final predictions (paule.py:1456-1470)
         planned_cp = planner.planned_cp()
@@ -578,7 +690,7 @@ class Paule():
                 out(pred_mel), initial_prod_semvec, out(initial_pred_semvec), prod_semvec_out, out(pred_semvec),
                 prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"), sem_steps,
                 prod_semvec_loss_steps, per_step("speech_classifier"), prod_cls, cp_steps, pred_semvec_steps,
-                prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, list())
+                prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, inv_model_loss)
         if self.use_somatosensory_feedback:
             # the produced tube side needs VocalTractLab's tube extraction (paule.py:1070-1095), which stays host-side and does
             # not ship: those fields are None / empty
@@ -592,7 +704,7 @@ class Paule():
                 prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"), sem_steps,
                 prod_semvec_loss_steps, list(), per_step("tube_mel"), list(), per_step("tube_semvec"), list(), cp_steps,
                 pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, list(), list(),
-                list(), list(), list(), list(), pred_model_loss, list(), list(), list())
+                list(), list(), list(), list(), pred_model_loss, inv_model_loss, list(), list())
         return PlanningResults(
             out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None, None,
             initial_prod_mel, out(initial_pred_mel),
@@ -600,7 +712,7 @@ class Paule():
             out(initial_pred_semvec), prod_semvec_out,
             out(pred_semvec), prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
             per_step("semvec") if sem_logged else list(), prod_semvec_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps,
-            grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, list())
+            grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, pred_model_loss, inv_model_loss)
 
 
 # BASELINE.json's north_star spells the class name in capitals

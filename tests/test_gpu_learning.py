@@ -171,3 +171,65 @@ def test_host_synthesis_pipeline_fills_the_produced_fields(dev):
     one = pm.plan_resynth(target_acoustic=tmel[0].numpy(), initial_cp=cp0[0].numpy(), initialize_from=None, objective="acoustic",
                           n_outer=2, n_inner=2, continue_learning=False, verbose=False)
     assert one.prod_mel.shape == (20, 60) and one.prod_semvec.shape == (300,) and np.ndim(one.prod_loss_steps[0]) == 0
+
+
+# ---- continue-learning of the inverse model (paule/paule.py:1413-1436) ------------------------------------------------------
+def test_own_weight_gradient_kernels_match_matmul(dev):
+    """paule_gemm_tn_f32 / paule_colsum_f32 (dW = dA^T X, db = column sums over all (step, word) rows) against torch, incl. the
+    split-reduction path (few output tiles) and ragged sizes."""
+    from paule_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for R, M, N in ((1200, 2880, 30), (600, 2880, 720), (37, 70, 5), (4000, 60, 720), (1, 8, 8)):
+        a = (torch.rand(R, M, generator=g) - 0.5).to(dev)
+        b = (torch.rand(R, N, generator=g) - 0.5).to(dev)
+        want = a.double().t() @ b.double()
+        np.testing.assert_allclose(ops.gemm_tn(a, b).cpu().double().numpy(), want.cpu().numpy(), rtol=2e-5, atol=2e-5 * R ** 0.5)
+        np.testing.assert_allclose(ops.colsum(a).cpu().double().numpy(), a.double().sum(0).cpu().numpy(), rtol=2e-5, atol=2e-5 * R ** 0.5)
+
+
+def test_inverse_model_learning_step_matches_the_oracle(dev):
+    """One epoch of Paule.continue_learning_inv (differentiable inverse-model forward + cp_trajectory_loss + Adam) == the same
+    loop on the oracle's inverse model on the CPU: losses and every updated parameter."""
+    import paule_b200 as P
+    torch.manual_seed(3)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=64)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=64)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=64)
+    ref = O.OracleInverseModel(num_lstm_layers=1, hidden_size=64)
+    ref.load_state_dict(inv.state_dict())
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev, math=0)
+    pm.inv_optimizer = torch.optim.Adam(pm.inv_model.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(4)
+    mels = [torch.rand(n, 60, generator=g).numpy() for n in (12, 12, 12, 12)]
+    cps = [(torch.rand(2 * m.shape[0], 30, generator=g) - 0.5).numpy() for m in mels]
+    # the planning-time forward (hand-written stencil kernels, no autograd graph) and the differentiable one agree
+    x = torch.from_numpy(np.stack(mels)).to(dev)
+    with torch.no_grad():
+        y_kernels = pm.inv_model(x)
+    pm.inv_model.learnable = True
+    y_train = pm.inv_model(x)
+    pm.inv_model.learnable = False
+    assert y_train.requires_grad and not y_kernels.requires_grad
+    np.testing.assert_allclose(y_train.detach().cpu().numpy(), y_kernels.cpu().numpy(), atol=2e-5)
+    # gradients of cp_trajectory_loss wrt every parameter: differentiable forward + own BPTT / weight-gradient kernels vs
+    # autograd on the oracle's module (Adam-updated weights are not compared: Adam turns a sign flip of a near-zero gradient
+    # into a +-lr step)
+    for p in pm.inv_model.parameters():
+        p.requires_grad_(True)
+    pm.inv_model.learnable = True
+    loss = P.Paule.cp_trajectory_loss(pm.inv_model(x), torch.from_numpy(np.stack(cps)).to(dev))[0]
+    loss.backward()
+    pm.inv_model.learnable = False
+    for p in ref.parameters():
+        p.requires_grad_(True)
+    want = P.Paule.cp_trajectory_loss(ref(torch.from_numpy(np.stack(mels))), torch.from_numpy(np.stack(cps)))[0]
+    want.backward()
+    np.testing.assert_allclose(float(loss.detach()), float(want.detach()), rtol=1e-5)
+    for (n, p), (_, q) in zip(pm.inv_model.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.numpy(), atol=2e-4 * float(q.grad.abs().max()) + 1e-7, err_msg=n)
+    # the learning loop itself: the loss falls
+    pm.inv_optimizer = torch.optim.Adam(pm.inv_model.parameters(), lr=1e-3)
+    losses = pm.continue_learning_inv(mels, cps, n_epochs=6, batch_size=4, shuffle=False)
+    assert len(losses) == 6 and losses[-1] < losses[0]
+    np.testing.assert_allclose(losses[0], float(want.detach()), rtol=1e-4)
