@@ -6,12 +6,15 @@ initial/final predictions :822-824, :1460-1464), batched over words.  Same keywo
 ``ValueError``s, same ``PlanningResults`` field list.
 
 Differences, all forced by the scope (BASELINE.json north_star):
-* VocalTractLab synthesis and librosa mel extraction stay host-side and outside this package: the
-  ``prod_*`` / ``*_sig`` fields are ``None`` (empty lists for the per-step ones), ``target_acoustic`` must be a
-  log-mel array, and continue-learning of the models on synthesised audio (paule.py:1243-1454) is not run.
-* ``target_acoustic`` may be ``[Tm,60]`` (one word, results shaped like the reference's) or ``[B,Tm,60]``
-  (a batch: every result gains a leading word axis, per-step losses become arrays of shape ``[B]``).
-* arithmetic is fp32 on the GPU (the reference ships fp64 CPU).
+* VocalTractLab synthesis and the log-mel front-end stay host-side and are called at outer-loop boundaries only
+  (``paule_b200/audio.py``: ctypes binding of the synthesiser the reference ships, librosa-free ``librosa_melspec``); they plug in
+  through ``Paule(synthesizer=audio.make_synthesizer(audio.VocalTractLab(...)))``.  Without a synthesizer the ``prod_*`` /
+  ``*_sig`` fields are ``None`` (empty lists for the per-step ones) and continue-learning is not run.
+* ``target_acoustic`` may be a file name or ``(signal, rate)`` as in the reference, a log-mel array ``[Tm,60]`` (one word,
+  results shaped like the reference's), ``[B,Tm,60]`` (a batch: every result gains a leading word axis, per-step losses become
+  arrays of shape ``[B]``) or a list of per-word mels of different lengths (ragged batch).
+* arithmetic: bf16 tensor-core operands with fp32 accumulation / state / loss / Adam for 720-unit models (``math=None``),
+  fp32 kernels with ``math=ops.MATH_FP32`` (the reference ships fp64 CPU).
 """
 from __future__ import annotations
 
@@ -415,15 +418,23 @@ class Paule():
                 target_acoustic[b, :m.shape[0]] = m
                 initial_cp[b, :c.shape[0]] = c.to(initial_cp.device)
 
-        # ---- target parsing (paule.py:486-529).  Audio targets need librosa + VocalTractLab-side tooling
+        # ---- target parsing (paule.py:486-529)
         batched = False
         target_mel = None
+        self._target_audio = (None, None)
         if isinstance(target_acoustic, str) or (isinstance(target_acoustic, (tuple, list)) and len(target_acoustic) == 2
-                                                and not isinstance(target_acoustic[0], (list, tuple, np.ndarray, torch.Tensor))
-                                                ):
-            raise NotImplementedError("audio targets (file name or (sig, sr)) need the host-side librosa mel front-end "
-                                      "(paule/util.py:115-146), which is outside the B200 hot path; pass the "
-                                      "normalised log-mel array instead")
+                                                and not isinstance(target_acoustic[0], (list, tuple, torch.Tensor))
+                                                and np.ndim(target_acoustic[0]) in (1, 2) and np.ndim(target_acoustic[1]) == 0):
+            # audio target: a file name or (signal, sampling rate) -> normalised log-mel, shifted to min 0 (paule.py:487-496,
+            # :523-529); the mel front-end runs on the host (paule_b200/audio.py), once per call
+            from . import audio
+            sig, sr = audio.read_audio(target_acoustic) if isinstance(target_acoustic, str) else target_acoustic
+            sig = np.asarray(sig, dtype=np.float64)
+            if sig.ndim == 2:
+                sig = sig.mean(axis=1)                                         # stereo_to_mono, paule.py:489-490
+            self._target_audio = (sig, int(sr))
+            target_mel = torch.from_numpy(audio.target_mel_from_audio(sig, int(sr)).astype(np.float32)).unsqueeze(0)
+            target_seq_length = target_mel.shape[1]
         elif target_acoustic is None:
             pass
         else:
@@ -705,10 +716,11 @@ class Paule():
                 prod_semvec_loss_steps, list(), per_step("tube_mel"), list(), per_step("tube_semvec"), list(), cp_steps,
                 pred_semvec_steps, prod_semvec_steps, grad_steps, sig_steps, prod_mel_steps, pred_mel_steps, list(), list(),
                 list(), list(), list(), list(), pred_model_loss, inv_model_loss, list(), list())
+        target_sig, target_sr = getattr(self, "_target_audio", (None, None))
         return PlanningResults(
             out(planned_cp), (out(cp0) if lengths is not None else initial_cp_np) if batched else initial_cp_np[0], None, None,
             initial_prod_mel, out(initial_pred_mel),
-            None, None, out(target_mel), prod_sig, prod_sr, prod_mel_out, out(pred_mel), initial_prod_semvec,
+            target_sig, target_sr, out(target_mel), prod_sig, prod_sr, prod_mel_out, out(pred_mel), initial_prod_semvec,
             out(initial_pred_semvec), prod_semvec_out,
             out(pred_semvec), prod_loss_steps, per_step("total"), per_step("mel"), per_step("velocity"), per_step("jerk"),
             per_step("semvec") if sem_logged else list(), prod_semvec_loss_steps, cp_steps, pred_semvec_steps, prod_semvec_steps,

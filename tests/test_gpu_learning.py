@@ -233,3 +233,25 @@ def test_inverse_model_learning_step_matches_the_oracle(dev):
     losses = pm.continue_learning_inv(mels, cps, n_epochs=6, batch_size=4, shuffle=False)
     assert len(losses) == 6 and losses[-1] < losses[0]
     np.testing.assert_allclose(losses[0], float(want.detach()), rtol=1e-4)
+
+
+def test_audio_target_goes_through_the_host_mel_front_end(dev):
+    """plan_resynth(target_acoustic=(signal, rate)) as in the reference (paule/paule.py:495-496, :523-529): the target mel is the
+    normalised, min-shifted log-mel of the waveform (paule_b200/audio.py), target_sig / target_sr come back in the results."""
+    import paule_b200 as P
+    from paule_b200 import audio as A
+    torch.manual_seed(0)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=64).to(dev)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=64).to(dev)
+    inv = P.InverseModelMelTimeSmoothResidual(num_lstm_layers=1, hidden_size=64).to(dev)
+    pm = P.Paule(pred_model=pred, inv_model=inv, embedder=emb, device=dev)
+    sr = 44100
+    t = np.arange(int(0.1 * sr)) / sr
+    sig = 0.2 * np.sin(2 * np.pi * 220.0 * t) * np.hanning(len(t))
+    res = pm.plan_resynth(target_acoustic=(sig, sr), initialize_from="acoustic", objective="acoustic_semvec", n_outer=1, n_inner=3,
+                          continue_learning=False, verbose=False)
+    want = A.target_mel_from_audio(sig, sr)
+    assert res.target_mel.shape == want.shape == (1 + len(sig) // 220, 60)
+    np.testing.assert_allclose(res.target_mel, want, atol=1e-5)
+    assert res.target_sr == sr and np.array_equal(res.target_sig, sig)
+    assert res.planned_cp.shape == (2 * want.shape[0], 30) and len(res.planned_loss_steps) == 3
