@@ -144,7 +144,7 @@ class BatchPlanner:
             if self.lengths is not None:
                 raise NotImplementedError("somatosensory feedback with ragged batches")
             from .branches import SomatosensoryBranch
-            self.soma = SomatosensoryBranch(*somatosensory, B=B, T=T, C=C, device=dev)
+            self.soma = SomatosensoryBranch(*somatosensory, B=B, T=T, C=C, device=dev, math=math)
         if self.cls_w is not None or self.soma is not None:
             self.aux_log = torch.zeros((self.max_log_steps, B, 3), **f32)
         lib = _lib.load()
@@ -350,6 +350,11 @@ class BatchPlanner:
             if clamped and not self._warned_clamp:   # informational: a recurrent gradient hit the exchange bound of the bf16 BPTT
                 warnings.warn(ops.CLAMPED_MSG, RuntimeWarning, stacklevel=2)
                 self._warned_clamp = True
+            if code == 0 and self.soma is not None and self.soma.status_words() is not None:
+                code, soma_clamped = self.soma.status_words()
+                if soma_clamped and not self._warned_clamp:
+                    warnings.warn(ops.CLAMPED_MSG, RuntimeWarning, stacklevel=2)
+                    self._warned_clamp = True
             if code != 0:
                 raise _lib.PauleB200Error(f"persistent recurrent kernel watchdog fired (status {code}): results are invalid")
 

@@ -169,10 +169,12 @@ def test_somatosensory_gradient_and_batch_match_the_oracle(dev, models, branch_m
             np.testing.assert_allclose(gk, r1["grads"][0].numpy(), rtol=gr, atol=gr * r1["grads"][0].abs().max().item())
     L = pl.losses()
     np.testing.assert_allclose(_np(L["total"]), r1["loss"].numpy(), rtol=lr)
-    np.testing.assert_allclose(_np(L["tube_mel"]), r1["aux"][:, :, 1].numpy(), rtol=1e-4)
-    np.testing.assert_allclose(_np(L["tube_semvec"]), r1["aux"][:, :, 2].numpy(), rtol=1e-4)
+    # (bf16 mode: the three tube models run on the tcgen05 kernels, the 360-unit ones zero-padded to 720 units)
+    assert pl.soma.tc == (math == 1)
+    np.testing.assert_allclose(_np(L["tube_mel"]), r1["aux"][:, :, 1].numpy(), rtol=1e-4 if math == 0 else 2e-3)
+    np.testing.assert_allclose(_np(L["tube_semvec"]), r1["aux"][:, :, 2].numpy(), rtol=1e-4 if math == 0 else 2e-3)
     np.testing.assert_allclose(_np(pl.planned_cp()), r1["planned_cp"].numpy(), atol=ca)
-    # the branch's own gradient = extra_grad of the first step (the branch runs in fp32 in both math modes)
+    # the branch's own gradient = extra_grad of the first step
     ramp = _ramp_cps(3, cp0.shape[1])
     w1 = O.plan_inner_loop_branches(p32, e32, ramp, tmel, 1, cp_tube_model=oct_, tube_mel_model=otm, tube_embedder=ote,
                                     log_grads=True)["grads"][0]
@@ -185,7 +187,9 @@ def test_somatosensory_gradient_and_batch_match_the_oracle(dev, models, branch_m
     got = _np(ops.transpose_btc(pl2.soma.extra_grad))
     scale = np.abs(want).max()
     assert scale > 1e-6, scale
-    np.testing.assert_allclose(got, want, atol=0.02 * scale)
+    np.testing.assert_allclose(got, want, atol=(0.02 if math == 0 else 0.05) * scale)
+    with pytest.raises(AssertionError):       # negative control: a vanished branch gradient is rejected
+        np.testing.assert_allclose(0.0 * got, want, atol=0.05 * scale)
     assert g_first is not None
 
 
