@@ -89,21 +89,10 @@ class SomatosensoryBranch:
         if getattr(self, "tc", False):
             H = 720
 
-            def padded(lstm, k):      # gate blocks of H rows, the model's units first, zeros behind (see the module docstring)
-                w_ih, w_hh = getattr(lstm, f"weight_ih_l{k}").detach().float(), getattr(lstm, f"weight_hh_l{k}").detach().float()
-                b_ih, b_hh = getattr(lstm, f"bias_ih_l{k}").detach().float(), getattr(lstm, f"bias_hh_l{k}").detach().float()
-                h, i = w_hh.shape[1], w_ih.shape[1]
-                if h == H:
-                    return ops.LstmWeights(w_ih, w_hh, b_ih, b_hh, tc=True)
-                i_pad = H if (k > 0) else i       # a deeper layer's input is the (padded) layer below
-                W_ih, W_hh = w_ih.new_zeros(4 * H, i_pad), w_hh.new_zeros(4 * H, H)
-                B_ih, B_hh = b_ih.new_zeros(4 * H), b_hh.new_zeros(4 * H)
-                for g in range(4):
-                    W_ih[g * H:g * H + h, :i] = w_ih[g * h:(g + 1) * h]
-                    W_hh[g * H:g * H + h, :h] = w_hh[g * h:(g + 1) * h]
-                    B_ih[g * H:g * H + h] = b_ih[g * h:(g + 1) * h]
-                    B_hh[g * H:g * H + h] = b_hh[g * h:(g + 1) * h]
-                return ops.LstmWeights(W_ih, W_hh, B_ih, B_hh, tc=True)
+            def padded(lstm, k):      # as a 720-unit layer (ops.pad_lstm_params; exact, see the module docstring)
+                return ops.LstmWeights(*ops.pad_lstm_params(getattr(lstm, f"weight_ih_l{k}"), getattr(lstm, f"weight_hh_l{k}"),
+                                                            getattr(lstm, f"bias_ih_l{k}"), getattr(lstm, f"bias_hh_l{k}"),
+                                                            input_padded=k > 0 and lstm.hidden_size < H), tc=True)
 
             def pad_cols(w):          # post_linear [out, h] -> [out, 720]
                 out = w.new_zeros(w.shape[0], H)

@@ -39,16 +39,20 @@ class _PackedLSTM:
         self.layers: List[ops.LstmWeights] = []
 
     def get(self, tc: bool = False) -> List[ops.LstmWeights]:
-        """tc: also hold the tcgen05 weight images (persistent-RNN kernels; hidden size 720 only)."""
+        """tc: also hold the tcgen05 weight images of the persistent-RNN kernels.  Those are built for 720 hidden units;
+        narrower layers are packed ZERO-PADDED to 720 units (exact, ops.pad_lstm_params) and ``lstm_stack`` drops the pad
+        columns of the output again."""
         params = list(self.lstm.parameters())
         key = (_versions(params), bool(tc))
         if key != self._key:
             self.layers = []
+            pad = tc and self.lstm.hidden_size < ops.TC_HIDDEN
             for k in range(self.lstm.num_layers):
-                self.layers.append(ops.LstmWeights(getattr(self.lstm, f"weight_ih_l{k}"),
-                                                   getattr(self.lstm, f"weight_hh_l{k}"),
-                                                   getattr(self.lstm, f"bias_ih_l{k}"),
-                                                   getattr(self.lstm, f"bias_hh_l{k}"), tc=tc))
+                p = [getattr(self.lstm, f"{n}_l{k}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                if pad:
+                    p = ops.pad_lstm_params(*p, input_padded=k > 0)
+                self.layers.append(ops.LstmWeights(*p, tc=tc))
+            self.padded_from = self.lstm.hidden_size if pad else None
             self._key = key
         return self.layers
 
@@ -74,11 +78,16 @@ def _param(p: torch.Tensor) -> torch.Tensor:
     return p if (p.dtype == torch.float32 and p.is_contiguous()) else p.float().contiguous()
 
 
-def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights], lstm: nn.LSTM = None) -> torch.Tensor:
+def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights], lstm: nn.LSTM = None, hidden: int = None) -> torch.Tensor:
     """x [B,T,I] batch-first -> top layer's h, TIME-MAJOR [T,B,H].  With ``lstm`` given and a weight gradient wanted, the
     live parameters go into the ops (so autograd reaches them) instead of the cached, detached operand pack."""
     h = x
     learn = lstm is not None and _learning(lstm.parameters())
+    true_h = lstm.hidden_size if lstm is not None else hidden      # the model's own width (zero-padded tensor-core layers)
+    if learn and layers and layers[0].packed is not None and true_h is not None and layers[0].hidden != true_h:
+        # weight gradients of a zero-padded layer would come back padded: continue-learning of narrow models stays on the fp32 ops
+        layers = [ops.LstmWeights(*(getattr(lstm, f"{n}_l{k}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")))
+                  for k in range(lstm.num_layers)]
     for k, L in enumerate(layers):
         if learn:
             w_ih, w_hh = _param(getattr(lstm, f"weight_ih_l{k}")), _param(getattr(lstm, f"weight_hh_l{k}"))
@@ -89,6 +98,8 @@ def lstm_stack(x: torch.Tensor, layers: List[ops.LstmWeights], lstm: nn.LSTM = N
             h, _, _ = ops.lstm_layer_fwd_tc(h, k == 0, w_ih, w_hh, bias, L.packed)
         else:
             h, _, _ = ops.lstm_layer_fwd(h, k == 0, w_ih, w_hh, bias)
+    if true_h is not None and h.shape[-1] != true_h:      # zero-padded tensor-core layers: the model's own units only
+        h = h[..., :true_h].contiguous()
     return h
 
 
@@ -116,7 +127,7 @@ def _use_tc(module) -> bool:
         math = getattr(_SCOPE, "math", None)
     if math is None:
         math = ops.MATH_FP32
-    return math != ops.MATH_FP32 and module.lstm.hidden_size == 720
+    return math != ops.MATH_FP32 and module.lstm.hidden_size <= ops.TC_HIDDEN and ops.tc_available()
 
 
 class ForwardModel(nn.Module):
@@ -162,7 +173,7 @@ class EmbeddingModel(nn.Module):
         if self.training and self.lstm.dropout > 0 and self.lstm.num_layers > 1:
             raise _lib.PauleB200Error("inter-layer LSTM dropout in training mode is not implemented on the CUDA path "
                                       "(Paule's embedder uses dropout=0: paule/paule.py:167)")
-        h = lstm_stack(x, self._pack.get(_use_tc(self)))                      # [T,B,H]
+        h = lstm_stack(x, self._pack.get(_use_tc(self)), hidden=self.lstm.hidden_size)   # [T,B,H]
         B = x.shape[0]
         idx = torch.as_tensor([int(l) - 1 for l in lens], device=x.device, dtype=torch.long)
         if idx.numel() != B:
@@ -299,7 +310,7 @@ class InverseModelMelTimeSmoothResidual(nn.Module):
             cur = nxt
         feat = torch.empty((B, Tm, 3 * Cm), device=x.device, dtype=torch.float32)
         _lib.check(lib.paule_vel_acc_f32(cur.data_ptr(), feat.data_ptr(), B, Tm, Cm, st), "paule_vel_acc_f32")
-        h = lstm_stack(feat, self._pack.get(_use_tc(self)))                                         # [Tm,B,H]
+        h = lstm_stack(feat, self._pack.get(_use_tc(self)), hidden=self.lstm.hidden_size)           # [Tm,B,H]
         y = ops.linear_tm(h, _f32c(self.post_linear.weight), _f32c(self.post_linear.bias), False, True)  # [B,Tm,30]
         Cc = y.shape[2]
         nb = len(self.ResidualConvBlocks)
@@ -356,7 +367,7 @@ class MelEmbeddingModelMelSmoothResidualUpsampling(nn.Module):
             _lib.check(lib.paule_melconv_res_f32(cur.data_ptr(), w.data_ptr(), b.data_ptr(), nxt.data_ptr(), B, Tm, Cm,
                                                  st), "paule_melconv_res_f32")
             cur = nxt
-        h = lstm_stack(cur, self._pack.get(_use_tc(self)))                                # [T,B,H]
+        h = lstm_stack(cur, self._pack.get(_use_tc(self)), hidden=self.lstm.hidden_size)  # [T,B,H]
         idx = torch.as_tensor([int(l) - 1 for l in lens], device=x.device, dtype=torch.long)
         if idx.numel() != B:
             raise ValueError(f"lens has {idx.numel()} entries for a batch of {B}")

@@ -98,6 +98,29 @@ def transpose_btc(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+TC_HIDDEN = 720      # hidden size the persistent tcgen05 recurrent kernels are built for
+
+
+def pad_lstm_params(w_ih: torch.Tensor, w_hh: torch.Tensor, b_ih: torch.Tensor, b_hh: torch.Tensor, input_padded: bool):
+    """An LSTM layer with h <= 720 hidden units as a 720-unit layer: gate blocks of 720 rows, the layer's units first, zeros
+    behind.  EXACT: a unit whose weights and biases are zero has pre-activation 0, so i = f = o = 1/2, g = 0, c = 0, h = 0 at
+    every step; it receives no gradient and passes none on (its W_hh column is zero).  ``input_padded``: the layer's input is
+    the padded output of the layer below (input columns padded likewise)."""
+    H = TC_HIDDEN
+    w_ih, w_hh, b_ih, b_hh = (t.detach().float() for t in (w_ih, w_hh, b_ih, b_hh))
+    h, i = w_hh.shape[1], w_ih.shape[1]
+    if h == H and not (input_padded and i < H):
+        return w_ih, w_hh, b_ih, b_hh
+    W_ih, W_hh = w_ih.new_zeros(4 * H, H if input_padded else i), w_hh.new_zeros(4 * H, H)
+    B_ih, B_hh = b_ih.new_zeros(4 * H), b_hh.new_zeros(4 * H)
+    for g in range(4):
+        W_ih[g * H:g * H + h, :i] = w_ih[g * h:(g + 1) * h]
+        W_hh[g * H:g * H + h, :h] = w_hh[g * h:(g + 1) * h]
+        B_ih[g * H:g * H + h] = b_ih[g * h:(g + 1) * h]
+        B_hh[g * H:g * H + h] = b_hh[g * h:(g + 1) * h]
+    return W_ih, W_hh, B_ih, B_hh
+
+
 def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a [R, M], b [R, N] (row-major, contiguous) -> a^T b [M, N]: the weight-gradient reduction over all (step, word) rows
     (paule_gemm_tn_f32)."""

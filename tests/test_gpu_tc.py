@@ -173,3 +173,38 @@ def test_tc_fused_input_projection(B, T, I):
     np.testing.assert_allclose(g1.cpu().numpy(), g0.cpu().numpy(), atol=2 * tol)
     # the first step has no recurrent part: it isolates the projection itself
     np.testing.assert_allclose(g1[0].cpu().numpy(), g0[0].cpu().numpy(), atol=5e-4 if I <= 32 else 1.5e-3)   # bf16 W_ih
+
+
+@pytest.mark.parametrize("hidden,layers", [(360, 1), (180, 4)])
+def test_narrow_models_run_zero_padded_on_the_tensor_core_kernels(setup, hidden, layers):
+    """Hidden sizes below 720 (the somatosensory models' 360 units, ForwardModel's default 4 x 180: paule/paule.py:231-249,
+    paule/models.py:335-339) run on the persistent tcgen05 kernels zero-padded to 720 units -- exact up to the bf16 operand
+    rounding: forward and the gradient wrt the input against torch.nn.LSTM on the CPU."""
+    import paule_b200 as P
+    from paule_b200 import ops
+    dev = setup[0]
+    torch.manual_seed(5)
+    mine = P.ForwardModel(num_lstm_layers=layers, hidden_size=hidden)
+    ref = torch.nn.LSTM(30, hidden, num_layers=layers, batch_first=True)
+    ref.load_state_dict(mine.lstm.state_dict())
+    lin = torch.nn.Linear(hidden, 60)
+    lin.load_state_dict(mine.post_linear.state_dict())
+    for p in mine.parameters():
+        p.requires_grad_(False)
+    mine = mine.to(dev)
+    mine.math = ops.MATH_BF16
+    g = torch.Generator().manual_seed(6)
+    x = (torch.rand(3, 24, 30, generator=g) - 0.5)
+    xr = x.clone().requires_grad_()
+    yr = torch.nn.functional.avg_pool1d(lin(ref(xr)[0]).transpose(1, 2), 2, stride=2).transpose(1, 2)
+    w = torch.rand(yr.shape, generator=g) - 0.5
+    (yr * w).sum().backward()
+    xg = x.to(dev).requires_grad_()
+    y = mine(xg)
+    assert mine._pack.padded_from == hidden and mine._pack.layers[0].packed is not None
+    (y * w.to(dev)).sum().backward()
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), atol=3e-3)
+    scale = xr.grad.abs().max().item()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), xr.grad.numpy(), atol=3e-2 * scale)
+    with pytest.raises(AssertionError):
+        np.testing.assert_allclose(0 * xg.grad.cpu().numpy(), xr.grad.numpy(), atol=3e-2 * scale)
