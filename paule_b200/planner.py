@@ -93,6 +93,11 @@ class BatchPlanner:
         self.B, self.T, self.Tm, self.H, self.C, self.Cm, self.S = B, T, Tm, H, C, Cm, S
         if math is None:
             math = ops.default_math(H)
+        # tensor-core math with models narrower than 720 units: every layer zero-padded to 720 units (exact)
+        self._pad = math != ops.MATH_FP32 and H < ops.TC_HIDDEN
+        if self._pad:
+            H = ops.TC_HIDDEN
+            self.H = H
         self.objective, self.math = objective, math
         self.lengths, self.word_frames = None, None
         if lengths is not None:
@@ -174,13 +179,22 @@ class BatchPlanner:
     def refresh_weights(self) -> None:
         """(Re)pack the model weights; call after the models' parameters changed."""
         p, e = self._pred, self._emb
-        self.w_fwd = ops.LstmWeights(p.lstm.weight_ih_l0, p.lstm.weight_hh_l0, p.lstm.bias_ih_l0, p.lstm.bias_hh_l0,
-                                     tc=self._tc)
-        self.w_e0 = ops.LstmWeights(e.lstm.weight_ih_l0, e.lstm.weight_hh_l0, e.lstm.bias_ih_l0, e.lstm.bias_hh_l0,
-                                    tc=self._tc)
-        self.w_e1 = ops.LstmWeights(e.lstm.weight_ih_l1, e.lstm.weight_hh_l1, e.lstm.bias_ih_l1, e.lstm.bias_hh_l1,
-                                    tc=self._tc)
-        self.post_w, self.post_b = _f32c(p.post_linear.weight), _f32c(p.post_linear.bias)
+
+        def layer(lstm, k):
+            q = [getattr(lstm, f"{n}_l{k}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+            if self._pad:      # narrower than the tensor-core kernels' 720 units: zero-padded (exact, ops.pad_lstm_params)
+                q = ops.pad_lstm_params(*q, input_padded=(lstm is e.lstm and k == 1))
+            return ops.LstmWeights(*q, tc=self._tc)
+
+        def cols(w):           # Linear weight [out, h] reading a padded h: zero columns behind the model's own units
+            w = _f32c(w)
+            if not self._pad or w.shape[1] == self.H:
+                return w
+            out = w.new_zeros(w.shape[0], self.H)
+            out[:, :w.shape[1]] = w
+            return out.contiguous()
+        self.w_fwd, self.w_e0, self.w_e1 = layer(p.lstm, 0), layer(e.lstm, 0), layer(e.lstm, 1)
+        self.post_w, self.post_b = cols(p.post_linear.weight), _f32c(p.post_linear.bias)
         self.post_w_t = self.post_w.t().contiguous()
         self.post_packed = None
         if self._tc:
@@ -201,7 +215,7 @@ class BatchPlanner:
             self.bwd_fused_packed = torch.empty(lib.paule_tc_gemm_packed_bytes(wc.shape[0], 4), dtype=torch.uint8, device=wc.device)
             _lib.check(lib.paule_tc_gemm_pack(wc.data_ptr(), self.bwd_fused_packed.data_ptr(), wc.shape[0], 4, ops._stream()),
                        "paule_tc_gemm_pack")
-        self.head_w, self.head_b = _f32c(e.linear_mapping.weight), _f32c(e.linear_mapping.bias)
+        self.head_w, self.head_b = cols(e.linear_mapping.weight), _f32c(e.linear_mapping.bias)
         self.head_w_t = self.head_w.t().contiguous()
         if getattr(self, "_struct", None) is not None:
             self._build_struct()

@@ -435,3 +435,31 @@ def test_soak_many_steps_no_watchdog_and_repeatable(dev, models, B, T, steps):
         pl.close()
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 2e-3
     np.testing.assert_allclose(_np(outs[0][1][-1]), _np(outs[1][1][-1]), rtol=1e-3)
+
+
+@pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
+def test_narrow_models_plan_on_the_tensor_core_path_zero_padded(dev):
+    """Models narrower than the 720 units the tcgen05 kernels are built for (here 360: the width of the reference's
+    somatosensory models, paule/paule.py:231-249) plan in tensor-core mode with every layer zero-padded to 720 units, which is
+    exact: losses / cps against the CPU oracle on the SAME 360-unit models, model-path gradient against fp64 autograd."""
+    import paule_b200 as P
+    torch.manual_seed(0)
+    pred = P.ForwardModel(num_lstm_layers=1, hidden_size=360).to(dev)
+    emb = P.EmbeddingModel(num_lstm_layers=2, hidden_size=360).to(dev)
+    p32, e32, _ = O.build_reference_models(0, 360, torch.float32, with_inverse=False)
+    assert O.state_dict_digest(p32) == O.state_dict_digest(pred.cpu()) and O.state_dict_digest(e32) == O.state_dict_digest(emb.cpu())
+    pred, emb = pred.to(dev), emb.to(dev)
+    cp0, tmel = O.synthetic_inputs(3, 40, seed=11)
+    pl = P.BatchPlanner(pred, emb, cp0.to(dev), tmel.to(dev), None, max_log_steps=4, math=1)
+    assert pl.H == 720 and pl._pad
+    pl.step(1)
+    p64, e64, _ = O.build_reference_models(0, 360, torch.float64, with_inverse=False)
+    want = O.model_path_grad(p64, e64, cp0.double(), tmel.double()).numpy()
+    got = _np(pl.last_grad_lstm())
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-2 * np.abs(want).max())
+    with pytest.raises(AssertionError):
+        np.testing.assert_allclose(0 * got, want, rtol=0, atol=2e-2 * np.abs(want).max())
+    pl.step(3)
+    r = O.plan_inner_loop(p32, e32, cp0, tmel, 4)
+    np.testing.assert_allclose(_np(pl.losses()["total"]), r["loss"].numpy(), rtol=1e-3)
+    np.testing.assert_allclose(_np(pl.planned_cp()), r["planned_cp"].numpy(), atol=1e-3)
