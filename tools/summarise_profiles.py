@@ -2,6 +2,7 @@
 import csv, io, json, os, subprocess, sys, collections, re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+prefix = sys.argv[2] if len(sys.argv) > 2 else ""          # gpurun_out/<prefix>launches.csv, <prefix>prof_*.ncu-rep
 out_dir = os.path.join(ROOT, "profiles"); os.makedirs(out_dir, exist_ok=True)
 
 def short(name):
@@ -10,7 +11,7 @@ def short(name):
 
 # ---- launch list: per-kernel share of one planning step (the timed region replays a CUDA graph of exactly these kernels)
 rows = []
-with open(os.path.join(ROOT, "gpurun_out", "launches.csv")) as f:
+with open(os.path.join(ROOT, "gpurun_out", prefix + "launches.csv")) as f:
     lines = [l for l in f if l.startswith('"')]
 for r in csv.DictReader(io.StringIO("".join(lines))):
     try:
@@ -51,7 +52,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "l1tex__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic",
            "smsp__inst_executed.sum", "sm__inst_executed_pipe_tc", "tensor"]
 for rep in ("prof_fwd", "prof_bwd", "prof_gemm", "prof_elem"):
-    path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
+    path = os.path.join(ROOT, "gpurun_out", prefix + rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
     txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
