@@ -230,6 +230,7 @@ inline int* status_of(void* xchg) { return reinterpret_cast<int*>(reinterpret_ca
 
 struct WavePlan {
   int fwd = 0;          // 0 serial, 1 forward model || post_linear || embedder l0, 2 + gate GEMM || embedder l1
+  int f_ctas = 0;       // CTA limit of the forward-model recurrence (0: its latency-optimal layout)
   int e0_ctas = 0, e1_ctas = 0;
   int bwd = 0;          // 0 serial, 2 BPTT l0 || dX GEMM || BPTT forward model (l1 before, alone), 3 all three BPTT kernels
   int b_nq = 0, g_par = 0;   // quarters per CTA of the co-resident BPTT kernels (one common layout), GEMM CTAs per column tile
@@ -256,6 +257,17 @@ WavePlan plan_wavefront(const paule_plan* p, bool use_sem) {
     } else {
       const int e1 = left1 > 0 ? tc::fwd2_ctas(B, left1) : 0;
       if (e1 > 0) { wp.fwd = 1; wp.e0_ctas = e1; }
+      // 64 words: the forward model's latency layout (92 CTAs) leaves no room for embedder layer 1.  With TWO quarters per
+      // CTA (46 CTAs, 3.25 instead of 2.2 us per step) all five kernels fit, and T x 3.25 us beats T x 2.2 + the serial gate
+      // GEMM and layer 1 (T/2 x 2.2 us).  PAULE_WAVEFRONT_DENSE=0 keeps the three-kernel pipeline.
+      static const bool dense = getenv("PAULE_WAVEFRONT_DENSE") == nullptr || atoi(getenv("PAULE_WAVEFRONT_DENSE")) != 0;
+      const int n_f2 = tc::fwd2_ctas(B, n_f - 1);      // the next denser layout
+      if (dense && fwd_max >= 2 && n_f2 > 0) {
+        const int left = (sm - n_f2 - n_m - n_g1) / 2;
+        const int e = left > 0 ? tc::fwd2_ctas(B, left) : 0;
+        const float t_three = (float)p->T * 2.2f + 110.f + (float)(p->T / 2) * 2.2f, t_five = (float)p->T * 3.25f + 40.f;
+        if (e > 0 && t_five < t_three) { wp.fwd = 2; wp.f_ctas = n_f2; wp.e0_ctas = wp.e1_ctas = e; }
+      }
     }
   }
   if (use_sem && p->bwd_fused_packed != nullptr && p->word_frames == nullptr && B <= 64 && bwd_max >= 2) {
@@ -307,7 +319,7 @@ int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& w
   PAULE_TRY(fork_streams(ss, s, n_side));
   // (1) forward-model recurrence, T steps, announces every h_t image
   PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_f, p->fwd.packed, p->fwd.bias, w.x_img_f, nullptr, w.c_f, w.xchg, w.hf_img, T, B, s,
-                               tc::WaveFlags{w.f_hf, nullptr, 0, 0u}, 0));
+                               tc::WaveFlags{w.f_hf, nullptr, 0, 0u}, wp.f_ctas));
   // (2) pooled post_linear, streaming: pred_mel + operand blocks of embedder layer 0
   PAULE_TRY(tc::gemm_img_stream(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, w.f_hf, w.wf_target, 2, w.f_x0,
                                 w.x_img_0, 2, status_of(w.xchg), ss->s[0]));

@@ -216,8 +216,13 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
     for (int it = 0; it < T; ++it) {
       const int t = T - 1 - it;
       // (1) everything that does not depend on da_{t+1}: stash, cell states, external gradient of one quarter
-      float2 s_i, s_f, s_g, s_o, ct, cp, dh;
-      auto load_q = [&](int q) {
+      // Two register sets: the loads of a quarter are issued a whole pipeline stage before they are consumed (the quarter after
+      // next of this group is fetched while the current one is finalised), so the HBM latency of the stash reads is hidden in
+      // the multi-quarter layouts too (ncu, 4 quarters per CTA: the cell warps sat behind these loads, the loaders idle-polled)
+      struct QIn { float2 s_i, s_f, s_g, s_o, ct, cp, dh; };
+      QIn qbuf[2];
+      auto load_q = [&](int q, QIn& in) {
+        float2 s_i, s_f, s_g, s_o, ct, cp, dh;
         s_i = s_f = s_g = s_o = ct = cp = dh = make_float2(0.f, 0.f);
         const int wp = grp * kGW + q * kWq + w;
         if (jvalid && wp < Bv) {
@@ -254,6 +259,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
             dh.x += v.x; dh.y += v.y;
           }
         }
+        in.s_i = s_i; in.s_f = s_f; in.s_g = s_g; in.s_o = s_o; in.ct = ct; in.cp = cp; in.dh = dh;
       };
       // stage 1 of quarter q: partial sums out of TMEM and over to the sibling that finalises them (st.async: the bytes
       // complete on the sibling's mbarrier)
@@ -281,7 +287,9 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         TRACE(3)
       };
       // stage 2 of quarter q: sum the four partials, cell adjoint, publish da_t
-      auto finalize_q = [&](int q) {
+      auto finalize_q = [&](int q, const QIn& in) {
+        const float2 s_i = in.s_i, s_f = in.s_f, s_g = in.s_g, s_o = in.s_o, ct = in.ct, cp = in.cp;
+        float2 dh = in.dh;
         // cell adjoint (oracle: manual_lstm_backward_input).  It is linear in (dh, dc): every factor that only depends on the
         // stash is computed BEFORE the wait for the partial sums, so that the critical path after the wait is a handful of FMAs:
         //   do = dh * k_o;  dc' = dc + dh * k_c;  d_i = dc' * k_i;  d_f = dc' * k_f;  d_g = dc' * k_g;  dc <- dc' * s_f
@@ -358,15 +366,19 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         if (tl0) TL(13, q, it)   // epilogue: image / stash stores issued
         TRACE(6)
       };
-      // software pipeline over this group's quarters: quarter q's push overlaps quarter q-1's wait for its partial sums
-      load_q(eg * kQPG);
+      // software pipeline over this group's quarters: quarter q's push overlaps quarter q-1's wait for its partial sums; the
+      // first two quarters of the group are loaded here, quarter q + 2 right after quarter q has been finalised (register set
+      // q & 1 is free again)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (q / kQPG == eg && q - eg * kQPG < 2) load_q(q, qbuf[q & 1]);
 #pragma unroll
       for (int st = 0; st <= NQ; ++st) {
         const bool own_st = st < NQ && st / kQPG == eg;
         if (own_st && it > 0 && (grp * NQ + st) * kWq < Bv) push_q(st);
-        if (st >= 1 && (st - 1) / kQPG == eg && (grp * NQ + st - 1) * kWq < Bv) {
-          finalize_q(st - 1);
-          if (own_st) load_q(st);
+        if (st >= 1 && (st - 1) / kQPG == eg) {
+          if ((grp * NQ + st - 1) * kWq < Bv) finalize_q(st - 1, qbuf[(st - 1) & 1]);
+          if (st + 1 < NQ && (st + 1) / kQPG == eg) load_q(st + 1, qbuf[(st + 1) & 1]);
         }
       }
     }
