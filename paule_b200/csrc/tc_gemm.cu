@@ -11,8 +11,9 @@
 //   pre-packed bf16 image.  Warp-specialised, persistent over output tiles:
 //     warp 0  TMA producer  (4-stage ring of {A 16 KB, B BN x 128 B}, full/empty mbarriers)
 //     warp 1  MMA issuer    (tcgen05.mma M=128, N=BN, K=16; tcgen05.commit frees the stage / publishes the accumulator)
-//     warps 2-5 epilogue    (tcgen05.ld 32 columns at a time, 32 x 32 transpose through shared memory, + bias, fp32 row
-//                           segments of 128 B to HBM)
+//     warps 2-9 epilogue    (tcgen05.ld 32 columns at a time, 32 x 32 transpose through shared memory, + bias, fp32 row
+//                           segments of 128 B to HBM; two warps per TMEM lane group take alternate column chunks -- with four
+//                           epilogue warps the K = 720 projection was bound by the epilogue, 7.4 us per tile against 2.8 us of MMA)
 //   with two TMEM accumulator buffers (2 x 256 columns) so that the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -22,7 +23,8 @@ namespace paule {
 namespace tc {
 
 constexpr int kGemmStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmEpiWarps = 8;                 // two per TMEM lane group: they split the 32-column chunks of a tile
+constexpr int kGemmThreads = 32 * (2 + kGemmEpiWarps);
 constexpr int kSegLen = kH;          // real columns per K segment
 constexpr int kSegPad = kKPad;       // padded columns per K segment (12 k-blocks)
 
@@ -34,7 +36,7 @@ constexpr int kSegPad = kKPad;       // padded columns per K segment (12 k-block
 __host__ __device__ inline int pick_bn(int n_pad) {
   if (n_pad == 720) return 144;
   if (n_pad == 2880) return 160;   // measured (tools/gemm_time.py, 64 / 256 words): 240: 56.3 / 172 us, 192: 51.9 / 161, 160: 50.3 / 159, 144: 52.1 / 172
-  for (int bn = 256; bn >= 16; bn -= 16)
+  for (int bn = 240; bn >= 16; bn -= 16)   // 240: four stages + the eight epilogue staging tiles fit the 227 KB of an SM
     if (n_pad % bn == 0) return bn;
   return 16;
 }
@@ -64,7 +66,7 @@ struct GemmBars {
   // epilogue staging, one 32 x 32 tile per warp: a thread owns one accumulator ROW after tcgen05.ld, but rows of C are
   // N floats apart -- storing from registers makes every warp store touch 32 lines at 16 bytes each (1 TB/s on the K = 720
   // projection).  Through this transpose every store instruction writes four 128-byte row segments with full sectors.
-  alignas(16) float stage[4][32][kStageLd];
+  alignas(16) float stage[kGemmEpiWarps][32][kStageLd];
 };
 
 // Streaming mode (layer wavefront): the GEMM runs CONCURRENTLY with the recurrent kernel that produces its A
@@ -75,7 +77,7 @@ struct GemmBars {
 //     once its image stores of that step are out; steps complete in order) until it reaches `src_target[grp]`;
 //   * the epilogue also emits the tile as bf16 operand blocks of the consumer's fused input projection
 //     (`x_out`: [steps][ceil(B/16)][16 rows][128 B], SWIZZLE_128B, N <= 64 columns) and then increments `dst_flags[grp * n_pairs +
-//     pair]` (release; 4 arrivals = the 4 epilogue warps).
+//     pair]` (release; one arrival per epilogue warp).
 struct GemmStream {
   const unsigned int* src_flags;   // [n_groups][src_steps]
   const unsigned int* src_target;  // [n_groups] arrivals that complete a source step
@@ -119,7 +121,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
 
   if (tid == 0) {
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tmem_full[i], 1); mbar_init(&bars.tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tmem_full[i], 1); mbar_init(&bars.tmem_empty[i], kGemmEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&bars.tmem_base);
@@ -202,6 +204,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
   } else {
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     const int lg = warp & 3;                     // TMEM lane group this warp may access
+    const int ew = warp - 2;                     // epilogue warp 0..7: stage buffer; ew >> 2 = which alternate column chunks
     const int r = lg * 32 + lane;                // tile row: two time steps x 64 words
     int local = 0;
     for (int tile = tile_first; tile < total; tile += tile_stride, ++local) {
@@ -214,7 +217,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
       tcgen05_fence_after();
       float* crow = C + ((size_t)t * B + (valid ? b : 0)) * N;
       const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * 256);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 32 * (ew >> 2); c0 < BN; c0 += 32 * (kGemmEpiWarps / 4)) {
         float v[32];
         if (BN - c0 >= 32) {
           tmem_ld_x32(taddr + (uint32_t)c0, v);
@@ -248,7 +251,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
         }
         if ((N & 3) == 0) {
           // ---- coalesced path: own row -> staging, then 8 instructions x (4 rows x 128 B)
-          float* srow = &bars.stage[lg][lane][0];
+          float* srow = &bars.stage[ew][lane][0];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           __syncwarp();
@@ -261,7 +264,7 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
             const int rr = 4 * i + (lane >> 3), r2 = lg * 32 + rr;
             const int t2 = 2 * sp + (r2 >> 6), b2 = grp * kRows + (r2 & 63);
             if (col_ok && t2 < steps && b2 < B) {
-              float4 o = *reinterpret_cast<const float4*>(&bars.stage[lg][rr][cc]);
+              float4 o = *reinterpret_cast<const float4*>(&bars.stage[ew][rr][cc]);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
               float4* dst = reinterpret_cast<float4*>(C + ((size_t)t2 * B + b2) * N + n);
               if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
@@ -318,8 +321,8 @@ namespace tc {
 
 static int gemm_attrs() {
   static unsigned long long attr_set = 0ull;
-  if (once_per_device(attr_set)) {   // the widest tile (BN = 256) bounds every launch
-    const int smem_max = kGemmStages * (16384 + 256 * 128) + (int)sizeof(GemmBars) + 1024 + 16;
+  if (once_per_device(attr_set)) {   // the widest tile (BN = 240) bounds every launch
+    const int smem_max = kGemmStages * (16384 + 240 * 128) + (int)sizeof(GemmBars) + 1024 + 16;
     PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   }
@@ -330,10 +333,10 @@ int gemm_stream_ctas(int64_t B, int64_t N, int n_par) {
   const int np = pad_n((int)N), bn = pick_bn(np);
   return (int)((B + kRows - 1) / kRows) * (np / bn) * n_par;
 }
-// arrivals that complete one pair of output steps in dst_flags: 4 epilogue warps per column tile
+// arrivals that complete one pair of output steps in dst_flags: one per epilogue warp and column tile
 unsigned int gemm_stream_arrivals(int64_t N) {
   const int np = pad_n((int)N), bn = pick_bn(np);
-  return 4u * (unsigned int)(np / bn);
+  return (unsigned int)kGemmEpiWarps * (unsigned int)(np / bn);
 }
 
 // the GEMM of paule_tc_gemm_img in streaming mode (see GemmStream); `status` may be NULL
