@@ -541,6 +541,11 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
 // group; four independent slots (4,1) instead of two lock-step pairs (2,2): 6.42 us at 384 words, one lock-step pair (1,2)
 // instead of two slots (2,1): 4.40 against 3.23 us at 128 words -- no gain, not built.  Also measured and dropped: reading the
 // exchange block once before probing (the loader usually returns to a slot after its data has landed): +20-30 % per step.
+// Also measured and dropped (round 2, profiles/r2_fwd3_flag_tma_ab.txt): a flag + TMA exchange for these layouts -- cell warps
+// store h_t into the bf16 image, one release store per CTA and quarter publishes it, one issuer warp per slot polls the 23 flag
+// words and pulls the operand with twelve bulk copies.  ~60 instead of ~4 000 exchange-side instructions per slot visit, but the
+// chain (release fence behind the stash stores -> acquire poll -> bulk copy) is 5 us against 2.2 us and four independent slots
+// did not hide it: 9.3 against 5.7 us per step at 384 words.
 template <bool FUSED>
 int dispatch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int nq_min) {
