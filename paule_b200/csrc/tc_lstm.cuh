@@ -14,28 +14,40 @@
 #define TRACE_DUMP(base) {}
 #endif
 
-// -DPAULE_TC_TIMELINE: CTA 0 records (event, slot, step, globaltimer) tuples of steps [kTlFirst, kTlFirst + kTlSteps) into the
-// free part of the exchange header (tools/tc_timeline.py prints them as a timeline).  Debug builds only.
+// -DPAULE_TC_TIMELINE: two threads of CTA 0 (loader warp 3's lane 0, the first cell warp's lane 0) record (event, slot, step,
+// globaltimer) tuples of steps [kTlFirst, kTlFirst + kTlSteps) into the free part of the exchange header (tools/tc_timeline.py
+// prints them as a timeline).  Each thread counts its own events in a register and owns a range of the 64 slots: plain
+// fire-and-forget stores -- an atomic slot counter costs the recording thread an L2 round trip (~0.45 us) per event, which
+// distorted the very chain it measured.  Debug builds only.
 #ifdef PAULE_TC_TIMELINE
+#define TL_DECL(base_, max_) unsigned int tl_n = 0u; const unsigned int tl_base = (base_), tl_max = (max_);
 #define TL(ev, slot, step)                                                                                      \
   {                                                                                                             \
-    if (blockIdx.x == 0 && (step) >= kTlFirst && (step) < kTlFirst + kTlSteps) {                                 \
-      const unsigned int _i = atomicAdd(reinterpret_cast<unsigned int*>(xchg + kXchgTlOff), 1u);                  \
-      if (_i < kTlMax) {                                                                                        \
-        uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + kXchgTlOff + 16) + 2 * (size_t)_i;                     \
-        _o[0] = ((uint64_t)(ev) << 32) | ((uint64_t)(slot) << 16) | (uint64_t)(step);                            \
-        _o[1] = globaltimer_ns();                                                                                \
-      }                                                                                                          \
+    if (blockIdx.x == 0 && (step) >= kTlFirst && (step) < kTlFirst + kTlSteps && !kTlSkip(ev) && tl_n < tl_max) { \
+      uint64_t* _o = reinterpret_cast<uint64_t*>(xchg + kXchgTlOff) + 2 * (size_t)(tl_base + tl_n);               \
+      _o[0] = ((uint64_t)(ev) << 32) | ((uint64_t)(slot) << 16) | (uint64_t)(step);                              \
+      _o[1] = globaltimer_ns();                                                                                  \
+      ++tl_n;                                                                                                    \
     }                                                                                                            \
   }
 #else
+#define TL_DECL(base_, max_)
 #define TL(ev, slot, step) {}
 #endif
 
 namespace paule {
 namespace tc {
-constexpr int kTlFirst = 60, kTlSteps = 3, kXchgTlOff = 3072;   // = kXchgTraceOff (1 KB: 62 events)
-constexpr unsigned int kTlMax = 62;
+#ifndef PAULE_TL_STEPS
+#define PAULE_TL_STEPS 3
+#endif
+constexpr int kTlFirst = 60, kTlSteps = PAULE_TL_STEPS, kXchgTlOff = 3072;   // = kXchgTraceOff (1 KB: 64 events)
+constexpr unsigned int kTlLoaderEvents = 26, kTlCellEvents = 38;              // slots of the two recording threads
+// -DPAULE_TL_BRIEF: drop the "starts waiting" / "stash stores issued" events (four-quarter layouts: 62 events are two steps)
+#ifdef PAULE_TL_BRIEF
+__host__ __device__ constexpr bool kTlSkip(int ev) { return ev == 10 || ev == 13; }
+#else
+__host__ __device__ constexpr bool kTlSkip(int) { return false; }
+#endif
 
 constexpr int kH = 720;                 // hidden size the tensor-core path is built for (paule/paule.py:124,167)
 constexpr int kKPad = 768;              // K padded to 12 k-blocks of 64

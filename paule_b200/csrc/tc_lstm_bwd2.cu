@@ -142,6 +142,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 #define PAULE_BWD_BACKOFF_NS 0
 #endif
     const unsigned int bwd_backoff = (NQ == 1 && gridDim.x >= 4 * 4 * kBwd2Groups) ? (unsigned int)PAULE_BWD_BACKOFF_NS : 0u;
+    TL_DECL(0u, kTlLoaderEvents)
     TRACE_DECL
     for (int it = 1; it < T; ++it) {
 #pragma unroll
@@ -212,6 +213,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
       for (int q = 0; q < NQ; ++q)
         if (q / kQPG == eg) mbar_arrive(&S.acc_free[q]);
 
+    TL_DECL(kTlLoaderEvents, kTlCellEvents)
     TRACE_DECL
     for (int it = 0; it < T; ++it) {
       const int t = T - 1 - it;

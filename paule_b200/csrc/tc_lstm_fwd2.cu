@@ -219,6 +219,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
       __syncwarp();
     };
     if (xwarp) fetch_x(0);
+    TL_DECL(0u, kTlLoaderEvents)
     TRACE_DECL
     for (int t = FUSED ? 0 : 1; t < T; ++t) {
       const uint32_t par = (uint32_t)((FUSED ? t : t - 1) & 1);
@@ -322,6 +323,7 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
       for (int s = 0; s < NS; ++s)
         if (kByQ || s % EG == eg) mbar_arrive(&S.acc_free[s]);
 
+    TL_DECL(kTlLoaderEvents, kTlCellEvents)
     TRACE_DECL
     for (int t = 0; t < T; ++t) {
       // input projection of this step (independent of h_{t-1}): quarter 0's loads are issued before the wait, quarter
@@ -546,6 +548,10 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
 // words and pulls the operand with twelve bulk copies.  ~60 instead of ~4 000 exchange-side instructions per slot visit, but the
 // chain (release fence behind the stash stores -> acquire poll -> bulk copy) is 5 us against 2.2 us and four independent slots
 // did not hide it: 9.3 against 5.7 us per step at 384 words.
+// Also measured and dropped (profiles/r2_xchg_prefetch_ab.txt): reading the NEXT visit's block one visit ahead into registers
+// (values validate themselves, so a speculative read is safe).  The timeline (tools/tc_timeline.py) shows a visit costing 1.7 us,
+// but the data lands only ~0.8 us before the visit begins: the speculative read mostly finds the old phase, and its extra loads
+// on lines that are being written slow every exchange -- 3.35 -> 4.52 us at 128 words, 5.7 -> 11.5 us at 384.
 template <bool FUSED>
 int dispatch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
                   void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int nq_min) {

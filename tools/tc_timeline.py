@@ -21,8 +21,8 @@ for B in [int(a) for a in sys.argv[1:]] or [384]:
         rc = lib.paule_tc_lstm_seq_fwd_x(g.data_ptr(), w.packed.data_ptr(), w.bias.data_ptr(), ximg.data_ptr(), h.data_ptr(), c.data_ptr(),
                                          xchg.data_ptr(), None, T, B, 1, st)
         e1.record(); torch.cuda.synchronize()
-    n = int(xchg[3072:3076].view(torch.int32).item())
-    ev = xchg[3072 + 16:3072 + 16 + 16 * min(n, 62)].view(torch.int64).cpu().reshape(-1, 2).tolist()
+    ev = [r for r in xchg[3072:4096].view(torch.int64).cpu().reshape(-1, 2).tolist() if r[1] != 0]
+    n = len(ev)
     ev.sort(key=lambda r: r[1])
     t0 = ev[0][1] if ev else 0
     print(f"B={B} fused fwd {e0.elapsed_time(e1)*1e3/T:.2f} us/step, rc={rc}, {n} events")
@@ -40,8 +40,8 @@ for B in [int(a) for a in sys.argv[1:]] or [384]:
         e0.record()
         rc = lib.paule_tc_lstm_seq_bwd_img(gg.data_ptr(), c.data_ptr(), w.packed.data_ptr(), dh.data_ptr(), 1, None, xchg.data_ptr(), daimg.data_ptr(), T, B, 1, st)
         e1.record(); torch.cuda.synchronize()
-    n = int(xchg[3072:3076].view(torch.int32).item())
-    ev = xchg[3072 + 16:3072 + 16 + 16 * min(n, 62)].view(torch.int64).cpu().reshape(-1, 2).tolist()
+    ev = [r for r in xchg[3072:4096].view(torch.int64).cpu().reshape(-1, 2).tolist() if r[1] != 0]
+    n = len(ev)
     ev.sort(key=lambda r: r[1])
     t0 = ev[0][1] if ev else 0
     print(f"B={B} bwd {e0.elapsed_time(e1)*1e3/T:.2f} us/step, rc={rc}, {n} events")
