@@ -53,6 +53,63 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// ---- CTA pair (cta_group::2): one tcgen05.mma spans the two SMs of a cluster of 2 -- M = 256 (128 rows in each CTA's tensor
+// memory), A from each CTA's own shared memory, B split over the two CTAs (N/2 rows each).  Issued by the leader CTA only.
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` when all previously issued pair MMAs completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst) {  // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t tmem_addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "r"(kCols) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics (as CUTLASS'
+// ClusterBarrier::arrive(cta_id)): the explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive
+// (~1 us per call, measured: it serialised the CTA-pair GEMM's per-stage hand-over).  What the arrive publishes here was
+// written by the async proxy (TMA, tcgen05.ld) and completed on an mbarrier / tcgen05 fence before this thread arrives.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait with cluster-scope acquire: the phase may have been completed by the other CTA of the cluster
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // A operand in tensor memory ("TS"): [M = 128 lanes, K] bf16, 32-bit column c of lane m holds k = 2c (low half) and 2c+1;
 // one instruction consumes K = 16 = 8 columns.  Measured (tools/mma_bench.cu): 12 warps x 4 MMAs (M=128, N=16) into one
 // accumulator complete in 653 cycles with A in TMEM against 2082 with A streamed from shared memory.
@@ -205,6 +262,21 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   for (unsigned int spin = 0;; ++spin) {
     if (mbar_try_wait(bar, parity)) return true;   // try_wait suspends in hardware: this is not a busy poll
     if ((spin & 63u) == 63u) {                     // watchdog bookkeeping stays off the wake-up path
+      if (t0 == 0) t0 = globaltimer_ns();
+      if (*err_flag != 0) return false;
+      if (globaltimer_ns() - t0 > kWatchdogNs) {
+        *err_flag = 2;
+        return false;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity, volatile int* err_flag) {
+  uint64_t t0 = 0;
+  for (unsigned int spin = 0;; ++spin) {
+    if (mbar_try_wait_cl(bar, parity)) return true;
+    if ((spin & 63u) == 63u) {
       if (t0 == 0) t0 = globaltimer_ns();
       if (*err_flag != 0) return false;
       if (globaltimer_ns() - t0 > kWatchdogNs) {

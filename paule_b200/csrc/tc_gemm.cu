@@ -35,7 +35,14 @@ constexpr int kSegPad = kKPad;       // padded columns per K segment (12 k-block
 // embedder layer 1): 160-wide tiles measured fastest at both ends.
 __host__ __device__ inline int pick_bn(int n_pad) {
   if (n_pad == 720) return 144;
-  if (n_pad == 2880) return 160;   // measured (tools/gemm_time.py, 64 / 256 words): 240: 56.3 / 172 us, 192: 51.9 / 161, 160: 50.3 / 159, 144: 52.1 / 172
+  if (n_pad == 2880) {
+#ifndef __CUDA_ARCH__
+    static const int forced = getenv("PAULE_GEMM_BN") ? atoi(getenv("PAULE_GEMM_BN")) : 0;   // A/B timing
+    if (forced >= 16 && forced <= 240 && forced % 16 == 0 && 2880 % forced == 0) return forced;
+#endif
+    return 160;
+  }
+  // N = 2880, single-CTA kernel, measured (tools/gemm_time.py, 64 / 256 words): 240: 56.3 / 172 us, 192: 51.9 / 161, 160: 50.3 / 159, 144: 52.1 / 172
   for (int bn = 240; bn >= 16; bn -= 16)   // 240: four stages + the eight epilogue staging tiles fit the 227 KB of an SM
     if (n_pad % bn == 0) return bn;
   return 16;
@@ -273,12 +280,15 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
           }
           __syncwarp();   // the staging tile is rewritten by the next chunk
         } else if (valid) {
-          for (int i = 0; i < lim; ++i) {
+          // (static indexing: a run-time index into v[] would put the whole array into local memory for every variant)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
             const int n = n0 + i;
-            if (n >= N) break;
-            float o = v[i] + (bias ? __ldg(bias + n) : 0.f);
-            if (accumulate) o += crow[n];
-            crow[n] = o;
+            if (i < lim && n < N) {
+              float o = v[i] + (bias ? __ldg(bias + n) : 0.f);
+              if (accumulate) o += crow[n];
+              crow[n] = o;
+            }
           }
         }
       }
@@ -294,6 +304,192 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ---- CTA-pair variant of the batch mode (wide outputs: N = 2880 / 720) ------------------------------------------------------
+// ncu on the K = 720, N = 2880 projection (profiles/r2b_ncu_gategemm.txt): tensor pipe 36 % active, L2 and crossbar at 26-41 % of
+// their peaks, producer and MMA warps waiting on each other -- every SM takes in ~41 B per cycle, about what an SM takes in
+// under cuBLAS at its peak, but a 128 x 160 tile only does 71 FLOP per byte received.  With tcgen05.mma.cta_group::2 the two SMs
+// of a cluster run ONE M = 256 MMA: each CTA stages its own 128 rows of A and only HALF of the B tile (80 rows), i.e. 26 instead
+// of 36 KB per k-block for the same arithmetic (98 FLOP per byte), and the ring holds 6 stages instead of 4.
+//   rank 0 (leader): producer, MMA issuer (M = 256), epilogue of the first row tile of the pair
+//   rank 1 (peer):   producer, forwarder (its "stage landed" -> the leader's peer_full barrier), epilogue of the second row tile
+// tcgen05.commit.cta_group::2 with a multicast mask frees the stage / publishes the accumulator in both CTAs.
+constexpr int kGemm2MaxStages = 8;
+struct Gemm2Bars {
+  uint64_t full[kGemm2MaxStages];     // this CTA's loads of the stage landed (tx-count)
+  uint64_t peer_full[kGemm2MaxStages];   // leader only: the peer's loads of the stage landed (remote arrive by the peer's forwarder)
+  uint64_t empty[kGemm2MaxStages];    // the pair's MMAs have read the stage (commit, multicast to both CTAs)
+  uint64_t tmem_full[2];              // accumulator complete (commit, multicast)
+  uint64_t tmem_empty[2];             // leader only: both CTAs' epilogue warps have drained the buffer
+  uint32_t tmem_base;
+  alignas(16) float stage[kGemmEpiWarps][32][kStageLd];
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+tc_gemm_img2_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, const float* __restrict__ bias,
+                    float* __restrict__ C, int steps, int B, int N, int KB, int BN, int accumulate, int* status,
+                    int kGemm2Stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_half = (uint32_t)BN * 64u;                  // this CTA's half of the B tile: BN / 2 rows x 128 B
+  const uint32_t stage_bytes = 16384u + b_half;                // BN % 16 == 0 keeps 1 KB alignment
+  Gemm2Bars& bars = *reinterpret_cast<Gemm2Bars*>(base + (size_t)kGemm2Stages * stage_bytes);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const uint32_t rank = cluster_ctarank_u32();
+  const bool leader = rank == 0;
+  __shared__ int local_err;
+  volatile int* err = (status != nullptr) ? reinterpret_cast<volatile int*>(status) : reinterpret_cast<volatile int*>(&local_err);
+  if (threadIdx.x == 0) local_err = 0;
+
+  const int n_groups = (B + kRows - 1) / kRows;
+  const int n_pairs = (steps + 1) / 2;
+  const int n_nt = pad_n(N) / BN;
+  const int n_rt = n_groups * n_pairs;                         // row tiles (two time steps of one 64-word group)
+  const int total = ((n_rt + 1) / 2) * n_nt;                   // pair tiles: column tile fastest, two consecutive row tiles
+  const int tile_first = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1);
+  auto coords = [&](int tile, int& nt, int& sp, int& grp, bool& valid_rt) {
+    nt = tile % n_nt;
+    int rt = 2 * (tile / n_nt) + (int)rank;
+    valid_rt = rt < n_rt;
+    if (!valid_rt) rt = n_rt - 1;                              // odd count: the last pair's second tile is computed and dropped
+    sp = rt % n_pairs; grp = rt / n_pairs;
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < kGemm2Stages; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.peer_full[i], 1); mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.tmem_full[i], 1); mbar_init(&bars.tmem_empty[i], 2 * kGemmEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(&bars.tmem_base);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit targets them
+  tcgen05_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer: own A rows, own half of the B tile =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = tile_first; tile < total; tile += tile_stride) {
+      int nt, sp, grp; bool vr;
+      coords(tile, nt, sp, grp, vr);
+      const int t0 = 2 * sp;
+      const bool two = (t0 + 1 < steps);
+      const uint8_t* a0 = a_img + ((size_t)(grp * steps + t0) * KB) * (kRows * 128);
+      const uint8_t* bt = b_img + (size_t)nt * KB * BN * 128 + (size_t)rank * b_half;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&bars.empty[s], ph ^ 1u, err);
+        if (elect_one_sync()) {
+          uint8_t* sa = base + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&bars.full[s], (two ? 16384u : 8192u) + b_half);
+          bulk_g2s(sa, a0 + (size_t)kb * (kRows * 128), kRows * 128, &bars.full[s]);
+          if (two) bulk_g2s(sa + 8192, a0 + ((size_t)KB + kb) * (kRows * 128), kRows * 128, &bars.full[s]);
+          bulk_g2s(sa + 16384, bt + (size_t)kb * BN * 128, b_half, &bars.full[s]);
+        }
+        __syncwarp();
+        if (++s == kGemm2Stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (M = 256 over the pair) =====================
+    const uint32_t idesc = make_idesc_bf16(256, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    int local = 0;
+    for (int tile = tile_first; tile < total; tile += tile_stride, ++local) {
+      const int ab = local & 1;
+      mbar_wait(&bars.tmem_empty[ab], (uint32_t)(((local >> 1) & 1) ^ 1), err);   // both epilogues drained this buffer
+      tcgen05_fence_after();
+      const uint32_t d = tmem + (uint32_t)(ab * 256);
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&bars.full[s], ph, err);
+        mbar_wait(&bars.peer_full[s], ph, err);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc_sw128(sa);
+        const uint64_t db = make_smem_desc_sw128(sa + 16384u);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_2cta(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2cta(&bars.empty[s], 3);
+          if (kb == KB - 1) umma_commit_2cta(&bars.tmem_full[ab], 3);
+        }
+        __syncwarp();
+        if (++s == kGemm2Stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== peer: forward "my part of the stage landed" to the leader =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = tile_first; tile < total; tile += tile_stride) {
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&bars.full[s], ph, err);
+        if (elect_one_sync()) mbar_arrive_remote(&bars.peer_full[s], 0u);
+        __syncwarp();
+        if (++s == kGemm2Stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue of this CTA's 128 rows: TMEM -> staging -> HBM =====================
+    const int lg = warp & 3;
+    const int ew = warp - 2;
+    int local = 0;
+    for (int tile = tile_first; tile < total; tile += tile_stride, ++local) {
+      int nt, sp, grp; bool vr;
+      coords(tile, nt, sp, grp, vr);
+      const int ab = local & 1;
+      mbar_wait(&bars.tmem_full[ab], (uint32_t)((local >> 1) & 1), err);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * 256);
+      for (int c0 = 32 * (ew >> 2); c0 < BN && vr; c0 += 32 * (kGemmEpiWarps / 4)) {
+        float v[32];
+        if (BN - c0 >= 32) {
+          tmem_ld_x32(taddr + (uint32_t)c0, v);
+        } else {
+          float v16[16];
+          tmem_ld_x16(taddr + (uint32_t)c0, v16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0.f; }
+        }
+        const int n0 = nt * BN + c0;
+        const int lim = (BN - c0 >= 32) ? 32 : 16;
+        float* srow = &bars.stage[ew][lane][0];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncwarp();
+        const int cc = (lane & 7) * 4, n = n0 + cc;
+        const bool col_ok = cc < lim && n < N;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), r2 = lg * 32 + rr;
+          const int t2 = 2 * sp + (r2 >> 6), b2 = grp * kRows + (r2 & 63);
+          if (col_ok && t2 < steps && b2 < B) {
+            float4 o = *reinterpret_cast<const float4*>(&bars.stage[ew][rr][cc]);
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            float4* dst = reinterpret_cast<float4*>(C + ((size_t)t2 * B + b2) * N + n);
+            if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            *dst = o;
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&bars.tmem_empty[ab]);
+        else mbar_arrive_remote(&bars.tmem_empty[ab], 0u);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // no CTA of the pair leaves (or frees tensor memory) while the other may still signal it
+  if (warp == 1) tmem_dealloc_2cta<512>(tmem);
 }
 
 }  // namespace tc
@@ -376,6 +572,29 @@ int paule::tc::gemm_img(const void* a_img, const void* packed_b, const float* bi
   const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
   const int n_groups = (int)((B + kRows - 1) / kRows), n_pairs = (int)((steps + 1) / 2);
   const int64_t total = (int64_t)n_groups * n_pairs * (np / bn);
+  // wide outputs: the CTA-pair kernel (PAULE_GEMM_2CTA=0: the single-CTA kernel, A/B timing)
+  static const bool pair_on = getenv("PAULE_GEMM_2CTA") == nullptr || atoi(getenv("PAULE_GEMM_2CTA")) != 0;
+  if (pair_on && bn >= 128 && (N % 4) == 0 && n_groups * n_pairs >= 2) {
+    static unsigned long long attr2 = 0ull;
+    const int smem_cap = 227 * 1024 - 256;   // opt-in maximum less the kernel's static shared memory
+    if (once_per_device(attr2))
+      PAULE_CUDA(cudaFuncSetAttribute(tc_gemm_img2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+    // as many stages as fit next to the barriers and the epilogue staging tiles (BN = 160: 7, BN = 144: 7, BN = 240: 6)
+    static const int forced_stages = getenv("PAULE_GEMM2_STAGES") ? atoi(getenv("PAULE_GEMM2_STAGES")) : 0;
+    const int fixed = (int)sizeof(Gemm2Bars) + 1024 + 16, per_stage = 16384 + bn * 64;
+    int stages = (smem_cap - fixed) / per_stage;
+    if (stages > kGemm2MaxStages) stages = kGemm2MaxStages;
+    if (forced_stages >= 2 && forced_stages <= stages) stages = forced_stages;
+    const int smem2 = stages * per_stage + fixed;
+    const int64_t pairs = (int64_t)((n_groups * n_pairs + 1) / 2) * (np / bn);
+    const int max_clusters = sm_count() / 2;
+    const int clusters = (int)(pairs < max_clusters ? pairs : max_clusters);
+    tc_gemm_img2_kernel<<<2 * clusters, kGemmThreads, (size_t)smem2, stream>>>(
+        reinterpret_cast<const uint8_t*>(a_img), reinterpret_cast<const uint8_t*>(packed_b), bias, C, (int)steps, (int)B,
+        (int)N, KB, bn, accumulate, status, stages);
+    PAULE_LAUNCH_CHECK("tc_gemm_img2_kernel");
+    return PAULE_OK;
+  }
   const int smem = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
   const int grid = (int)((total < (int64_t)sm_count()) ? total : (int64_t)sm_count());
   GemmStream st{};
