@@ -299,9 +299,10 @@ WavePlan plan_wavefront(const paule_plan* p, bool use_sem) {
   return wp;
 }
 
-int zero_wave_flags(const paule_plan* p, const Workspace& w, cudaStream_t s) {
+int zero_wave_flags(const paule_plan* p, const Workspace& w, cudaStream_t s, bool targets = true) {
   const int n_groups = (int)((p->B + 63) / 64);
   PAULE_CUDA(cudaMemsetAsync(w.wf_flags, 0, sizeof(unsigned int) * w.wf_flag_count, s));
+  if (!targets) return PAULE_OK;   // the targets only depend on B: the forward pipeline of the same step wrote them
   wave_targets_kernel<<<(n_groups + 63) / 64, 64, 0, s>>>(w.wf_target, w.wf_target_b, (int)p->B, n_groups);
   PAULE_LAUNCH_CHECK("wave_targets_kernel");
   return PAULE_OK;
@@ -341,7 +342,7 @@ int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& w
   return PAULE_OK;
 }
 
-// BPTT of the embedder (both layers, or layer 0 only) and of the forward model as one reverse-time pipeline.  On entry dhp holds
+// BPTT of the embedder (both layers, or layer 0 only) and of the forward model as one reverse-time pipeline.  dhp first receives
 // the mel-loss part d(mel term)/d(pooled h) = dmel W_post; the streaming GEMM adds dA_0 (W_ih0 W_post) step by step.
 int backward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& wp, paule_stream_t stream) {
   const int64_t B = p->B, T = p->T, Tm = T / 2, H = p->H;
@@ -350,9 +351,23 @@ int backward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& 
   SideStreams* ss = nullptr;
   PAULE_TRY(side_streams(&ss));
   const unsigned int g_arr = tc::gemm_stream_arrivals(H);
-  PAULE_TRY(zero_wave_flags(p, w, s));
-  if (wp.bwd == 2)   // layer 1 first, alone, in its usual layout; its dX GEMM as a batch GEMM
+  PAULE_TRY(zero_wave_flags(p, w, s, wp.fwd == 0));   // (the forward pipeline of this step already wrote the targets)
+  // mel-loss part of d/d(pooled h): dhp = dmel W_post (the un-pooling, x0.5 to both frames of a pair, is folded into the BPTT's dh
+  // load); only the forward model's BPTT reads it
+  auto mel_part = [&](cudaStream_t st) {
+    return paule_linear_f32(w.dmel, p->post_w_t, nullptr, w.dhp, Tm * B, H, p->Cm, 1, p->Cm, 0, 0, 1, H, 0, 0,
+                            reinterpret_cast<paule_stream_t>(st));
+  };
+  if (wp.bwd == 2) {
+    // layer 1 first, alone, in its usual layout (96 of the 148 SMs at 64 words); its dX GEMM as a batch GEMM.  The mel part runs
+    // beside it on the SMs it leaves free.
+    PAULE_TRY(fork_streams(ss, s, 1));
+    PAULE_TRY(mel_part(ss->s[0]));
     PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, stream));
+    PAULE_TRY(join_streams(ss, s, 1));
+  } else {
+    PAULE_TRY(mel_part(s));
+  }
   // PAULE_WAVE_SERIALIZE=1 (debugging): the same kernels with the same flags, one after the other on one stream in dependency
   // order -- every wait finds its counter complete
   static const bool serialize = getenv("PAULE_WAVE_SERIALIZE") != nullptr;
@@ -516,7 +531,7 @@ extern "C" int64_t paule_plan_step_launches(const paule_plan* p) {
   }
   const WavePlan wb = plan_wavefront(p, use_sem);
   if (use_sem && wb.bwd != 0) {
-    n += 2 + 1 + (wb.bwd == 2 ? bpass + 1 : 2) + 3 + 1 + 1;              // head^T, post^T, targets, l1 (+ dX), BF, l0, GEMM, status, dX
+    n += 2 + (wb.fwd == 0 ? 1 : 0) + (wb.bwd == 2 ? bpass + 1 : 2) + 3 + 1 + 1;   // head^T, post^T, (targets), l1 (+ dX), BF, l0, GEMM, status, dX
   } else {
     if (use_sem) n += 1 + ragged + 2 * (bpass + 1);
     n += 1 + bpass + 1;
@@ -548,9 +563,7 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
   const WavePlan wp = plan_wavefront(p, use_sem);
   if (use_sem && wp.bwd != 0) {                                                    // discrepancy.backward(), :1052, as a pipeline
     PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));   // dh1[Tm-1] = dsv W_head
-    // mel-loss part of d/d(pooled h); the un-pooling (x0.5 to both frames of a pair) is folded into the BPTT's dh load
-    PAULE_TRY(paule_linear_f32(w.dmel, p->post_w_t, nullptr, w.dhp, Tm * B, H, Cm, 1, Cm, 0, 0, 1, H, 0, 0, s));
-    PAULE_TRY(backward_wavefront(p, w, wp, s));
+    PAULE_TRY(backward_wavefront(p, w, wp, s));   // (computes the mel-loss part dhp = dmel W_post itself)
     PAULE_TRY(adam_clamp_logged(p->cp, w.dcp_lstm, w.dcp_smooth, p->adam_m, p->adam_v, p->step_count, p->lr, p->beta1,
                                 p->beta2, p->eps, p->clamp, p->smiling, p->past_cp, p->past_T, p->grad_out, T, B, C, s,
                                 p->extra_grad));
