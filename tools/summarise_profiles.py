@@ -50,8 +50,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__inst_executed_pipe_uniform", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
            "launch__grid_size", "launch__block_size", "launch__cluster", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "l1tex__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic",
-           "smsp__inst_executed.sum", "sm__inst_executed_pipe_tc", "tensor"]
-for rep in ("prof_fwd", "prof_bwd", "prof_gemm", "prof_elem"):
+           "smsp__inst_executed.sum", "sm__inst_executed_pipe_tc", "tensor", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__throughput.avg",
+           "sm__cycles_active.avg"]
+for rep in ("prof_fwd", "prof_bwd", "prof_gemm", "prof_gemm2", "prof_gategemm", "prof_elem"):
     path = os.path.join(ROOT, "gpurun_out", prefix + rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -84,8 +85,14 @@ for kind in ("fwd", "bwd"):
     if os.path.exists(path):
         rd, wr, dur = _metric(path, "dram__bytes_read.sum"), _metric(path, "dram__bytes_write.sum"), _metric(path, "gpu__time_duration.sum")
         if rd is not None and wr is not None and dur:
-            # the captured launch is one layer of the bench workload (B = 64): 200 steps if it ran > 400 us, else 100
-            steps = 200 if dur > 400e-6 else 100
+            # the captured launch is one layer of the bench workload (B = 64, T = 200): the forward model (200 steps; forward: the
+            # 2-quarter fused layout <2, 1, 1, 2> or, without the dense pipeline, <1, 1, 1, 1>; backward: > 500 us) or an embedder
+            # layer (100 steps)
+            head = open(path).read(400)
+            if kind == "fwd":
+                steps = 200 if ("fwd2_kernel<2, 1, 1, 2>" in head or "fwd2_kernel<1, 1, 1, 1>" in head) else 100
+            else:
+                steps = 200 if dur > 500e-6 else 100
             traffic[kind] = {"dram_bytes_per_word_step": (rd + wr) / (64 * steps), "captured_steps": steps, "captured_us": dur * 1e6,
                              "source": f"profiles/{tag}_ncu_{kind}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
 json.dump(traffic, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
