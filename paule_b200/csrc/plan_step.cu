@@ -520,7 +520,7 @@ extern "C" int64_t paule_plan_step_launches(const paule_plan* p) {
     n += 1 + (T + 1);                                                    // post_linear^T, BPTT + dX of the forward model
     return n;
   }
-  const int64_t fpass = (B + 6 * 64 - 1) / (6 * 64), bpass = (B + 5 * 64 - 1) / (5 * 64);   // launches per recurrent layer
+  const int64_t fpass = tc::fwd2_passes(B), bpass = tc::bwd2_passes(B);   // launches per recurrent layer
   const WavePlan wf = need_sv ? plan_wavefront(p, false) : WavePlan{};
   if (wf.fwd != 0) {
     n += 1 + 1 + fpass + 1 + 1 + 1;                                      // targets, x image, forward model, GEMM, embedder l0, status

@@ -115,6 +115,50 @@ inline int64_t pass_words(int64_t B, int max_groups, int nq) {
   return (per + gw - 1) / gw * gw;
 }
 
+// Batches beyond one launch: the words are independent, so the batch is cut into passes, each with its own quarters per CTA.
+// A multi-quarter layout's step time does not depend on how many of its word groups are occupied, so
+// balancing the words over the passes wastes groups: 1024 words through the BPTT kernel are 4 balanced passes of 256 words at
+// 4 quarters per CTA (4 x 7.05 us per step, 4 of 5 groups used) -- or 4 full passes of 240 words at 3 quarters plus one
+// latency-layout pass of 64 (4 x 5.2 + 2.85 us).  plan_passes minimises the summed step time over the passes with a small
+// dynamic program over word quarters; cost[nq] = measured us per step of the layout with nq quarters per CTA.
+struct PassPlan {
+  int n = 0;
+  int nq[96];       // quarters per CTA of pass i
+  int words[96];    // words of pass i (multiples of 16 except the last)
+};
+inline bool plan_passes(int64_t B, int max_groups, const float* cost, PassPlan* out) {
+  const int64_t Q64 = (B + kWq - 1) / kWq;
+  if (Q64 > 2048) return false;
+  const int Q = (int)Q64;
+  static thread_local float best[2049];
+  static thread_local unsigned char pick[2049];
+  best[0] = 0.f;
+  for (int q = 1; q <= Q; ++q) {
+    best[q] = 1e30f;
+    for (int nq = 1; nq <= 4; ++nq) {
+      const int cap = max_groups * nq, rest = q > cap ? q - cap : 0;
+      const float c = best[rest] + cost[nq] + 1e-3f * (float)nq;   // ties: the smaller layout
+      if (c < best[q]) { best[q] = c; pick[q] = (unsigned char)nq; }
+    }
+  }
+  out->n = 0;
+  int64_t left = B;
+  for (int q = Q; q > 0;) {
+    if (out->n >= 96) return false;
+    const int nq = pick[q], cap = max_groups * nq, take = q > cap ? cap : q;
+    const int64_t w = (int64_t)take * kWq < left ? (int64_t)take * kWq : left;
+    out->nq[out->n] = nq;
+    out->words[out->n] = (int)w;
+    ++out->n;
+    left -= w;
+    q -= take;
+  }
+  return true;
+}
+// measured us per step by quarters per CTA (tools/rnn_time.py, B200): forward (1,1) / (2,1) / (3,1) / (2,2), backward NQ = 1..4
+constexpr float kFwdStepUs[5] = {0.f, 2.25f, 3.3f, 4.7f, 5.7f};
+constexpr float kBwdStepUs[5] = {0.f, 2.85f, 3.7f, 5.2f, 7.05f};
+
 // Probe polling variants, measured at 64 words (forward step 2.42 us with the defaults): two probe loads in flight 2.75 us
 // (more polling traffic slows every exchange), a 40 / 120 ns back-off between failed probes 2.39 / 2.41 us (neutral).
 // Later A/B (same box, two builds each): 300 ns -> forward 2.27 -> 2.19 us at 64 words, but 1.74 -> 1.83 us at one word and
@@ -285,6 +329,9 @@ int lstm_seq_fwd2x(float* gates, const void* packed, const float* bias, const vo
                    void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf = kNoWave, int max_ctas = 0);
 // CTAs lstm_seq_fwd2x launches for B words when at most max_ctas (0: no limit) may be used; 0 = does not fit one launch
 int fwd2_ctas(int64_t B, int max_ctas);
+// launches of one recurrent layer over B words (the pass plan above; 1 up to 384 / 320 words)
+int fwd2_passes(int64_t B);
+int bwd2_passes(int64_t B);
 // batched tcgen05 GEMM over image sequences (tc_gemm.cu): batch mode with a status word, streaming mode for the wavefront
 int gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
              int64_t nseg, int accumulate, int* status, cudaStream_t s);

@@ -392,9 +392,12 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   cluster_sync_all2();   // no CTA exits while a sibling may still address its shared memory
 }
 
+// B = words of the whole batch (row stride of the time-major tensors); the launch covers words [seg0, seg0 + seg_words)
+// (seg_words = 0: all of them), in balanced passes of this layout when they exceed one launch
 template <int NQ, int EG>
 int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
-                void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf) {
+                void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int64_t seg0 = 0,
+                int64_t seg_words = 0) {
   static unsigned long long attr_set = 0ull;
   const int smem_own = (int)sizeof(Bwd2Smem<NQ>) + 1024;
   const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // one CTA per SM, whatever runs beside it
@@ -404,9 +407,10 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
   // Cluster launch WITHOUT the cooperative attribute: at most 120 CTAs (30 clusters of 4, one CTA per SM by shared memory and
   // TMEM) always fit the 132 cluster-schedulable SMs, so every CTA is co-resident without the co-residency check -- and
   // Nsight Compute rejects the cooperative + cluster combination (round 1: the driver's ncu pass over smoke() died here).
-  const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQBwd, NQ);
-  for (int64_t r0 = 0; r0 < B; r0 += pw) {
-    const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
+  const int64_t seg_end = seg_words > 0 ? seg0 + seg_words : B;
+  const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(seg_end - seg0, kMaxQBwd, NQ);
+  for (int64_t r0 = seg0; r0 < seg_end; r0 += pw) {
+    const int Bv = (int)((seg_end - r0 < pw) ? (seg_end - r0) : pw);
     const int ng = (int)((Bv + gw - 1) / gw);
     // (the status word in the header is sticky: it starts at zero and is never cleared by a launch)
     PAULE_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(xchg) + kXchgHeader, 0x40, (size_t)ng * 2 * 4 * NQ * kLLBlockBytes, s));
@@ -442,23 +446,59 @@ int bwd2_ctas(int64_t B, int nq) {
   return groups <= kMaxQBwd ? (int)groups * kBwd2Groups * 4 : 0;
 }
 int bwd2_default_nq(int64_t B) { return choose_nq(B, kMaxQBwd); }
+int bwd2_passes(int64_t B) {
+  static const bool balanced = getenv("PAULE_RNN_BALANCED") != nullptr || getenv("PAULE_RNN_NQ") != nullptr;
+  const int64_t cap = (int64_t)kMaxQBwd * kWq * 4;
+  PassPlan pp;
+  if (B > cap && !balanced && plan_passes(B, kMaxQBwd, kBwdStepUs, &pp)) return pp.n;
+  return (int)((B + cap - 1) / cap);
+}
+
+static int bwd2_segment(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                        void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int nq,
+                        int64_t seg0, int64_t seg_words);
 
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int force_nq) {
+  // more words than one launch holds: cut into passes by summed step time (tc_lstm.cuh, plan_passes); PAULE_RNN_BALANCED=1 or a
+  // forced layout keeps the balanced passes of one layout
+  static const bool balanced = getenv("PAULE_RNN_BALANCED") != nullptr || getenv("PAULE_RNN_NQ") != nullptr;
+  if (force_nq <= 0 && !balanced && B > (int64_t)kMaxQBwd * kWq * 4) {
+    PassPlan pp;
+    if (plan_passes(B, kMaxQBwd, kBwdStepUs, &pp)) {
+      int64_t r0 = 0;
+      for (int i = 0; i < pp.n; ++i) {
+        const int rc = bwd2_segment(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf, pp.nq[i], r0,
+                                    pp.words[i]);
+        if (rc != PAULE_OK) return rc;
+        r0 += pp.words[i];
+      }
+      return PAULE_OK;
+    }
+  }
   // two quarters per CTA: two epilogue groups, one quarter each (4.57 -> 3.62 us per step at 128 words).  With three or four
   // quarters a second group measured 4-6 % SLOWER (contiguous halves; 20 % slower interleaved) and is not used.
   // PAULE_RNN_EG=1 restores one group everywhere (A/B timing).
-  static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
   int nq = choose_nq(B, kMaxQBwd);
   if (force_nq > 0) {   // layer wavefront: BPTT kernels that run side by side must be the SAME instantiation (see plan_step.cu)
     if (bwd2_ctas(B, force_nq) == 0) return PAULE_ERR_ARG;
     nq = force_nq;
   }
-  if (nq == 1) return launch_bwd2<1, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
-  if (nq == 2 && !one_group) return launch_bwd2<2, 2>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
-  if (nq == 2) return launch_bwd2<2, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
-  if (nq == 3) return launch_bwd2<3, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
-  return launch_bwd2<4, 1>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf);
+  return bwd2_segment(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf, nq, 0, 0);
+}
+
+static int bwd2_segment(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
+                        void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int nq,
+                        int64_t seg0, int64_t seg_words) {
+  static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
+#define PAULE_BWD_CASE(NQ_, EG_) \
+  return launch_bwd2<NQ_, EG_>(gates, c, packed, dh_seq, dh_mode, dh_last, xchg, da_img_seq, T, B, keep_da, s, wf, seg0, seg_words)
+  if (nq == 1) PAULE_BWD_CASE(1, 1);
+  if (nq == 2 && !one_group) PAULE_BWD_CASE(2, 2);
+  if (nq == 2) PAULE_BWD_CASE(2, 1);
+  if (nq == 3) PAULE_BWD_CASE(3, 1);
+  PAULE_BWD_CASE(4, 1);
+#undef PAULE_BWD_CASE
 }
 
 }  // namespace tc

@@ -504,9 +504,11 @@ int pack_v2(const float* w_ih, const float* w_hh, int64_t I, uint8_t* packed, cu
   return PAULE_OK;
 }
 
+// B = words of the whole batch (row stride of the time-major tensors); the launch covers words [seg0, seg0 + seg_words)
+// (seg_words = 0: all of them), in balanced passes of this layout when they exceed one launch
 template <int NS, int QS, bool FUSED, int EG>
 int launch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf) {
+                void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int64_t seg0 = 0, int64_t seg_words = 0) {
   static unsigned long long attr_set = 0ull;
   constexpr int NQ = NS * QS;
   const int smem_own = (int)sizeof(Fwd2Smem<NS, QS>) + 1024;
@@ -514,10 +516,11 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
   if (once_per_device(attr_set)) {
     PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_fwd2_kernel<NS, QS, FUSED, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(B, kMaxQ, NQ);
+  const int64_t seg_end = seg_words > 0 ? seg0 + seg_words : B;
+  const int64_t gw = (int64_t)kWq * NQ, pw = pass_words(seg_end - seg0, kMaxQ, NQ);
   // words are independent: batches larger than one launch run as consecutive, balanced passes
-  for (int64_t r0 = 0; r0 < B; r0 += pw) {
-    const int Bv = (int)((B - r0 < pw) ? (B - r0) : pw);
+  for (int64_t r0 = seg0; r0 < seg_end; r0 += pw) {
+    const int Bv = (int)((seg_end - r0 < pw) ? (seg_end - r0) : pw);
     const int ng = (int)((Bv + gw - 1) / gw);
     // exchange blocks of this pass start with the phase bit set (0x4040 per value): never a valid first step.  The status
     // word in the header is NOT cleared here: it starts at zero (zero-filled scratch) and stays set once a watchdog fired.
@@ -554,12 +557,28 @@ int launch_fwd2(float* gates, const void* packed, const float* bias, const void*
 // on lines that are being written slow every exchange -- 3.35 -> 4.52 us at 128 words, 5.7 -> 11.5 us at 384.
 template <bool FUSED>
 int dispatch_fwd2(float* gates, const void* packed, const float* bias, const void* x_img, float* h, float* c, void* xchg,
-                  void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int nq_min) {
+                  void* h_img_seq, int64_t T, int64_t B, cudaStream_t s, WaveFlags wf, int nq_min, int64_t seg0 = 0,
+                  int64_t seg_words = 0) {
   static const bool one_group = getenv("PAULE_RNN_EG") != nullptr && atoi(getenv("PAULE_RNN_EG")) == 1;
   // PAULE_FWD_LAYOUT=<NS><QS><EG> (e.g. 222) forces a layout (A/B timing, tools/ab_groups.sh)
   static const int forced = getenv("PAULE_FWD_LAYOUT") ? atoi(getenv("PAULE_FWD_LAYOUT")) : 0;
 #define PAULE_FWD_CASE(NS_, QS_, EG_) \
-  return launch_fwd2<NS_, QS_, FUSED, EG_>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s, wf)
+  return launch_fwd2<NS_, QS_, FUSED, EG_>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s, wf, seg0, seg_words)
+  // more words than one launch holds: cut into passes by summed step time (tc_lstm.cuh, plan_passes); PAULE_RNN_BALANCED=1 or a
+  // forced layout keeps the balanced passes of one layout
+  static const bool balanced = getenv("PAULE_RNN_BALANCED") != nullptr || getenv("PAULE_RNN_NQ") != nullptr;
+  if (seg_words == 0 && nq_min <= 1 && forced == 0 && !balanced && B > (int64_t)kMaxQ * kWq * 4) {
+    PassPlan pp;
+    if (plan_passes(B, kMaxQ, kFwdStepUs, &pp)) {
+      int64_t r0 = 0;
+      for (int i = 0; i < pp.n; ++i) {
+        const int rc = dispatch_fwd2<FUSED>(gates, packed, bias, x_img, h, c, xchg, h_img_seq, T, B, s, wf, pp.nq[i], r0, pp.words[i]);
+        if (rc != PAULE_OK) return rc;
+        r0 += pp.words[i];
+      }
+      return PAULE_OK;
+    }
+  }
   switch (nq_min > 1 ? 0 : forced) {
     case 111: PAULE_FWD_CASE(1, 1, 1);
     case 211: PAULE_FWD_CASE(2, 1, 1);
@@ -569,7 +588,8 @@ int dispatch_fwd2(float* gates, const void* packed, const float* bias, const voi
     case 222: PAULE_FWD_CASE(2, 2, 2);
     default: break;
   }
-  int nq = choose_nq(B, kMaxQ);
+  int nq = choose_nq(seg_words > 0 ? seg_words : B, kMaxQ);
+  if (seg_words > 0) nq = nq_min;    // a pass of the plan: its layout was chosen there
   if (nq < nq_min) nq = nq_min;      // a co-resident kernel (layer wavefront) leaves this one fewer SMs: more quarters per CTA
   if (nq == 1) PAULE_FWD_CASE(1, 1, 1);
   if (one_group) {
@@ -591,6 +611,15 @@ static int nq_for(int64_t B, int max_ctas) {
     if (groups <= kMaxQ && (max_ctas <= 0 || groups * kFwd2Groups <= max_ctas)) return nq;
   }
   return 0;
+}
+
+int fwd2_passes(int64_t B) {
+  static const bool balanced = getenv("PAULE_RNN_BALANCED") != nullptr || getenv("PAULE_RNN_NQ") != nullptr ||
+                               getenv("PAULE_FWD_LAYOUT") != nullptr;
+  const int64_t cap = (int64_t)kMaxQ * kWq * 4;
+  PassPlan pp;
+  if (B > cap && !balanced && plan_passes(B, kMaxQ, kFwdStepUs, &pp)) return pp.n;
+  return (int)((B + cap - 1) / cap);
 }
 
 int fwd2_ctas(int64_t B, int max_ctas) {

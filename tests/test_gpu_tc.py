@@ -27,7 +27,8 @@ def _status(xchg):
     return int(xchg[2048:2052].view(torch.int32).item())    # kXchgErrOff: watchdog flag of the persistent kernels
 
 
-@pytest.mark.parametrize("B,T", [(64, 24), (1, 9), (37, 16), (100, 12), (130, 7), (300, 6), (450, 5)])
+# (450, 5), (1000, 4): more words than one launch holds -- passes of different layouts (tc_lstm.cuh, plan_passes)
+@pytest.mark.parametrize("B,T", [(64, 24), (1, 9), (37, 16), (100, 12), (130, 7), (300, 6), (450, 5), (1000, 4)])
 def test_tc_forward_and_backward_match_fp32_kernels(setup, B, T):
     from paule_b200 import _lib, ops
     dev, lib, w = setup
@@ -95,7 +96,7 @@ def test_tc_is_repeatable(setup):
         assert (d > 5e-5).float().mean().item() < 1e-2
 
 
-@pytest.mark.parametrize("B,T", [(64, 10), (37, 7), (100, 5)])
+@pytest.mark.parametrize("B,T", [(64, 10), (37, 7), (100, 5), (500, 4)])   # 500: image groups that straddle two passes
 def test_tc_gemm_over_image_sequences(setup, B, T):
     """paule_tc_gemm_img on the bf16 images a persistent kernel left behind == fp32 GEMM on the fp32 tensors
     (K = 720 input projection with bias; K = 2880 dX with N = 720 / 60 / 30, overwrite and accumulate)."""
