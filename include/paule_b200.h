@@ -203,6 +203,11 @@ PAULE_API int paule_tc_gemm_img(const void* a_img, const void* packed_b, const f
  *               paule_tc_gemm_img) instead of ping-ponging inside xchg. */
 PAULE_API size_t paule_tc_rnn_xchg_bytes(int64_t B);
 PAULE_API size_t paule_tc_img_seq_bytes(int64_t T, int64_t B, int64_t images_per_step);
+/* How paule_tc_lstm_seq_fwd* (backward = 0) / paule_tc_lstm_seq_bwd* (backward = 1) cut a batch of B words into launches: pass i
+ * covers words_out[i] consecutive words with nq_out[i] word quarters (16 words) per CTA.  One pass up to 384 / 320 words;
+ * beyond that the passes minimise the summed per-step time of the layouts (host-side only, no device work).  Returns the
+ * number of passes (<= cap entries are written), or -1 on bad arguments. */
+PAULE_API int paule_tc_rnn_pass_plan(int64_t B, int backward, int32_t* nq_out, int32_t* words_out, int cap);
 PAULE_API int paule_tc_lstm_seq_fwd(float* gates, const void* packed, float* h, float* c, void* xchg, void* h_img_seq,
                           int64_t T, int64_t B, int math, paule_stream_t stream);
 /* Fused input projection (layers whose input size is <= 64: the ForwardModel LSTM fed by the cps, embedder layer 0 fed by the

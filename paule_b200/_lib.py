@@ -68,6 +68,7 @@ SIGNATURES = {
     "paule_tc_gemm_pack": (C.c_int, [vp, vp, i64, i64, vp]),
     "paule_tc_gemm_img": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, C.c_int, vp]),
     "paule_tc_rnn_xchg_bytes": (sz, [i64]),
+    "paule_tc_rnn_pass_plan": (i32, [i64, i32, vp, vp, i32]),
     "paule_tc_img_seq_bytes": (sz, [i64, i64, i64]),
     "paule_tc_lstm_seq_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]),
     "paule_tc_x_image_bytes": (sz, [i64, i64]),

@@ -333,6 +333,9 @@ int fwd2_ctas(int64_t B, int max_ctas);
 // launches of one recurrent layer over B words (the pass plan above; 1 up to 384 / 320 words)
 int fwd2_passes(int64_t B);
 int bwd2_passes(int64_t B);
+// the passes themselves (at most cap entries written; returns their number)
+int fwd2_pass_plan(int64_t B, int32_t* nq_out, int32_t* words_out, int cap);
+int bwd2_pass_plan(int64_t B, int32_t* nq_out, int32_t* words_out, int cap);
 // batched tcgen05 GEMM over image sequences (tc_gemm.cu): batch mode with a status word, streaming mode for the wavefront
 int gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
              int64_t nseg, int accumulate, int* status, cudaStream_t s);

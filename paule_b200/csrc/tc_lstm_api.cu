@@ -23,6 +23,11 @@ extern "C" int paule_tc_pack_lstm(const float* w_ih, const float* w_hh, void* pa
   return pack_v2(w_ih, w_hh, I, img, as_stream(stream));
 }
 
+extern "C" int paule_tc_rnn_pass_plan(int64_t B, int backward, int32_t* nq_out, int32_t* words_out, int cap) {
+  if (B <= 0 || cap < 0 || (cap > 0 && (!nq_out || !words_out))) return -1;
+  return backward ? paule::tc::bwd2_pass_plan(B, nq_out, words_out, cap) : paule::tc::fwd2_pass_plan(B, nq_out, words_out, cap);
+}
+
 extern "C" size_t paule_tc_rnn_xchg_bytes(int64_t B) {
   (void)B;
   return (size_t)kXchgHeader + kLLBytes;   // header (status word, trace words) + the exchange blocks of one launch

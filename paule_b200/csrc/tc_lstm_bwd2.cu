@@ -446,13 +446,20 @@ int bwd2_ctas(int64_t B, int nq) {
   return groups <= kMaxQBwd ? (int)groups * kBwd2Groups * 4 : 0;
 }
 int bwd2_default_nq(int64_t B) { return choose_nq(B, kMaxQBwd); }
-int bwd2_passes(int64_t B) {
+int bwd2_pass_plan(int64_t B, int32_t* nq_out, int32_t* words_out, int cap_out) {
   static const bool balanced = getenv("PAULE_RNN_BALANCED") != nullptr || getenv("PAULE_RNN_NQ") != nullptr;
   const int64_t cap = (int64_t)kMaxQBwd * kWq * 4;
   PassPlan pp;
-  if (B > cap && !balanced && plan_passes(B, kMaxQBwd, kBwdStepUs, &pp)) return pp.n;
-  return (int)((B + cap - 1) / cap);
+  if (!(B > cap && !balanced && plan_passes(B, kMaxQBwd, kBwdStepUs, &pp))) {   // one layout, balanced passes
+    const int nq = choose_nq(B, kMaxQBwd);
+    const int64_t pw = pass_words(B, kMaxQBwd, nq);
+    pp.n = 0;
+    for (int64_t r0 = 0; r0 < B && pp.n < 96; r0 += pw) { pp.nq[pp.n] = nq; pp.words[pp.n] = (int)(B - r0 < pw ? B - r0 : pw); ++pp.n; }
+  }
+  for (int i = 0; i < pp.n && i < cap_out; ++i) { nq_out[i] = pp.nq[i]; words_out[i] = pp.words[i]; }
+  return pp.n;
 }
+int bwd2_passes(int64_t B) { return bwd2_pass_plan(B, nullptr, nullptr, 0); }
 
 static int bwd2_segment(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                         void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int nq,

@@ -613,14 +613,21 @@ static int nq_for(int64_t B, int max_ctas) {
   return 0;
 }
 
-int fwd2_passes(int64_t B) {
+int fwd2_pass_plan(int64_t B, int32_t* nq_out, int32_t* words_out, int cap_out) {
   static const bool balanced = getenv("PAULE_RNN_BALANCED") != nullptr || getenv("PAULE_RNN_NQ") != nullptr ||
                                getenv("PAULE_FWD_LAYOUT") != nullptr;
   const int64_t cap = (int64_t)kMaxQ * kWq * 4;
   PassPlan pp;
-  if (B > cap && !balanced && plan_passes(B, kMaxQ, kFwdStepUs, &pp)) return pp.n;
-  return (int)((B + cap - 1) / cap);
+  if (!(B > cap && !balanced && plan_passes(B, kMaxQ, kFwdStepUs, &pp))) {   // one layout, balanced passes
+    const int nq = choose_nq(B, kMaxQ);
+    const int64_t pw = pass_words(B, kMaxQ, nq);
+    pp.n = 0;
+    for (int64_t r0 = 0; r0 < B && pp.n < 96; r0 += pw) { pp.nq[pp.n] = nq; pp.words[pp.n] = (int)(B - r0 < pw ? B - r0 : pw); ++pp.n; }
+  }
+  for (int i = 0; i < pp.n && i < cap_out; ++i) { nq_out[i] = pp.nq[i]; words_out[i] = pp.words[i]; }
+  return pp.n;
 }
+int fwd2_passes(int64_t B) { return fwd2_pass_plan(B, nullptr, nullptr, 0); }
 
 int fwd2_ctas(int64_t B, int max_ctas) {
   const int nq = nq_for(B, max_ctas);

@@ -66,3 +66,31 @@ def test_error_strings_and_no_device_is_loud():
         assert lib.paule_device_check() == 4
         with pytest.raises(_lib.PauleB200Error):
             _lib.require_device()
+
+
+@pytest.mark.parametrize("backward", [0, 1])
+def test_pass_plan_of_the_recurrent_kernels(backward):
+    """paule_tc_rnn_pass_plan (host-side only): the passes cover every word exactly once, respect the launch capacity of their
+    layout (6 / 5 word groups of 16 nq words) and never cost more summed step time than balanced passes of one layout."""
+    from paule_b200 import _lib
+    lib = _lib.load()
+    groups = 5 if backward else 6
+    cost = ([0, 3.00, 3.81, 5.34, 7.10] if backward else [0, 2.23, 3.64, 4.71, 5.79])
+    nq, words = (ctypes.c_int32 * 96)(), (ctypes.c_int32 * 96)()
+    assert lib.paule_tc_rnn_pass_plan(0, backward, nq, words, 96) == -1
+    for B in (1, 16, 64, 96, 97, 256, 320, 321, 384, 385, 400, 512, 1000, 1024, 2048, 5000):
+        n = lib.paule_tc_rnn_pass_plan(B, backward, nq, words, 96)
+        assert 1 <= n <= 96
+        assert sum(words[i] for i in range(n)) == B
+        for i in range(n):
+            assert 1 <= nq[i] <= 4 and 0 < words[i] <= groups * 16 * nq[i]
+            if i + 1 < n:
+                assert words[i] % 16 == 0, "only the last pass may end inside a word quarter"
+        if B <= groups * 64:
+            assert n == 1, "one launch whenever the batch fits one"
+        else:
+            full = groups * 64                       # balanced passes of the four-quarter layout (round 1's schedule)
+            n_bal = -(-B // full)
+            per = -(-B // n_bal)
+            nq_bal = min(4, -(-per // (groups * 16)))
+            assert sum(cost[nq[i]] for i in range(n)) <= n_bal * cost[nq_bal] + 1e-6
