@@ -191,6 +191,15 @@ PAULE_API size_t paule_tc_gemm_packed_bytes(int64_t N, int64_t nseg);
 PAULE_API int paule_tc_gemm_pack(const float* W, void* packed, int64_t N, int64_t nseg, paule_stream_t stream);
 PAULE_API int paule_tc_gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C,
                       int64_t steps, int64_t B, int64_t N, int64_t nseg, int accumulate, paule_stream_t stream);
+/* Narrow-K variant (K <= 64: one k-block): C [steps,B,N] (+)= X W^T + bias with X [steps,B,K] fp32 converted to bf16 operand
+ * images first.  Replaces the FFMA post_linear^T of the backward pass (dh = dmel W_post, K = 60, N = 720: 17.7 GFLOP at 1024
+ * words x 200 mel frames) by the tcgen05 GEMM; `img` >= paule_tc_a_image_bytes(steps, B) bytes, ZERO-FILLED once by the owner. */
+PAULE_API size_t paule_tc_gemm_packed_bytes_k64(int64_t N);
+PAULE_API int paule_tc_gemm_pack_k64(const float* W /* [N,K] */, void* packed, int64_t N, int64_t K, paule_stream_t stream);
+PAULE_API size_t paule_tc_a_image_bytes(int64_t steps, int64_t B);
+PAULE_API int paule_tc_a_image(const float* x, void* img, int64_t steps, int64_t B, int64_t I, paule_stream_t stream);
+PAULE_API int paule_tc_gemm_img_k64(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps,
+                          int64_t B, int64_t N, int accumulate, paule_stream_t stream);
 
 /* Persistent-RNN forward / backward of one H=720 layer: W_hh slices stay resident in shared memory
  * for the whole sequence, one cooperative launch per layer and 64-word group, grid barrier per time step.
@@ -303,6 +312,9 @@ typedef struct paule_plan {
      post_linear.weight^T x EmbeddingModel.lstm.weight_ih_l0^T, with (N = H, nseg = 4): embedder layer 0's dA goes to
      d/d(pooled forward-model h) in ONE streaming GEMM while both BPTT kernels run.  NULL: serial backward. */
   const void* bwd_fused_packed;
+  /* tensor-core math: paule_tc_gemm_pack_k64 of post_linear.weight^T ([H, Cm], N = H, K = Cm <= 64) -- the serial backward then
+     computes d/d(pooled forward-model h) = dmel W_post on the tcgen05 GEMM instead of the FFMA kernel.  NULL: FFMA. */
+  const void* post_t_packed;
 } paule_plan;
 
 PAULE_API size_t paule_plan_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t C, int64_t Cm, int64_t S, int math);

@@ -39,6 +39,7 @@ class Plan(C.Structure):
         ("word_frames", vp),
         ("cls_w", vp), ("cls_b", vp), ("extra_terms", vp), ("extra_grad", vp), ("aux_log", vp),
         ("bwd_fused_packed", vp),
+        ("post_t_packed", vp),
     ]
 
 
@@ -67,6 +68,11 @@ SIGNATURES = {
     "paule_tc_gemm_packed_bytes": (sz, [i64, i64]),
     "paule_tc_gemm_pack": (C.c_int, [vp, vp, i64, i64, vp]),
     "paule_tc_gemm_img": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, C.c_int, vp]),
+    "paule_tc_gemm_packed_bytes_k64": (sz, [i64]),
+    "paule_tc_gemm_pack_k64": (C.c_int, [vp, vp, i64, i64, vp]),
+    "paule_tc_a_image_bytes": (sz, [i64, i64]),
+    "paule_tc_a_image": (C.c_int, [vp, vp, i64, i64, i64, vp]),
+    "paule_tc_gemm_img_k64": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, C.c_int, vp]),
     "paule_tc_rnn_xchg_bytes": (sz, [i64]),
     "paule_tc_rnn_pass_plan": (i32, [i64, i32, vp, vp, i32]),
     "paule_tc_img_seq_bytes": (sz, [i64, i64, i64]),

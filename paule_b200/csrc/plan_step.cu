@@ -36,6 +36,7 @@ struct Workspace {
   // the co-resident recurrence and the per-step arrival counters
   void *xchg2, *xchg3;
   void *da_img_0, *da_img_1;              // dA images of the embedder layers when the three BPTT kernels run concurrently
+  void *dmel_img;                         // d(loss)/d(pred_mel) as bf16 A images of the narrow-K post_linear^T GEMM
   // arrival counters [word group][step or pair of steps] of every hand-over, one contiguous block (zeroed once per step)
   unsigned int *wf_flags;                 // start of the block
   size_t wf_flag_count;
@@ -93,6 +94,7 @@ Workspace carve(void* base, int64_t B, int64_t T, int64_t H, int64_t C, int64_t 
     }
     w.wf_target = reinterpret_cast<unsigned int*>(take(G));
     w.wf_target_b = reinterpret_cast<unsigned int*>(take(G));
+    w.dmel_img = Cm <= 64 ? take_bytes(paule_tc_a_image_bytes(Tm, B)) : nullptr;
   }
   w.floats = off;
   return w;
@@ -120,6 +122,7 @@ int check_plan(const paule_plan* p) {
 }
 
 inline bool use_tc(const paule_plan* p) { return p->math != PAULE_MATH_FP32; }
+inline bool Cm_small(const paule_plan* p) { return p->Cm <= 64; }
 
 // recurrence of one layer on time-major data; gates already holds x W_ih^T + b
 int recur_forward(const paule_plan* p, const paule_lstm_layer& L, int64_t steps, float* gates, float* h, float* c,
@@ -535,6 +538,7 @@ extern "C" int64_t paule_plan_step_launches(const paule_plan* p) {
   } else {
     if (use_sem) n += 1 + ragged + 2 * (bpass + 1);
     n += 1 + bpass + 1;
+    if (p->post_t_packed != nullptr && Cm_small(p)) n += 1;               // dmel -> operand images of the narrow-K GEMM
   }
   return n;
 }
@@ -583,7 +587,14 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
     PAULE_TRY(layer_backward(p, p->emb0, w.gates_0, w.c_0, w.dh0, 1, nullptr, Tm, w.dmel, 1, w, s));  // += d(mel loss)/dmel
   }
   // post_linear^T; the un-pooling (x0.5 to both frames of a pair) is folded into the BPTT's dh load
-  PAULE_TRY(paule_linear_f32(w.dmel, p->post_w_t, nullptr, w.dhp, Tm * B, H, Cm, 1, Cm, 0, 0, 1, H, 0, 0, s));
+  if (use_tc(p) && p->post_t_packed != nullptr && w.dmel_img != nullptr) {
+    // on tcgen05: dmel -> bf16 operand images (one k-block per step and 64 words), then the narrow-K batch GEMM (K = Cm <= 64)
+    // -- the FFMA kernel's 2 Tm B H Cm FLOP were 2 % of the step at 1024 words (0.71 ms of 35.6)
+    PAULE_TRY(paule_tc_a_image(w.dmel, w.dmel_img, Tm, B, Cm, s));
+    PAULE_TRY(tc::gemm_img_kb(w.dmel_img, p->post_t_packed, nullptr, w.dhp, Tm, B, H, 1, 0, status_of(w.xchg), as_stream(s)));
+  } else {
+    PAULE_TRY(paule_linear_f32(w.dmel, p->post_w_t, nullptr, w.dhp, Tm * B, H, Cm, 1, Cm, 0, 0, 1, H, 0, 0, s));
+  }
   PAULE_TRY(layer_backward(p, p->fwd, w.gates_f, w.c_f, w.dhp, 2, nullptr, T, w.dcp_lstm, 0, w, s));
   // optimizer.step() + clamp + smiling + past_cp (paule.py:1199-1211)
   PAULE_TRY(adam_clamp_logged(p->cp, w.dcp_lstm, w.dcp_smooth, p->adam_m, p->adam_v, p->step_count, p->lr, p->beta1,

@@ -49,17 +49,40 @@ __host__ __device__ inline int pick_bn(int n_pad) {
 }
 __host__ __device__ inline int pad_n(int n) { return (n + 15) / 16 * 16; }
 
-// W [N, nseg*720] fp32 row-major -> image [n_tile][kb (nseg*12)][BN rows][128 B], zero padded
-__global__ void pack_gemm_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int N, int nseg, int BN) {
-  const int KB = nseg * kNumKB;
+// W [N, nseg*seg_len] fp32 row-major -> image [n_tile][kb (nseg * seg_pad / 64)][BN rows][128 B], zero padded
+// (seg_len = 720, seg_pad = 768: the hidden-size segments; seg_len = K <= 64, seg_pad = 64: one k-block, the narrow-K GEMM)
+__global__ void pack_gemm_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int N, int nseg, int BN, int seg_len,
+                                   int seg_pad) {
+  const int KB = nseg * seg_pad / 64;
   const int nt = blockIdx.x;
   const size_t tile_bytes = (size_t)KB * BN * 128;
-  for (int e = threadIdx.x; e < BN * nseg * kSegPad; e += blockDim.x) {
-    const int r = e / (nseg * kSegPad), kp = e % (nseg * kSegPad);
-    const int seg = kp / kSegPad, ks = kp % kSegPad;
+  for (int e = threadIdx.x; e < BN * nseg * seg_pad; e += blockDim.x) {
+    const int r = e / (nseg * seg_pad), kp = e % (nseg * seg_pad);
+    const int seg = kp / seg_pad, ks = kp % seg_pad;
     const int n = nt * BN + r;
-    const float v = (n < N && ks < kSegLen) ? W[(size_t)n * (nseg * kSegLen) + seg * kSegLen + ks] : 0.f;
+    const float v = (n < N && ks < seg_len) ? W[(size_t)n * (nseg * seg_len) + seg * seg_len + ks] : 0.f;
     *reinterpret_cast<__nv_bfloat16*>(img + (size_t)nt * tile_bytes + umma_offset(BN, r, kp)) = __float2bfloat16_rn(v);
+  }
+}
+
+// x [steps, B, I <= 64] fp32 -> A operand images of a narrow-K GEMM: one k-block per (64-word group, step),
+// [grp][step][64 rows][128 B] bf16, SWIZZLE_128B, columns >= I zero.  A thread converts one 16-byte chunk (8 columns) of a row.
+__global__ void a_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int64_t steps, int64_t B, int I) {
+  const int64_t total = steps * B * 8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 7);
+    const int64_t tb = e >> 3, b = tb % B, t = tb / B;
+    const float* src = x + tb * I + 8 * c;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 8 * c + 2 * j;
+      const __nv_bfloat162 pr = __floats2bfloat162_rn(k < I ? __ldg(src + 2 * j) : 0.f, k + 1 < I ? __ldg(src + 2 * j + 1) : 0.f);
+      w[j] = *reinterpret_cast<const uint32_t*>(&pr);
+    }
+    const int row = (int)(b % kRows);
+    uint8_t* dst = img + ((size_t)(b / kRows) * (size_t)steps + (size_t)t) * (kRows * 128) + (size_t)row * 128 + ((c ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -507,9 +530,42 @@ extern "C" int paule_tc_gemm_pack(const float* W, void* packed, int64_t N, int64
   PAULE_REQUIRE(W && packed && N > 0 && nseg > 0 && nseg <= 4);
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0);
   const int np = pad_n((int)N), bn = pick_bn(np);
-  pack_gemm_b_kernel<<<np / bn, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed), (int)N, (int)nseg, bn);
+  pack_gemm_b_kernel<<<np / bn, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed), (int)N, (int)nseg, bn,
+                                                               kSegLen, kSegPad);
   PAULE_LAUNCH_CHECK("pack_gemm_b_kernel");
   return PAULE_OK;
+}
+
+// narrow-K GEMM (K <= 64, one k-block): weights W [N, K] and the fp32 -> image conversion of its A operand
+extern "C" size_t paule_tc_gemm_packed_bytes_k64(int64_t N) { return N <= 0 ? 0 : (size_t)pad_n((int)N) * 64 * 2; }
+extern "C" int paule_tc_gemm_pack_k64(const float* W, void* packed, int64_t N, int64_t K, paule_stream_t stream) {
+  PAULE_REQUIRE(W && packed && N > 0 && K > 0 && K <= 64);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0);
+  const int np = pad_n((int)N), bn = pick_bn(np);
+  pack_gemm_b_kernel<<<np / bn, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed), (int)N, 1, bn, (int)K, 64);
+  PAULE_LAUNCH_CHECK("pack_gemm_b_kernel");
+  return PAULE_OK;
+}
+extern "C" size_t paule_tc_a_image_bytes(int64_t steps, int64_t B) {
+  if (steps <= 0 || B <= 0) return 0;
+  return (size_t)((B + kRows - 1) / kRows) * (size_t)steps * (kRows * 128);
+}
+// x [steps, B, I <= 64] fp32 -> img (>= paule_tc_a_image_bytes, ZERO-FILLED once by the owner: rows of words >= B)
+extern "C" int paule_tc_a_image(const float* x, void* img, int64_t steps, int64_t B, int64_t I, paule_stream_t stream) {
+  PAULE_REQUIRE(x && img && steps >= 0 && B > 0 && I > 0 && I <= 64 && (I % 2) == 0);
+  PAULE_REQUIRE(reinterpret_cast<uintptr_t>(img) % 16 == 0);
+  const int64_t total = steps * B * 8;
+  if (total == 0) return PAULE_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  a_image_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint8_t*>(img), steps, B, (int)I);
+  PAULE_LAUNCH_CHECK("a_image_kernel");
+  return PAULE_OK;
+}
+// C [steps, B, N] (+)= A W^T + bias over the images of paule_tc_a_image and the weights of paule_tc_gemm_pack_k64
+extern "C" int paule_tc_gemm_img_k64(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps,
+                                     int64_t B, int64_t N, int accumulate, paule_stream_t stream) {
+  return paule::tc::gemm_img_kb(a_img, packed_b, bias, C, steps, B, N, 1, accumulate, nullptr, as_stream(stream));
 }
 
 namespace paule {
@@ -564,12 +620,19 @@ extern "C" int paule_tc_gemm_img(const void* a_img, const void* packed_b, const 
 // paule_tc_gemm_img with the caller's sticky status word: a timed-out TMA / MMA wait is recorded there (planner.check())
 int paule::tc::gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B,
                         int64_t N, int64_t nseg, int accumulate, int* status, cudaStream_t stream) {
-  PAULE_REQUIRE(a_img && packed_b && C && steps >= 0 && B > 0 && N > 0 && nseg > 0 && nseg <= 4);
+  PAULE_REQUIRE(nseg > 0 && nseg <= 4);
+  return gemm_img_kb(a_img, packed_b, bias, C, steps, B, N, (int)nseg * kNumKB, accumulate, status, stream);
+}
+
+// the batch GEMM with an explicit number of 64-wide k-blocks per row of A
+int paule::tc::gemm_img_kb(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B,
+                           int64_t N, int KB, int accumulate, int* status, cudaStream_t stream) {
+  PAULE_REQUIRE(a_img && packed_b && C && steps >= 0 && B > 0 && N > 0 && KB > 0 && KB <= 4 * kNumKB);
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(a_img) % 16 == 0 && reinterpret_cast<uintptr_t>(packed_b) % 16 == 0);
   PAULE_REQUIRE(reinterpret_cast<uintptr_t>(C) % 16 == 0);
   if (steps == 0) return PAULE_OK;
   PAULE_TRY(gemm_attrs());
-  const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
+  const int np = pad_n((int)N), bn = pick_bn(np);
   const int n_groups = (int)((B + kRows - 1) / kRows), n_pairs = (int)((steps + 1) / 2);
   const int64_t total = (int64_t)n_groups * n_pairs * (np / bn);
   // wide outputs: the CTA-pair kernel (PAULE_GEMM_2CTA=0: the single-CTA kernel, A/B timing)

@@ -339,6 +339,8 @@ int bwd2_pass_plan(int64_t B, int32_t* nq_out, int32_t* words_out, int cap);
 // batched tcgen05 GEMM over image sequences (tc_gemm.cu): batch mode with a status word, streaming mode for the wavefront
 int gemm_img(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
              int64_t nseg, int accumulate, int* status, cudaStream_t s);
+int gemm_img_kb(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N, int KB,
+                int accumulate, int* status, cudaStream_t s);
 int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
                     int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
                     unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s, int reverse = 0,

@@ -215,6 +215,14 @@ class BatchPlanner:
             self.bwd_fused_packed = torch.empty(lib.paule_tc_gemm_packed_bytes(wc.shape[0], 4), dtype=torch.uint8, device=wc.device)
             _lib.check(lib.paule_tc_gemm_pack(wc.data_ptr(), self.bwd_fused_packed.data_ptr(), wc.shape[0], 4, ops._stream()),
                        "paule_tc_gemm_pack")
+        self.post_t_packed = None
+        if self._tc and self.post_w_t.shape[1] <= 64 and self.post_w_t.shape[1] % 2 == 0:
+            # serial backward: d/d(pooled forward-model h) = dmel W_post on the tcgen05 GEMM (K = 60: one k-block)
+            lib = _lib.load()
+            n_h, k_m = self.post_w_t.shape
+            self.post_t_packed = torch.empty(lib.paule_tc_gemm_packed_bytes_k64(n_h), dtype=torch.uint8, device=self.post_w_t.device)
+            _lib.check(lib.paule_tc_gemm_pack_k64(self.post_w_t.data_ptr(), self.post_t_packed.data_ptr(), n_h, k_m, ops._stream()),
+                       "paule_tc_gemm_pack_k64")
         self.head_w, self.head_b = cols(e.linear_mapping.weight), _f32c(e.linear_mapping.bias)
         self.head_w_t = self.head_w.t().contiguous()
         if getattr(self, "_struct", None) is not None:
@@ -248,6 +256,7 @@ class BatchPlanner:
         s.extra_grad = None if self.soma is None else self.soma.extra_grad.data_ptr()
         s.aux_log = None if self.aux_log is None else self.aux_log.data_ptr()
         s.bwd_fused_packed = None if self.bwd_fused_packed is None else self.bwd_fused_packed.data_ptr()
+        s.post_t_packed = None if self.post_t_packed is None else self.post_t_packed.data_ptr()
         self._struct = s
 
     def struct_ref(self):

@@ -209,3 +209,29 @@ def test_narrow_models_run_zero_padded_on_the_tensor_core_kernels(setup, hidden,
     np.testing.assert_allclose(xg.grad.cpu().numpy(), xr.grad.numpy(), atol=3e-2 * scale)
     with pytest.raises(AssertionError):
         np.testing.assert_allclose(0 * xg.grad.cpu().numpy(), xr.grad.numpy(), atol=3e-2 * scale)
+
+
+@pytest.mark.parametrize("B,T,N,K", [(37, 7, 720, 60), (100, 5, 720, 60), (500, 4, 720, 60), (64, 6, 2880, 30), (16, 3, 60, 64)])
+def test_tc_gemm_narrow_k(setup, B, T, N, K):
+    """paule_tc_a_image + paule_tc_gemm_img_k64 (K <= 64: one k-block; post_linear^T of the serial backward) == fp32 GEMM, overwrite
+    and accumulate, with and without bias."""
+    from paule_b200 import _lib, ops
+    dev, lib, _ = setup
+    g = torch.Generator(device="cpu").manual_seed(B * 7 + T)
+    st = ops._stream()
+    x = torch.randn(T, B, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    img = torch.zeros(lib.paule_tc_a_image_bytes(T, B), dtype=torch.uint8, device=dev)
+    pk = torch.empty(lib.paule_tc_gemm_packed_bytes_k64(N), dtype=torch.uint8, device=dev)
+    _lib.check(lib.paule_tc_gemm_pack_k64(W.data_ptr(), pk.data_ptr(), N, K, st))
+    _lib.check(lib.paule_tc_a_image(x.data_ptr(), img.data_ptr(), T, B, K, st))
+    base = torch.randn(T, B, N, generator=g).to(dev)
+    o1, o2 = torch.full((T, B, N), float("nan"), device=dev), base.clone()
+    _lib.check(lib.paule_tc_gemm_img_k64(img.data_ptr(), pk.data_ptr(), bias.data_ptr(), o1.data_ptr(), T, B, N, 0, st))
+    _lib.check(lib.paule_tc_gemm_img_k64(img.data_ptr(), pk.data_ptr(), None, o2.data_ptr(), T, B, N, 1, st))
+    torch.cuda.synchronize()
+    ref = x.double() @ W.double().t()
+    scale = ref.abs().max().item()
+    np.testing.assert_allclose(o1.cpu().double().numpy(), (ref + bias.double()).cpu().numpy(), atol=1e-2 * scale)
+    np.testing.assert_allclose(o2.cpu().double().numpy(), (ref + base.double()).cpu().numpy(), atol=1e-2 * scale)
