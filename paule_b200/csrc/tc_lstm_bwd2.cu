@@ -87,7 +87,12 @@ __device__ __forceinline__ void cluster_sync_all2() {
 // EG: epilogue groups (see tc_lstm_fwd2.cu): with EG = 2 a second group of 8 warps owns the second half of the CTA's quarters
 // (contiguous halves, in the loaders' visiting order: an interleaved split delays quarter q's publication behind the MMAs of
 // quarter q + 2 and measured 20 % slower), so two quarters' reductions and cell adjoints run concurrently.
-template <int NQ, int EG>
+// QS: lock-step quarters as in the forward kernel (the NQ quarters form NQ / QS slots; a slot's QS quarters share ONE loader
+// visit, operand buffer and MMA of N = 16 QS, and epilogue group j owns quarter j of every slot).  Measured in round 2 for
+// <4, 2, 2> and <2, 2, 2>: SLOWER than independent quarters (8.09 against 6.37 us per step at 256 words, 4.86 against 3.59 at 128)
+// -- unlike the forward kernel, whose cell pass dominates a visit, here the reduction hop between the four gate CTAs does, and a
+// pair's two reductions queue behind one MMA.  Only QS = 1 is instantiated (and tested).
+template <int NQ, int EG, int QS = 1>
 __global__ void __launch_bounds__(b2_threads(EG), 1)
 tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, const uint8_t* __restrict__ packed,
                     const float* __restrict__ dh_seq, int dh_mode, const float* __restrict__ dh_last,
@@ -100,6 +105,12 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   constexpr int kEpiW = kB2EpiWarps * EG, kB2Threads = b2_threads(EG);
   static_assert(EG == 1 || EG == 2, "one or two epilogue groups");
   constexpr int kQPG = (NQ + EG - 1) / EG;             // quarters per epilogue group: group eg owns [eg kQPG, (eg + 1) kQPG)
+  static_assert(NQ % QS == 0 && (QS == 1 || QS == EG), "lock-step quarters: one epilogue group per quarter of a slot");
+  constexpr int NS = NQ / QS;                          // slots (independent recurrences as far as the loaders are concerned)
+  constexpr int kSW = kWq * QS;                        // words per slot (the MMA N)
+  constexpr bool kByQ = QS > 1;                        // group eg owns quarter eg of every slot
+  constexpr int kOwn = kByQ ? NS : kQPG;               // quarters per epilogue group
+  constexpr int kSlotBlk = QS * kLLBlockBytes;         // exchange block of one (slot, parity, gate): [12 kb][16 QS rows][128 B]
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int g = (int)cluster_ctarank_u32();                 // gate handled by this CTA's K slice
   const int cl = blockIdx.x >> 2;
@@ -109,8 +120,8 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 
   if (tid == 0) {
     for (int q = 0; q < NQ; ++q) {
-      mbar_init(&S.mma_done[q], kNumKB);
-      mbar_init(&S.acc_free[q], kB2EpiWarps);
+      mbar_init(&S.mma_done[q], kNumKB);                           // (indexed by slot: the first NS entries are used)
+      mbar_init(&S.acc_free[q], kB2EpiWarps * (kByQ ? EG : 1));
       mbar_init(&S.red_full[q], 1);
     }
     fence_mbar_init();
@@ -132,7 +143,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
   if (warp >= kEpiW) {
     // ===================== loader + MMA issuer of k-block kb =====================
     const int kb = warp - kEpiW;
-    const uint32_t idesc = make_idesc_bf16(kV2M, kWq);
+    const uint32_t idesc = make_idesc_bf16(kV2M, kSW);
     const uint32_t ta = tmem + (uint32_t)(kV2WCol + kb * 32);
     // probes: lane p < 16 watches cell warp p&7 (rows 2(p&7), 2(p&7)+1) of writer CTA p>>3 of the k-block's two
     const uint32_t probe_off = (uint32_t)(((lane & 7) * 2 * 64 + ((lane >> 3) & 1) * 32) * 2);
@@ -146,22 +157,26 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
     TRACE_DECL
     for (int it = 1; it < T; ++it) {
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int rows = min(kWq, Bv - (grp * NQ + q) * kWq);   // valid words of this quarter: only their rows travel
+      for (int q = 0; q < NS; ++q) {                              // q = slot (= quarter when QS == 1)
+        const int rows = min(kSW, Bv - (grp * NQ + q * QS) * kWq);   // valid words of this slot: only their rows travel
         if (rows <= 0) continue;
-        const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && ((lane & 7) * 2 < rows);
-        uint8_t* bdst = &S.b[q][(size_t)kb * kWq * 128];
+        // the probe sits in the last quarter of the slot that has this lane's row (the quarters of a slot are published concurrently)
+        const int prow = (lane & 7) * 2;
+        const int pq = prow < rows ? min(QS - 1, (rows - 1 - prow) / kWq) : 0;
+        const bool prober = lane < 16 && (kb < kNumKB - 1 || lane < 8) && (prow < rows);
+        uint8_t* bdst = &S.b[q * QS][(size_t)kb * kSW * 128];
         const uint64_t db = make_smem_desc_sw128(smem_u32(bdst));
-        const uint8_t* src = ll + (size_t)((q * 2 + ((it - 1) & 1)) * 4 + g) * kLLBlockBytes + (size_t)kb * (kWq * 128);
+        const uint8_t* src = ll + (size_t)((q * 2 + ((it - 1) & 1)) * 4 + g) * kSlotBlk + (size_t)kb * (kSW * 128);
+        const uint32_t poff = probe_off + (uint32_t)(pq * kWq * 64 * 2);
         if (kb == 3 && lane == 0) TL(1, q, it)   // loader: quarter visit starts
 #ifdef PAULE_TC_TRACE
         uint64_t ftr[2] = {0, 0};
-        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, ftr, bwd_backoff)) break;
+        if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(it - 1), lane, poff, prober, rows, err, ftr, bwd_backoff)) break;
         tr_acc[0] += ftr[0] - tr_last;   // until the probes pass
         tr_last = ftr[0];
         TRACE(1)
 #else
-        if (!xchg_fetch_kblock<1>(src, bdst, kb, phase_bits(it - 1), lane, probe_off, prober, rows, err, nullptr, bwd_backoff)) break;
+        if (!xchg_fetch_kblock<QS>(src, bdst, kb, phase_bits(it - 1), lane, poff, prober, rows, err, nullptr, bwd_backoff)) break;
 #endif
         fence_proxy_async_shared();
         __syncwarp();
@@ -171,7 +186,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         TRACE(2)
         if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + (uint32_t)(kV2AccCol + q * kWq), ta + 8 * k, db + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem + (uint32_t)(kV2AccCol + q * kSW), ta + 8 * k, db + 2 * k, idesc, 1u);
           umma_commit(&S.mma_done[q]);
         }
         __syncwarp();
@@ -198,20 +213,23 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
     const int a = lane & 15, w = (lane >> 4) + 2 * w8;
     const int j = ugb * kV2M + g * 32 + 2 * a;
     const bool jvalid = j < kH;
-    const size_t ll_off = ((size_t)((j >> 6) * kWq + w) * 64 + (size_t)(j & 63)) * 2;
+    // byte offset of this thread's unit pair inside a slot's exchange block, quarter 0 of the slot (+ 16 rows per quarter)
+    const size_t ll_off = ((size_t)((j >> 6) * kSW + w) * 64 + (size_t)(j & 63)) * 2;
+    auto own = [&](int q) { return kByQ ? (q % QS == eg) : (q / kQPG == eg); };
+    auto own_q = [&](int i) { return kByQ ? (i * QS + eg) : (eg * kQPG + i); };   // i-th quarter of this epilogue group
     const bool jpublish = j < kH + 16;   // k-block 11: units 704..735 are read, zeros beyond H
     float dc[NQ][2];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) dc[q][0] = dc[q][1] = 0.f;
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
-      if (q / kQPG == eg) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
+      if (own(q)) tmem_zero_x8(taddr + (uint32_t)(q * kWq));
     tmem_st_wait();
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0)
       for (int q = 0; q < NQ; ++q)
-        if (q / kQPG == eg) mbar_arrive(&S.acc_free[q]);
+        if (own(q)) mbar_arrive(&S.acc_free[q / QS]);
 
     TL_DECL(kTlLoaderEvents, kTlCellEvents)
     TRACE_DECL
@@ -270,7 +288,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         if (leader) mbar_arrive_expect_tx(&S.red_full[q], kRedBytes);   // arm this step's phase (count 1 + 8 KB of tx)
         TRACE(0)
         if (tl0) TL(10, q, it)   // epilogue: starts waiting for the accumulator
-        mbar_wait(&S.mma_done[q], (uint32_t)((it - 1) & 1), err);
+        mbar_wait(&S.mma_done[q / QS], (uint32_t)((it - 1) & 1), err);
         if (tl0) TL(11, q, it)   // epilogue: accumulator complete
         TRACE(1)
         tcgen05_fence_after();
@@ -284,7 +302,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         st_async_v4(red_dst + (uint32_t)(q * 4 * 32 * kRedStride * 4), p[0], p[1], p[2], p[3], bar_dst + (uint32_t)(q * 8));
         st_async_v4(red_dst + (uint32_t)(q * 4 * 32 * kRedStride * 4) + 16, p[4], p[5], p[6], p[7], bar_dst + (uint32_t)(q * 8));
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.acc_free[q]);
+        if (lane == 0) mbar_arrive(&S.acc_free[q / QS]);
         if (tl0) TL(14, q, it)   // epilogue: partial sums pushed
         TRACE(3)
       };
@@ -324,12 +342,12 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
         const int wp = grp * kGW + q * kWq + w;
         const bool wvalid = wp < Bv;
         if (t > 0 && jpublish && wvalid) {   // da_t into the four gate blocks of the exchange: critical path of the next step
-          uint8_t* dst = ll + (size_t)((q * 2 + (it & 1)) * 4) * kLLBlockBytes + ll_off;
+          uint8_t* dst = ll + (size_t)(((q / QS) * 2 + (it & 1)) * 4) * kSlotBlk + ll_off + (size_t)(q % QS) * (kWq * 64 * 2);
           const uint32_t ph = phase_bits(it);
-          xchg_store(dst + 0 * (size_t)kLLBlockBytes, xchg_clamped(d_i) | ph);
-          xchg_store(dst + 1 * (size_t)kLLBlockBytes, xchg_clamped(d_f) | ph);
-          xchg_store(dst + 2 * (size_t)kLLBlockBytes, xchg_clamped(d_g) | ph);
-          xchg_store(dst + 3 * (size_t)kLLBlockBytes, xchg_clamped(d_o) | ph);
+          xchg_store(dst + 0 * (size_t)kSlotBlk, xchg_clamped(d_i) | ph);
+          xchg_store(dst + 1 * (size_t)kSlotBlk, xchg_clamped(d_f) | ph);
+          xchg_store(dst + 2 * (size_t)kSlotBlk, xchg_clamped(d_g) | ph);
+          xchg_store(dst + 3 * (size_t)kSlotBlk, xchg_clamped(d_o) | ph);
           // off the critical path: a gradient beyond the +-1.5 exchange bound (or NaN / Inf) was clamped above -- record it
           // in the header's informational word (NOT the status word: the wait loops abort on that one) so that the caller learns
           // its results deviate
@@ -372,15 +390,21 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
       // first two quarters of the group are loaded here, quarter q + 2 right after quarter q has been finalised (register set
       // q & 1 is free again)
 #pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (q / kQPG == eg && q - eg * kQPG < 2) load_q(q, qbuf[q & 1]);
+      for (int i = 0; i < 2 && i < kOwn; ++i)
+        if (own_q(i) < NQ) load_q(own_q(i), qbuf[i & 1]);
 #pragma unroll
-      for (int st = 0; st <= NQ; ++st) {
-        const bool own_st = st < NQ && st / kQPG == eg;
-        if (own_st && it > 0 && (grp * NQ + st) * kWq < Bv) push_q(st);
-        if (st >= 1 && (st - 1) / kQPG == eg) {
-          if ((grp * NQ + st - 1) * kWq < Bv) finalize_q(st - 1, qbuf[(st - 1) & 1]);
-          if (st + 1 < NQ && (st + 1) / kQPG == eg) load_q(st + 1, qbuf[(st + 1) & 1]);
+      for (int i = 0; i <= kOwn; ++i) {
+        if (i < kOwn && own_q(i) < NQ && it > 0) {
+          if ((grp * NQ + own_q(i)) * kWq < Bv) {
+            push_q(own_q(i));
+          } else if (kByQ && (grp * NQ + (own_q(i) / QS) * QS) * kWq < Bv) {
+            // an empty quarter of a slot that holds words: the loaders still wait for this group's release of the accumulator
+            if (lane == 0) mbar_arrive(&S.acc_free[own_q(i) / QS]);
+          }
+        }
+        if (i >= 1 && own_q(i - 1) < NQ) {
+          if ((grp * NQ + own_q(i - 1)) * kWq < Bv) finalize_q(own_q(i - 1), qbuf[(i - 1) & 1]);
+          if (i + 1 < kOwn && own_q(i + 1) < NQ) load_q(own_q(i + 1), qbuf[(i + 1) & 1]);
         }
       }
     }
@@ -394,7 +418,7 @@ tc_lstm_bwd2_kernel(float* __restrict__ gates, const float* __restrict__ c_seq, 
 
 // B = words of the whole batch (row stride of the time-major tensors); the launch covers words [seg0, seg0 + seg_words)
 // (seg_words = 0: all of them), in balanced passes of this layout when they exceed one launch
-template <int NQ, int EG>
+template <int NQ, int EG, int QS = 1>
 int launch_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                 void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf, int64_t seg0 = 0,
                 int64_t seg_words = 0) {
@@ -402,7 +426,7 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
   const int smem_own = (int)sizeof(Bwd2Smem<NQ>) + 1024;
   const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // one CTA per SM, whatever runs beside it
   if (once_per_device(attr_set)) {
-    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PAULE_CUDA(cudaFuncSetAttribute(tc_lstm_bwd2_kernel<NQ, EG, QS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   // Cluster launch WITHOUT the cooperative attribute: at most 120 CTAs (30 clusters of 4, one CTA per SM by shared memory and
   // TMEM) always fit the 132 cluster-schedulable SMs, so every CTA is co-resident without the co-residency check -- and
@@ -433,7 +457,7 @@ int launch_bwd2(float* gates, const float* c, const void* packed, const float* d
     uint8_t* xc = reinterpret_cast<uint8_t*>(xchg);
     uint8_t* is = reinterpret_cast<uint8_t*>(da_img_seq);
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed) + kPackedBwd2Off;
-    PAULE_CUDA(cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
+    PAULE_CUDA(cudaLaunchKernelEx(&cfg, tc_lstm_bwd2_kernel<NQ, EG, QS>, gp, cp, pk, dsp, dh_mode, dlp, xc, is, (int)T, Bv, (int)B,
                                   (int)r0, keep_da, wf));
   }
   return PAULE_OK;
