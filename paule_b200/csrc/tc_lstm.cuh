@@ -158,7 +158,7 @@ inline bool plan_passes(int64_t B, int max_groups, const float* cost, PassPlan* 
 // measured us per step by quarters per CTA (tools/rnn_time.py, B200): forward (1,1) / (2,1) / (3,1) / (2,2), backward NQ = 1..4
 // at the layouts' full capacity (96 / 192 / 288 / 384 and 80 / 160 / 240 / 320 words)
 constexpr float kFwdStepUs[5] = {0.f, 2.23f, 3.64f, 4.71f, 5.79f};
-constexpr float kBwdStepUs[5] = {0.f, 3.00f, 3.81f, 5.34f, 7.10f};
+constexpr float kBwdStepUs[5] = {0.f, 2.87f, 3.67f, 5.00f, 6.45f};
 
 // Probe polling variants, measured at 64 words (forward step 2.42 us with the defaults): two probe loads in flight 2.75 us
 // (more polling traffic slows every exchange), a 40 / 120 ns back-off between failed probes 2.39 / 2.41 us (neutral).
