@@ -415,9 +415,10 @@ def test_watchdog_status_is_checked_when_results_are_read(dev, models):
 
 
 @pytest.mark.skipif(not _tc_available(), reason="tcgen05 path not built")
-@pytest.mark.parametrize("B,T,steps", [(64, 200, 300), (100, 60, 150), (1, 200, 200), (200, 40, 100)])
+@pytest.mark.parametrize("B,T,steps", [(64, 200, 300), (100, 60, 150), (1, 200, 200), (200, 40, 100), (450, 20, 60)])
 def test_soak_many_steps_no_watchdog_and_repeatable(dev, models, B, T, steps):
-    """Soak of the exchange protocol of the persistent kernels (latency layout, 2- and 3-quarter CTAs, multi-pass): hundreds
+    """Soak of the exchange protocol of the persistent kernels (latency layout, 2- and 3-quarter CTAs, a batch beyond one launch
+    cut into passes of different layouts) and of the CTA-pair GEMMs between them: hundreds
     of steps = 10^5 .. 10^6 inter-CTA exchanges per run; the watchdog word must stay clear, the loss finite and falling, and
     two runs of the same job must agree up to the bf16 rounding flips of the arrival-ordered accumulation."""
     from paule_b200 import BatchPlanner
