@@ -235,6 +235,7 @@ struct WavePlan {
   int fwd = 0;          // 0 serial, 1 forward model || post_linear || embedder l0, 2 + gate GEMM || embedder l1
   int f_ctas = 0;       // CTA limit of the forward-model recurrence (0: its latency-optimal layout)
   int e0_ctas = 0, e1_ctas = 0;
+  int m_par = 2, g1_ct = 1;   // CTAs per column tile of the streaming post_linear, column tiles per CTA of the streaming gate GEMM
   int bwd = 0;          // 0 serial, 2 BPTT l0 || dX GEMM || BPTT forward model (l1 before, alone), 3 all three BPTT kernels
   int b_nq = 0, g_par = 0;   // quarters per CTA of the co-resident BPTT kernels (one common layout), GEMM CTAs per column tile
 };
@@ -270,6 +271,25 @@ WavePlan plan_wavefront(const paule_plan* p, bool use_sem) {
         const int e = left > 0 ? tc::fwd2_ctas(B, left) : 0;
         const float t_three = (float)p->T * 2.2f + 110.f + (float)(p->T / 2) * 2.2f, t_five = (float)p->T * 3.25f + 40.f;
         if (e > 0 && t_five < t_three) { wp.fwd = 2; wp.f_ctas = n_f2; wp.e0_ctas = wp.e1_ctas = e; }
+      }
+      // (c) all five kernels with the forward model in its LATENCY layout: the gate GEMM on half as many CTAs (two column tiles
+      // each: 0.86 MB per pair of steps through one SM, 8.6 us against the 11.6 us an embedder step pair takes), the pooled
+      // post_linear on one, the embedder layers at four quarters per CTA -- at 64 words that is 92 + 1 + 23 + 9 + 23 = all 148
+      // SMs.  The embedder layers (T/2 steps at 5.79 us) then set the pace instead of the forward model at two quarters per CTA
+      // (T steps at 3.25 us).  No margin is needed for progress: kernels are launched in dependency order and none waits for a
+      // later one, so a kernel that does not fit starts late instead of dead-locking.  PAULE_WAVEFRONT_FULL=0 disables it.
+      static const bool full = getenv("PAULE_WAVEFRONT_FULL") == nullptr || atoi(getenv("PAULE_WAVEFRONT_FULL")) != 0;
+      if (full && fwd_max >= 2) {
+        const int n_m1 = tc::gemm_stream_ctas(B, p->Cm, 1), n_g1h = tc::gemm_stream_ctas(B, 4 * p->H, 1, 2);
+        const int left = (sm_count() - n_f - n_m1 - n_g1h) / 2;
+        const int e = left > 0 ? tc::fwd2_ctas(B, left) : 0;
+        if (e > 0 && n_g1h < n_g1) {
+          const int64_t quarters = (B + tc::kWq - 1) / tc::kWq;
+          const int nq_e = (int)((quarters * tc::kFwd2Groups + e - 1) / e);                     // quarters per CTA of the embedder layers
+          const float t_full = (float)(p->T / 2) * tc::kFwdStepUs[nq_e < 1 ? 1 : (nq_e > 4 ? 4 : nq_e)] + 40.f;
+          const float t_now = wp.fwd == 2 ? (float)p->T * 3.25f + 40.f : (float)p->T * 2.2f + 110.f + (float)(p->T / 2) * 2.2f;
+          if (t_full < t_now) { wp.fwd = 2; wp.f_ctas = 0; wp.e0_ctas = wp.e1_ctas = e; wp.m_par = 1; wp.g1_ct = 2; }
+        }
       }
     }
   }
@@ -326,7 +346,7 @@ int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& w
                                tc::WaveFlags{w.f_hf, nullptr, 0, 0u}, wp.f_ctas));
   // (2) pooled post_linear, streaming: pred_mel + operand blocks of embedder layer 0
   PAULE_TRY(tc::gemm_img_stream(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, w.f_hf, w.wf_target, 2, w.f_x0,
-                                w.x_img_0, 2, status_of(w.xchg), ss->s[0]));
+                                w.x_img_0, wp.m_par, status_of(w.xchg), ss->s[0]));
   // (3) embedder layer 0, fed step by step; announces its h images when layer 1 runs in the pipeline too
   PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_0, p->emb0.packed, p->emb0.bias, w.x_img_0, nullptr, w.c_0, w.xchg2, w.h_img, Tm, B,
                                ss->s[1], tc::WaveFlags{wp.fwd == 2 ? w.f_h0 : nullptr, w.f_x0, P, tc::gemm_stream_arrivals(Cm)},
@@ -334,7 +354,7 @@ int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& w
   if (wp.fwd == 2) {
     // (4) the gate GEMM over all time steps, streaming: Xp1 = h_0 W_ih1^T + b
     PAULE_TRY(tc::gemm_img_stream(w.h_img, p->emb1.packed_ih, p->emb1.bias, w.gates_1, Tm, B, 4 * H, 1, w.f_h0, w.wf_target, 1,
-                                  w.f_g1, nullptr, 1, status_of(w.xchg), ss->s[2]));
+                                  w.f_g1, nullptr, 1, status_of(w.xchg), ss->s[2], 0, 0, wp.g1_ct));
     // (5) embedder layer 1: its cell warps wait for the pre-activations of the step
     PAULE_TRY(tc::lstm_seq_fwd2(w.gates_1, p->emb1.packed, w.h_1, w.c_1, w.xchg3, nullptr, Tm, B, ss->s[3],
                                 tc::WaveFlags{nullptr, w.f_g1, P, tc::gemm_stream_arrivals(4 * H)}, wp.e1_ctas));

@@ -116,6 +116,7 @@ struct GemmStream {
   int* status;                     // sticky status word (watchdog), or nullptr
   int src_per_step;                // source steps per output step (2: pooled post_linear over frame pairs)
   int n_par;                       // CTAs that alternate over the step pairs of one (group, column tile)
+  int n_ct;                        // column tiles per CTA (1: one CTA per column tile; 2: half as many CTAs, each walks two tiles per pair)
   int reverse;                     // the producer runs backwards in time (BPTT): pairs from the last to the first
 };
 
@@ -137,12 +138,12 @@ tc_gemm_img_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict_
   const int n_pairs = (steps + 1) / 2;
   const int n_nt = pad_n(N) / BN;
   // tile walk: batch mode = all tiles strided over the grid; streaming = this CTA's (group, column tile), every n_par-th pair
-  const int total = STREAM ? (n_pairs - (int)(blockIdx.x % st.n_par) + st.n_par - 1) / st.n_par : n_groups * n_pairs * n_nt;
+  const int total = STREAM ? (n_pairs - (int)(blockIdx.x % st.n_par) + st.n_par - 1) / st.n_par * st.n_ct : n_groups * n_pairs * n_nt;
   const int tile_first = STREAM ? 0 : (int)blockIdx.x, tile_stride = STREAM ? 1 : (int)gridDim.x;
   auto coords = [&](int tile, int& nt, int& sp, int& grp) {
     if (STREAM) {
-      const int cta = (int)blockIdx.x / st.n_par;
-      nt = cta % n_nt; grp = cta / n_nt; sp = (int)(blockIdx.x % st.n_par) + tile * st.n_par;
+      const int cta = (int)blockIdx.x / st.n_par, n_col = n_nt / st.n_ct;   // CTAs per group that share the columns
+      nt = cta % n_col + (tile % st.n_ct) * n_col; grp = cta / n_col; sp = (int)(blockIdx.x % st.n_par) + (tile / st.n_ct) * st.n_par;
       if (st.reverse) sp = n_pairs - 1 - sp;
     } else {
       nt = tile % n_nt; const int rest = tile / n_nt; sp = rest % n_pairs; grp = rest / n_pairs;
@@ -581,9 +582,10 @@ static int gemm_attrs() {
   return PAULE_OK;
 }
 
-int gemm_stream_ctas(int64_t B, int64_t N, int n_par) {
+int gemm_stream_ctas(int64_t B, int64_t N, int n_par, int n_ct) {
   const int np = pad_n((int)N), bn = pick_bn(np);
-  return (int)((B + kRows - 1) / kRows) * (np / bn) * n_par;
+  if (n_ct < 1 || (np / bn) % n_ct != 0) n_ct = 1;
+  return (int)((B + kRows - 1) / kRows) * (np / bn / n_ct) * n_par;
 }
 // arrivals that complete one pair of output steps in dst_flags: one per epilogue warp and column tile
 unsigned int gemm_stream_arrivals(int64_t N) {
@@ -594,15 +596,17 @@ unsigned int gemm_stream_arrivals(int64_t N) {
 // the GEMM of paule_tc_gemm_img in streaming mode (see GemmStream); `status` may be NULL
 int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
                     int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
-                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s, int reverse, int accumulate) {
+                    unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s, int reverse, int accumulate,
+                    int n_ct) {
   PAULE_REQUIRE(a_img && packed_b && C && steps > 0 && B > 0 && N > 0 && nseg > 0 && nseg <= 4 && src_flags && src_target);
   PAULE_REQUIRE(n_par >= 1 && (x_out == nullptr || N <= kXK));
   PAULE_TRY(gemm_attrs());
   const int np = pad_n((int)N), bn = pick_bn(np), KB = (int)nseg * kNumKB;
   const int smem_own = kGemmStages * (16384 + bn * 128) + (int)sizeof(GemmBars) + 1024 + 16;
   const int smem = smem_own > kExclusiveSmemBytes ? smem_own : kExclusiveSmemBytes;   // never shares an SM (tensor memory)
-  GemmStream st{src_flags, src_target, dst_flags, reinterpret_cast<uint8_t*>(x_out), status, src_per_step, n_par, reverse};
-  tc_gemm_img_kernel<true><<<gemm_stream_ctas(B, N, n_par), kGemmThreads, (size_t)smem, s>>>(
+  if (n_ct < 1 || (np / bn) % n_ct != 0) n_ct = 1;
+  GemmStream st{src_flags, src_target, dst_flags, reinterpret_cast<uint8_t*>(x_out), status, src_per_step, n_par, n_ct, reverse};
+  tc_gemm_img_kernel<true><<<gemm_stream_ctas(B, N, n_par, n_ct), kGemmThreads, (size_t)smem, s>>>(
       reinterpret_cast<const uint8_t*>(a_img), reinterpret_cast<const uint8_t*>(packed_b), bias, C, (int)steps, (int)B, (int)N,
       KB, bn, accumulate, st);
   PAULE_LAUNCH_CHECK("tc_gemm_img_kernel<stream>");

@@ -344,8 +344,8 @@ int gemm_img_kb(const void* a_img, const void* packed_b, const float* bias, floa
 int gemm_img_stream(const void* a_img, const void* packed_b, const float* bias, float* C, int64_t steps, int64_t B, int64_t N,
                     int64_t nseg, const unsigned int* src_flags, const unsigned int* src_target, int src_per_step,
                     unsigned int* dst_flags, void* x_out, int n_par, int* status, cudaStream_t s, int reverse = 0,
-                    int accumulate = 0);
-int gemm_stream_ctas(int64_t B, int64_t N, int n_par);
+                    int accumulate = 0, int n_ct = 1);
+int gemm_stream_ctas(int64_t B, int64_t N, int n_par, int n_ct = 1);
 unsigned int gemm_stream_arrivals(int64_t N);
 int lstm_seq_bwd2(float* gates, const float* c, const void* packed, const float* dh_seq, int dh_mode, const float* dh_last,
                   void* xchg, void* da_img_seq, int64_t T, int64_t B, int keep_da, cudaStream_t s, WaveFlags wf = kNoWave,
