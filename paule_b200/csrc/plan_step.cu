@@ -382,12 +382,24 @@ int backward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& 
                             reinterpret_cast<paule_stream_t>(st));
   };
   if (wp.bwd == 2) {
-    // layer 1 first, alone, in its usual layout (96 of the 148 SMs at 64 words); its dX GEMM as a batch GEMM.  The mel part runs
-    // beside it on the SMs it leaves free.
-    PAULE_TRY(fork_streams(ss, s, 1));
-    PAULE_TRY(mel_part(ss->s[0]));
-    PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, stream));
-    PAULE_TRY(join_streams(ss, s, 1));
+    // layer 1 first, alone among the BPTT kernels, in its usual layout (96 of the 148 SMs at 64 words).  Beside it, on the SMs it
+    // leaves free: the mel part, and its own dX GEMM in streaming mode (dh0 = dA_1 W_ih1 follows the recurrence step by step and
+    // is complete a few microseconds after it instead of a batch GEMM later).  PAULE_WAVE_B1_BATCH=1: the batch GEMM (A/B timing).
+    static const bool b1_batch = getenv("PAULE_WAVE_B1_BATCH") != nullptr;
+    if (b1_batch) {
+      PAULE_TRY(fork_streams(ss, s, 1));
+      PAULE_TRY(mel_part(ss->s[0]));
+      PAULE_TRY(layer_backward(p, p->emb1, w.gates_1, w.c_1, nullptr, 0, w.dh1_last, Tm, w.dh0, 0, w, stream));
+      PAULE_TRY(join_streams(ss, s, 1));
+    } else {
+      PAULE_TRY(fork_streams(ss, s, 2));
+      PAULE_TRY(tc::lstm_seq_bwd2(w.gates_1, w.c_1, p->emb1.packed, nullptr, 0, w.dh1_last, w.xchg, w.da_img_1, Tm, B, 0, s,
+                                  tc::WaveFlags{w.f_da1, nullptr, 0, 0u}, 0));
+      PAULE_TRY(tc::gemm_img_stream(w.da_img_1, p->emb1.packed_ih_t, nullptr, w.dh0, Tm, B, H, 4, w.f_da1, w.wf_target_b, 1, w.f_dh0,
+                                    nullptr, 4, status_of(w.xchg), ss->s[1], 1, 0));
+      PAULE_TRY(mel_part(ss->s[0]));
+      PAULE_TRY(join_streams(ss, s, 2));
+    }
   } else {
     PAULE_TRY(mel_part(s));
   }
