@@ -450,6 +450,13 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             *reinterpret_cast<uint32_t*>(img_seq + ((size_t)(wg / kRows) * (size_t)T + t) * kXchgImageBytes +
                                          umma_offset(kRows, wg % kRows, u & ~1)) = payload;
           }
+          if (wf.img_flags != nullptr && wq < Bv) {
+            // layer wavefront: this warp's image stores of step t are out -- one release-arrival per (step, quarter, warp).
+            // BEFORE the stash stores: the release orders everything the warp wrote so far, and the consumer (a streaming GEMM)
+            // only reads the images; behind the stash stores it cost the pace-setting layer of a pipeline ~0.3 us per step.
+            __syncwarp();
+            if (lane == 0) red_release_add_u32(wf.img_flags + (size_t)((w0 + wq) / kRows) * (size_t)T + t, 1u);
+          }
 #ifndef PAULE_EXPERIMENT_NO_STASH   // timing experiment only (results are then useless to the backward pass)
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -466,11 +473,6 @@ tc_lstm_fwd2_kernel(float* __restrict__ gates, const uint8_t* __restrict__ packe
             }
           }
 #endif
-          if (wf.img_flags != nullptr && wq < Bv) {
-            // layer wavefront: this warp's image stores of step t are out -- one release-arrival per (step, quarter, warp)
-            __syncwarp();
-            if (lane == 0) red_release_add_u32(wf.img_flags + (size_t)((w0 + wq) / kRows) * (size_t)T + t, 1u);
-          }
           if (tl0) TL(13, q, t)   // epilogue: quarter's stash stores issued
           TRACE(4)
         }
