@@ -13,7 +13,9 @@ int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const
                      float* terms, const int32_t* step_count, int slots, float* dmel, float* dsv, float* dcp_smooth,
                      float* scratch, int64_t T, int64_t Tm, const int32_t* word_T, int64_t B, int64_t C, int64_t Cm,
                      int64_t S, int objective, paule_stream_t stream, const float* cls_w = nullptr,
-                     const float* cls_b = nullptr, const float* extra_terms = nullptr, float* aux_log = nullptr);
+                     const float* cls_b = nullptr, const float* extra_terms = nullptr, float* aux_log = nullptr, int which = 0);
+// `which`: 0 both kernels; 1 only the smoothness kernel (cp -> dcp_smooth + per-tile partial sums: independent of the models'
+// forward pass, so the planning step runs it beside the forward pipeline); 2 only the per-word loss kernel (needs 1's partials)
 
 // ragged batches (word_T[b] cp frames per word): out[b,:] = seq[word_T[b]/2 - 1, b, :], and its adjoint into a zero-filled
 // [Tm,B,H] sequence

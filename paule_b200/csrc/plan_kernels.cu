@@ -447,16 +447,19 @@ int plan_loss_logged(const float* mel, const float* tmel, const float* sv, const
                      float* terms, const int32_t* step_count, int slots, float* dmel, float* dsv, float* dcp_smooth,
                      float* scratch, int64_t T, int64_t Tm, const int32_t* word_T, int64_t B, int64_t C, int64_t Cm,
                      int64_t S, int objective, paule_stream_t stream, const float* cls_w, const float* cls_b,
-                     const float* extra_terms, float* aux_log) {
+                     const float* extra_terms, float* aux_log, int which) {
   PAULE_REQUIRE(mel && tmel && cp && terms && dmel && dcp_smooth && scratch && slots >= 1);
   PAULE_REQUIRE((sv == nullptr) == (tsv == nullptr));
   PAULE_REQUIRE(T >= 13 && Tm >= 1 && B >= 1 && C >= 1 && C <= kMaxC && Cm >= 1 && S >= 1);
   PAULE_REQUIRE(objective >= 0 && objective <= 2);
   if (objective != PAULE_OBJ_ACOUSTIC) PAULE_REQUIRE(sv && tsv && dsv);
   const int n_tiles = (int)ceil_div(T, (int64_t)kTileT);
-  smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
-                                                                                 n_tiles);
-  PAULE_LAUNCH_CHECK("smooth_terms_kernel");
+  if (which != 2) {
+    smooth_terms_kernel<<<dim3(n_tiles, (unsigned)B), 256, 0, as_stream(stream)>>>(cp, dcp_smooth, scratch, T, word_T, B, C,
+                                                                                   n_tiles);
+    PAULE_LAUNCH_CHECK("smooth_terms_kernel");
+  }
+  if (which == 1) return PAULE_OK;
   word_loss_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(mel, tmel, sv, tsv, scratch, n_tiles, terms,
                                                                step_count, slots, dmel, dsv, T, Tm, word_T, B, C, Cm,
                                                                S, objective, cls_w, cls_b, extra_terms, aux_log);

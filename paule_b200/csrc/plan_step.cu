@@ -331,7 +331,10 @@ int zero_wave_flags(const paule_plan* p, const Workspace& w, cudaStream_t s, boo
   return PAULE_OK;
 }
 
-int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& wp, paule_stream_t stream) {
+// smooth_early: the planning step's smoothness kernel (velocity / jerk / local-linear terms of the cps and their gradient) does
+// not depend on the models' forward pass -- it is launched on the first side stream, in front of the streaming post_linear, and
+// runs beside the start of the pipeline
+int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& wp, paule_stream_t stream, bool smooth_early = false) {
   const int64_t B = p->B, T = p->T, Tm = T / 2, Cm = p->Cm, H = p->H;
   const int P = (int)((Tm + 1) / 2);
   cudaStream_t s = as_stream(stream);
@@ -344,6 +347,10 @@ int forward_wavefront(const paule_plan* p, const Workspace& w, const WavePlan& w
   // (1) forward-model recurrence, T steps, announces every h_t image
   PAULE_TRY(tc::lstm_seq_fwd2x(w.gates_f, p->fwd.packed, p->fwd.bias, w.x_img_f, nullptr, w.c_f, w.xchg, w.hf_img, T, B, s,
                                tc::WaveFlags{w.f_hf, nullptr, 0, 0u}, wp.f_ctas));
+  if (smooth_early)
+    PAULE_TRY(plan_loss_logged(p->pred_mel, p->target_mel, nullptr, nullptr, p->cp, p->loss_log, p->step_count, p->log_slot_count,
+                               w.dmel, w.dsv, w.dcp_smooth, w.partial, T, Tm, p->word_frames, B, p->C, Cm, p->S, PAULE_OBJ_ACOUSTIC,
+                               reinterpret_cast<paule_stream_t>(ss->s[0]), nullptr, nullptr, nullptr, nullptr, 1));
   // (2) pooled post_linear, streaming: pred_mel + operand blocks of embedder layer 0
   PAULE_TRY(tc::gemm_img_stream(w.hf_img, p->post_packed, p->post_b, p->pred_mel, Tm, B, Cm, 2, w.f_hf, w.wf_target, 2, w.f_x0,
                                 w.x_img_0, wp.m_par, status_of(w.xchg), ss->s[0]));
@@ -477,17 +484,22 @@ int embed_models(const paule_plan* p, const Workspace& w, const float* mel, floa
   return embed_top(p, w, sv, s);
 }
 
-int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s) {
+// smooth_done (optional, planning step only): set when the smoothness kernel of the criterion was launched beside the forward pass
+int forward_models(const paule_plan* p, const Workspace& w, bool need_semvec, paule_stream_t s, bool* smooth_done = nullptr) {
   const int64_t B = p->B, T = p->T, H = p->H, Tm = T / 2, Cm = p->Cm;
   if (need_semvec) {
     // batches that leave room for it: the layers of the forward pass as ONE pipeline
     const WavePlan wp = plan_wavefront(p, false);
     if (wp.fwd == 2) {
-      PAULE_TRY(forward_wavefront(p, w, wp, s));
+      // (not in the every-SM-taken plan: measured 1.82 -> 1.96 ms per step at 64 words -- there is no SM left for a bystander)
+      const bool early = smooth_done != nullptr && wp.g1_ct == 1;
+      PAULE_TRY(forward_wavefront(p, w, wp, s, early));
+      if (early) *smooth_done = true;
       return embed_head(p, w, p->pred_sv, s);
     }
     if (wp.fwd == 1) {
-      PAULE_TRY(forward_wavefront(p, w, wp, s));
+      PAULE_TRY(forward_wavefront(p, w, wp, s, smooth_done != nullptr));
+      if (smooth_done) *smooth_done = true;
       return embed_top(p, w, p->pred_sv, s);
     }
   }
@@ -591,11 +603,12 @@ extern "C" int paule_plan_step(const paule_plan* p, paule_stream_t s) {
   const bool need_sv = use_sem || (p->log_semantics && p->target_sv);
 
   PAULE_TRY(paule_step_tick(p->step_count, s));                                   // optimizer step counter
-  PAULE_TRY(forward_models(p, w, need_sv, s));                                    // paule.py:913, :924
+  bool smooth_done = false;
+  PAULE_TRY(forward_models(p, w, need_sv, s, &smooth_done));                      // paule.py:913, :924
   PAULE_TRY(plan_loss_logged(p->pred_mel, p->target_mel, need_sv ? p->pred_sv : nullptr,
                              need_sv ? p->target_sv : nullptr, p->cp, p->loss_log, p->step_count, p->log_slot_count,
                              w.dmel, w.dsv, w.dcp_smooth, w.partial, T, Tm, p->word_frames, B, C, Cm, S, p->objective,
-                             s, p->cls_w, p->cls_b, p->extra_terms, p->aux_log));  // :986
+                             s, p->cls_w, p->cls_b, p->extra_terms, p->aux_log, smooth_done ? 2 : 0));  // :986
   const WavePlan wp = plan_wavefront(p, use_sem);
   if (use_sem && wp.bwd != 0) {                                                    // discrepancy.backward(), :1052, as a pipeline
     PAULE_TRY(paule_linear_f32(w.dsv, p->head_w_t, nullptr, w.dh1_last, B, H, S, 1, S, 0, 0, 1, H, 0, 0, s));   // dh1[Tm-1] = dsv W_head
